@@ -1,0 +1,167 @@
+/* posekf.h -- C ABI of libposekf_b200.so: the B200 (sm_100a) batched quaternion EKF.
+ *
+ * This is the drop-in boundary for the offline replay path of varunbachalli/PoseEstimationKF.
+ * The reference has no FFI layer for this path -- its boundary is the Python import surface used by
+ * `Python Kalman Filter/main_file.py:1-6` -- so every entry point below cites the reference
+ * Python function (file:line, relative to the reference repository; PKF = "Python Kalman Filter",
+ * SRV = "Kalman Filter Server/PoseEstimator") whose arithmetic it replaces for a batch of N
+ * independent filters.  INTEGRATION.md shows the ctypes binding a maintainer of the reference adds.
+ *
+ * Conventions
+ *   - All pointers are DEVICE pointers unless the function name ends in `_host`.
+ *   - Batched arrays are component-major ("structure of arrays"): a per-filter k-vector is stored
+ *     as float[k][N] so that consecutive filters are consecutive in memory (coalesced).
+ *     Matrices are row-major flattened: a 4x4 is float[16][N], entry (i,j) at row 4*i+j.
+ *   - Quaternions are scalar-first [w,x,y,z]  (PKF/ExtendedKalmanFilter.py:17, PKF/Wahba.py:47).
+ *   - Kernels never allocate or free; outputs are caller-allocated.  No global state: every entry
+ *     point is re-entrant.  Launches are asynchronous on `stream` (a cudaStream_t, may be NULL).
+ *   - Return value: 0 = ok; >0 = a cudaError_t; <0 = invalid argument (POSEKF_EINVAL...).
+ *   - NaN/Inf propagate as in the reference (nothing is clamped silently).
+ */
+#ifndef POSEKF_H_
+#define POSEKF_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define POSEKF_EINVAL (-1)      /* bad size / null pointer / bad enum                     */
+#define POSEKF_EALIGN (-2)      /* pointer or stride alignment requirement not met        */
+#define POSEKF_ENODEV (-3)      /* no sm_100 device / driver entry point unavailable      */
+
+/* Wahba solver selection (see DESIGN.md "Wahba stage") */
+#define POSEKF_WAHBA_QR2    0   /* rank-2 SVD: QR of both vector pairs + closed-form 2x2 polar factor */
+#define POSEKF_WAHBA_JACOBI 1   /* B formed as in PKF/Wahba.py:11-13, one-sided Jacobi SVD in registers */
+
+/* Stream staging selection for posekf_replay_f32 */
+#define POSEKF_STAGE_AUTO 0     /* TMA when alignment allows, else LDG */
+#define POSEKF_STAGE_LDG  1     /* coalesced global loads, register prefetch one step ahead */
+#define POSEKF_STAGE_TMA  2     /* cp.async.bulk.tensor (TMA) multi-stage shared-memory ring */
+
+/* Library / build info: returns a static string such as "posekf_b200 0.1 sm_100a". */
+const char* posekf_version(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * Fused replay: T steps of Prediction+Correction for N filters in one launch.
+ * Replaces the loop body of PKF/main_file.py:38-47, i.e. per step and filter
+ *   KalmanFilter.Prediction  PKF/ExtendedKalmanFilter.py:58-68  (GetJacobian_A :43-48,
+ *                            GetJacobian_B :51-56, RungeKutta4 :25-41, inv :65)
+ *   KalmanFilter.Correction  PKF/ExtendedKalmanFilter.py:70-80  (Wahba.getQuarternion
+ *                            PKF/Wahba.py:49-50 -> getRotation :8-17, RotationMatrix2Quart :20-47,
+ *                            Comparator :16-23, norm PKF/UtilityFunctions.py:16-21)
+ * and optionally the accel/mag low-pass of SRV/KalmanFilter.cpp:21-24 (PKF/Test.py:27-33).
+ *
+ *   n_filters   N
+ *   n_steps     T
+ *   streams     [T][9][Ns] : rows 0-2 gyro (rad/s), 3-5 acc, 6-8 mag
+ *   n_streams   Ns: number of distinct input columns; filter n reads column n % Ns.  Ns == N for a
+ *               plain replay; Ns < N (N % Ns == 0) for a Q/R sweep that shares trajectories.
+ *   dt          seconds between samples: one float (dt_per_step = 0) or [T] (dt_per_step = 1).
+ *               (The reference passes integer ns timestamps and differences them,
+ *               PKF/ExtendedKalmanFilter.py:32,62; ns do not fit float32, so the caller differences.)
+ *   acc_ref, mag_ref  [3][Ns] : the log's acc_0 / mag_0 (Wahba reference vectors, PKF/Wahba.py:4-6)
+ *   q_scale, r_scale  [N] : Q = q*I3, R = r*I4 as produced by setQ/setR (PKF/ExtendedKalmanFilter.py:12-15)
+ *   lpf_alpha_acc/mag  low-pass coefficient, < 0 disables the stage
+ *   state_x     [4][N]  in: X before the first step, out: X after the last step
+ *   state_p     [10][N] in/out: upper triangle of P in the order 00 01 02 03 11 12 13 22 23 33
+ *   state_lpf   [6][N]  in/out low-pass state (acc xyz, mag xyz); may be NULL when both alphas < 0
+ *   out_traj    [T][4][N] state after every step, or NULL
+ *   out_flip    [T][N] uint8, 1 where the comparator negated the Wahba quaternion
+ *               (PKF/ExtendedKalmanFilter.py:73-75), or NULL
+ *   wahba_algo  POSEKF_WAHBA_*
+ *   staging     POSEKF_STAGE_*
+ */
+int posekf_replay_f32(int64_t n_filters, int64_t n_steps, const float* streams, int64_t n_streams,
+                      const float* dt, int dt_per_step, const float* acc_ref, const float* mag_ref,
+                      const float* q_scale, const float* r_scale, float lpf_alpha_acc, float lpf_alpha_mag,
+                      float* state_x, float* state_p, float* state_lpf, float* out_traj, uint8_t* out_flip,
+                      int wahba_algo, int staging, void* stream);
+
+/* Same replay with HOST buffers: streams_host [T][9][N] is streamed through the device in time
+ * chunks (double-buffered H2D copies overlapped with the filter kernel, state carried across
+ * chunks on the device), results are copied back.  This is the call an offline-replay user makes.
+ *   out_x_host [4][N], out_p_host [10][N] (may be NULL), out_traj_host [T][4][N] (may be NULL).
+ *   x0_host / p0_host may be NULL (X=[1,0,0,0], P=I4: PKF/main_file.py:23,26).
+ *   chunk_steps  steps per chunk (0 = choose so that one chunk is about 1 GiB).
+ *   device      CUDA device ordinal.
+ * Host buffers should be page-locked (cudaHostAlloc / cudaHostRegister) for full PCIe rate. */
+int posekf_replay_host_f32(int64_t n_filters, int64_t n_steps, const float* streams_host, float dt,
+                           const float* acc_ref_host, const float* mag_ref_host, const float* q_scale_host,
+                           const float* r_scale_host, float lpf_alpha_acc, float lpf_alpha_mag,
+                           const float* x0_host, const float* p0_host, float* out_x_host, float* out_p_host,
+                           float* out_traj_host, int64_t chunk_steps, int wahba_algo, int device);
+
+/* ---------------------------------------------------------------------------------------------
+ * Wahba.getRotation / Wahba.getQuarternion for N (acc, mag) pairs.   PKF/Wahba.py:8-17,49-50
+ *   acc_ref, mag_ref  [3][N], or [3] when ref_shared != 0 (one Wahba object, PKF/Wahba.py:4-6)
+ *   acc, mag    [3][N]
+ *   k_acc,k_mag [N] weights, or NULL: then the scalars k_acc_s / k_mag_s are used, or, when
+ *               weights_from_acc != 0, the reference's k_acc=|acc_z|, k_mag=1-|acc_z|
+ *               (PKF/ExtendedKalmanFilter.py:71)
+ *   out_rot     [9][N] rotation matrix (row-major) or NULL;  out_quat [4][N] or NULL
+ *   jacobi_sweeps  maximum cyclic sweeps for POSEKF_WAHBA_JACOBI (<=0: default 6; the loop exits
+ *               early when every lane of the warp has converged)
+ */
+int posekf_wahba_f32(int64_t n, const float* acc_ref, const float* mag_ref, int ref_shared, const float* acc,
+                     const float* mag, const float* k_acc, const float* k_mag, float k_acc_s, float k_mag_s,
+                     int weights_from_acc, float* out_rot, float* out_quat, int wahba_algo, int jacobi_sweeps,
+                     void* stream);
+
+/* Wahba.RotationMatrix2Quart for N matrices: rot [9][N] -> quat [4][N].   PKF/Wahba.py:20-47 */
+int posekf_rot2quat_f32(int64_t n, const float* rot, float* out_quat, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * KalmanFilter.Prediction for N filters, general matrices.   PKF/ExtendedKalmanFilter.py:58-68
+ *   gyro [3][N]; dt [N] seconds (dt_shared=0) or one float (dt_shared=1); x [4][N]; p [16][N];
+ *   q_mat [9], r_mat [16] shared by all filters; q_scale/r_scale [N] optional per-filter multipliers
+ *   (NULL = 1) so that Q_n = q_scale[n]*q_mat.   Outputs z [4][N], p_out [16][N], k_out [16][N].
+ */
+int posekf_predict_f32(int64_t n, const float* gyro, const float* dt, int dt_shared, const float* x, const float* p,
+                       const float* q_mat, const float* r_mat, const float* q_scale, const float* r_scale,
+                       float* out_z, float* out_p, float* out_k, void* stream);
+
+/* KalmanFilter.Correction for N filters, general P and K.   PKF/ExtendedKalmanFilter.py:70-80
+ *   mag, acc [3][N] (NB the reference's argument order is Mag, Acc); acc_ref/mag_ref as in
+ *   posekf_wahba_f32; z [4][N]; p,k [16][N].  Outputs x [4][N], p_out [16][N], out_flip [N] uint8 or
+ *   NULL, out_meas [4][N] (the sign-fixed Wahba quaternion) or NULL.
+ */
+int posekf_correct_f32(int64_t n, const float* mag, const float* acc, const float* acc_ref, const float* mag_ref,
+                       int ref_shared, const float* z, const float* p, const float* k, float* out_x, float* out_p,
+                       uint8_t* out_flip, float* out_meas, int wahba_algo, void* stream);
+
+/* KalmanFilter.RungeKutta4 (static) for N states: q [4][N], dt seconds, w [3][N] -> out_q [4][N].
+ * PKF/ExtendedKalmanFilter.py:25-41 (the reference's T is in ns and is scaled by 1e-9 at :32). */
+int posekf_rk4_f32(int64_t n, const float* q, const float* dt, int dt_shared, const float* w, float* out_q,
+                   void* stream);
+
+/* GetJacobian_A / GetJacobian_B: w [3][N] -> a [16][N];  q [4][N] -> b [12][N] (4x3 row-major).
+ * PKF/ExtendedKalmanFilter.py:43-48, :51-56.  Either pair may be NULL. */
+int posekf_jacobians_f32(int64_t n, const float* w, float* out_a, const float* q, float* out_b, void* stream);
+
+/* KalmanFilter.Comparator: conj(q1) (x) q2 for N pairs, [4][N] each.  PKF/ExtendedKalmanFilter.py:16-23 */
+int posekf_comparator_f32(int64_t n, const float* q1, const float* q2, float* out, void* stream);
+
+/* Low-pass y <- alpha x + (1-alpha) y along time for N channels-triples.
+ * x [T][3][N] -> out [T][3][N] (may alias x); state [3][N] in/out (start at 0 like
+ * SRV/KalmanFilter.cpp:16-18 / PKF/Test.py:7-9).   SRV/KalmanFilter.cpp:21-24, PKF/Test.py:27-33 */
+int posekf_lowpass_f32(int64_t n, int64_t n_steps, const float* x, float alpha, float* state, float* out,
+                       void* stream);
+
+/* UtilityFunctions.Quart2RPY for N quaternions: q [4][N] -> rpy degrees [3][N] (asin not clamped).
+ * PKF/UtilityFunctions.py:3-14 */
+int posekf_quat2rpy_f32(int64_t n, const float* q, float* out_rpy_deg, void* stream);
+
+/* UtilityFunctions.norm for N vectors of length k: v [k][N] -> out [N].  PKF/UtilityFunctions.py:16-21 */
+int posekf_norm_f32(int64_t n, int k, const float* v, float* out, void* stream);
+
+/* Measurement helper (not in the reference): runs a register-resident FFMA loop on every SM and
+ * returns the achieved FP32 rate in TFLOP/s (2 flop per FFMA) -- the denominator of the FP32
+ * roofline, measured in the same process and at the same clocks as the filter kernel. */
+int posekf_fp32_peak_tflops(int device, double* out_tflops, double* out_ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* POSEKF_H_ */

@@ -1,0 +1,351 @@
+"""Batched (N independent filters) API over torch CUDA tensors.
+
+This is the host-side mirror of the reference's interface for the replay path: the same
+operations as `KalmanFilter.Prediction/Correction`, `Wahba.getRotation/getQuarternion`,
+`RungeKutta4`, ... (`Python Kalman Filter/ExtendedKalmanFilter.py`, `Wahba.py`,
+`UtilityFunctions.py`), for a batch, plus the fused `replay` that runs the loop of
+`Python Kalman Filter/main_file.py:38-47` on the device.  torch is used for device memory and
+streams only; all arithmetic happens in libposekf_b200.so (include/posekf.h).
+
+Layout: batched arrays are component-major `[k, N]` float32 CUDA tensors (filter index fastest);
+IMU streams are `[T, 9, N]` (gyro xyz, acc xyz, mag xyz).  Helpers convert from/to the reference's
+per-filter `[N, k]` / `[N, 4, 4]` shapes.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import torch
+
+from . import _lib
+
+_TRI = [(0, 0), (0, 1), (0, 2), (0, 3), (1, 1), (1, 2), (1, 3), (2, 2), (2, 3), (3, 3)]
+
+
+# ------------------------------------------------------------------------------------------------
+# helpers
+# ------------------------------------------------------------------------------------------------
+def _require_cuda(*tensors):
+    for t in tensors:
+        if t is None:
+            continue
+        if not isinstance(t, torch.Tensor) or not t.is_cuda:
+            raise _lib.PosekfError("poseestimationkf_b200 runs on CUDA tensors only (no CPU fallback)")
+        if t.dtype != torch.float32 and t.dtype != torch.uint8:
+            raise TypeError(f"expected float32 tensors, got {t.dtype}")
+        if not t.is_contiguous():
+            raise ValueError("tensors passed to the batched API must be contiguous")
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def tri_from_full(P: torch.Tensor) -> torch.Tensor:
+    """[N,4,4] covariance -> packed upper triangle [10,N] (order 00 01 02 03 11 12 13 22 23 33)."""
+    return torch.stack([P[:, i, j] for i, j in _TRI]).contiguous()
+
+
+def full_from_tri(p: torch.Tensor) -> torch.Tensor:
+    """[10,N] -> symmetric [N,4,4]."""
+    N = p.shape[1]
+    P = torch.empty((N, 4, 4), dtype=p.dtype, device=p.device)
+    for k, (i, j) in enumerate(_TRI):
+        P[:, i, j] = p[k]
+        P[:, j, i] = p[k]
+    return P
+
+
+def soa(a: torch.Tensor) -> torch.Tensor:
+    """per-filter rows [N,k] (or [N,r,c]) -> component-major [k,N] (or [r*c,N])."""
+    return a.reshape(a.shape[0], -1).t().contiguous()
+
+
+def aos(a: torch.Tensor, *shape) -> torch.Tensor:
+    """component-major [k,N] -> per-filter [N,k] (optionally reshaped to [N,*shape])."""
+    out = a.t().contiguous()
+    return out.reshape(out.shape[0], *shape) if shape else out
+
+
+# ------------------------------------------------------------------------------------------------
+# fused replay
+# ------------------------------------------------------------------------------------------------
+@dataclass
+class ReplayState:
+    """Filter state carried between `replay` calls (time-chunked replay, checkpoint/resume).
+    x [4,N], p [10,N] packed upper triangle of P, lpf [6,N] or None."""
+    x: torch.Tensor
+    p: torch.Tensor
+    lpf: torch.Tensor | None = None
+
+    @staticmethod
+    def initial(n_filters: int, device, with_lpf: bool = False) -> "ReplayState":
+        """X=[1,0,0,0], P=I4 (Python Kalman Filter/main_file.py:23,26); low-pass state 0
+        (Kalman Filter Server/PoseEstimator/KalmanFilter.cpp:16-18)."""
+        x = torch.zeros((4, n_filters), dtype=torch.float32, device=device)
+        x[0] = 1.0
+        p = torch.zeros((10, n_filters), dtype=torch.float32, device=device)
+        p[[0, 4, 7, 9]] = 1.0
+        lpf = torch.zeros((6, n_filters), dtype=torch.float32, device=device) if with_lpf else None
+        return ReplayState(x, p, lpf)
+
+    def covariance(self) -> torch.Tensor:
+        return full_from_tri(self.p)
+
+    def clone(self) -> "ReplayState":
+        return ReplayState(self.x.clone(), self.p.clone(), None if self.lpf is None else self.lpf.clone())
+
+
+def _per_filter(v, n, device):
+    if isinstance(v, torch.Tensor):
+        _require_cuda(v)
+        if v.shape != (n,):
+            raise ValueError(f"per-filter scalar must have shape ({n},), got {tuple(v.shape)}")
+        return v
+    return torch.full((n,), float(v), dtype=torch.float32, device=device)
+
+
+def replay(streams: torch.Tensor, acc_ref: torch.Tensor, mag_ref: torch.Tensor, *, dt, q=1.0, r=0.1,
+           state: ReplayState | None = None, n_filters: int | None = None, lpf_alpha_acc: float | None = None,
+           lpf_alpha_mag: float | None = None, out_traj: torch.Tensor | None = None, store_trajectory: bool = False,
+           store_flips: bool = False, wahba: str = "qr2", staging: str = "auto"):
+    """Run T Prediction+Correction steps for N filters in one kernel launch.
+
+    streams [T,9,Ns]; acc_ref, mag_ref [3,Ns]; dt: float seconds or [T] float32 CUDA tensor;
+    q, r: floats or [N] tensors (Q=q*I3, R=r*I4).  `n_filters` > Ns replays every trajectory
+    N/Ns times (filter n reads column n % Ns) -- the Q/R sweep layout.  `state` is updated in place
+    (created with the reference's initial values when None).  Returns (state, traj [T,4,N] or None,
+    flips [T,N] uint8 or None)."""
+    _require_cuda(streams, acc_ref, mag_ref, out_traj)
+    if streams.dim() != 3 or streams.shape[1] != 9:
+        raise ValueError("streams must be [T, 9, Ns]")
+    T, _, Ns = streams.shape
+    N = Ns if n_filters is None else int(n_filters)
+    if acc_ref.shape != (3, Ns) or mag_ref.shape != (3, Ns):
+        raise ValueError("acc_ref / mag_ref must be [3, Ns]")
+    dev = streams.device
+    use_lpf = lpf_alpha_acc is not None or lpf_alpha_mag is not None
+    if state is None:
+        state = ReplayState.initial(N, dev, with_lpf=use_lpf)
+    if use_lpf and state.lpf is None:
+        state.lpf = torch.zeros((6, N), dtype=torch.float32, device=dev)
+    _require_cuda(state.x, state.p, state.lpf)
+    if state.x.shape != (4, N) or state.p.shape != (10, N):
+        raise ValueError("state has the wrong shape for this batch")
+    if isinstance(dt, torch.Tensor):
+        _require_cuda(dt)
+        if dt.shape != (T,):
+            raise ValueError("dt tensor must be [T]")
+        dt_t, per_step = dt, 1
+    else:
+        dt_t, per_step = torch.full((1,), float(dt), dtype=torch.float32, device=dev), 0
+    q_t, r_t = _per_filter(q, N, dev), _per_filter(r, N, dev)
+    if store_trajectory and out_traj is None:
+        out_traj = torch.empty((T, 4, N), dtype=torch.float32, device=dev)
+    if out_traj is not None and out_traj.shape != (T, 4, N):
+        raise ValueError("out_traj must be [T, 4, N]")
+    flips = torch.empty((T, N), dtype=torch.uint8, device=dev) if store_flips else None
+    with torch.cuda.device(dev):
+        rc = _lib.load().posekf_replay_f32(
+            N, T, _ptr(streams), Ns, _ptr(dt_t), per_step, _ptr(acc_ref), _ptr(mag_ref), _ptr(q_t), _ptr(r_t),
+            -1.0 if lpf_alpha_acc is None else float(lpf_alpha_acc),
+            -1.0 if lpf_alpha_mag is None else float(lpf_alpha_mag),
+            _ptr(state.x), _ptr(state.p), _ptr(state.lpf), _ptr(out_traj), _ptr(flips),
+            _lib.WAHBA[wahba], _lib.STAGING[staging], _stream())
+    _lib.check(rc, "posekf_replay_f32")
+    return state, out_traj, flips
+
+
+def replay_host(streams, acc_ref, mag_ref, *, dt: float, q, r, lpf_alpha_acc=None, lpf_alpha_mag=None,
+                store_trajectory=False, chunk_steps: int = 0, wahba: str = "qr2", device: int = 0):
+    """End-to-end replay from HOST memory (CPU torch tensors, ideally pinned): the stream is pushed
+    through the GPU in double-buffered time chunks and the final state (and optionally the
+    trajectory) is copied back.  streams [T,9,N] float32 CPU; acc_ref/mag_ref [3,N]; q, r [N].
+    Returns (x [4,N], p [10,N], traj [T,4,N] or None) as CPU tensors."""
+    for t in (streams, acc_ref, mag_ref, q, r):
+        if t.is_cuda or t.dtype != torch.float32 or not t.is_contiguous():
+            raise ValueError("replay_host takes contiguous float32 CPU tensors")
+    T, _, N = streams.shape
+    pin = streams.is_pinned()
+    x = torch.empty((4, N), dtype=torch.float32, pin_memory=pin)
+    p = torch.empty((10, N), dtype=torch.float32, pin_memory=pin)
+    traj = torch.empty((T, 4, N), dtype=torch.float32, pin_memory=pin) if store_trajectory else None
+    rc = _lib.load().posekf_replay_host_f32(
+        N, T, _ptr(streams), float(dt), _ptr(acc_ref), _ptr(mag_ref), _ptr(q), _ptr(r),
+        -1.0 if lpf_alpha_acc is None else float(lpf_alpha_acc),
+        -1.0 if lpf_alpha_mag is None else float(lpf_alpha_mag),
+        None, None, _ptr(x), _ptr(p), _ptr(traj), int(chunk_steps), _lib.WAHBA[wahba], int(device))
+    _lib.check(rc, "posekf_replay_host_f32")
+    return x, p, traj
+
+
+# ------------------------------------------------------------------------------------------------
+# stand-alone operators (component-major in / out)
+# ------------------------------------------------------------------------------------------------
+def wahba(acc_ref, mag_ref, acc, mag, *, k_acc=None, k_mag=None, weights_from_acc=False, want_rotation=False,
+          want_quaternion=True, algo: str = "qr2", jacobi_sweeps: int = 0):
+    """Wahba.getRotation / getQuarternion for N pairs.  acc, mag [3,N]; acc_ref, mag_ref [3,N] or
+    [3] (shared); k_acc/k_mag: floats, [N] tensors, or None with weights_from_acc=True for the
+    reference's |acc_z| / 1-|acc_z|.  Returns (R [9,N] or None, q [4,N] or None)."""
+    _require_cuda(acc_ref, mag_ref, acc, mag)
+    N = acc.shape[1]
+    shared = int(acc_ref.dim() == 1)
+    dev = acc.device
+    ka_t = km_t = None
+    ka_s = km_s = 0.0
+    if isinstance(k_acc, torch.Tensor):
+        _require_cuda(k_acc, k_mag)
+        ka_t, km_t = k_acc, k_mag
+    elif not weights_from_acc:
+        if k_acc is None or k_mag is None:
+            raise ValueError("give k_acc/k_mag or weights_from_acc=True")
+        ka_s, km_s = float(k_acc), float(k_mag)
+    R = torch.empty((9, N), dtype=torch.float32, device=dev) if want_rotation else None
+    qt = torch.empty((4, N), dtype=torch.float32, device=dev) if want_quaternion else None
+    with torch.cuda.device(dev):
+        rc = _lib.load().posekf_wahba_f32(N, _ptr(acc_ref), _ptr(mag_ref), shared, _ptr(acc), _ptr(mag), _ptr(ka_t),
+                                          _ptr(km_t), ka_s, km_s, int(weights_from_acc), _ptr(R), _ptr(qt),
+                                          _lib.WAHBA[algo], int(jacobi_sweeps), _stream())
+    _lib.check(rc, "posekf_wahba_f32")
+    return R, qt
+
+
+def rot2quat(rot):
+    """Wahba.RotationMatrix2Quart: rot [9,N] -> [4,N]."""
+    _require_cuda(rot)
+    out = torch.empty((4, rot.shape[1]), dtype=torch.float32, device=rot.device)
+    with torch.cuda.device(rot.device):
+        _lib.check(_lib.load().posekf_rot2quat_f32(rot.shape[1], _ptr(rot), _ptr(out), _stream()), "posekf_rot2quat_f32")
+    return out
+
+
+def predict(gyro, dt, x, p, q_mat, r_mat, q_scale=None, r_scale=None):
+    """KalmanFilter.Prediction: gyro [3,N], dt float or [N] tensor (seconds), x [4,N], p [16,N],
+    q_mat [9], r_mat [16] -> (z [4,N], P [16,N], K [16,N])."""
+    _require_cuda(gyro, x, p, q_mat, r_mat, q_scale, r_scale)
+    N = gyro.shape[1]
+    dev = gyro.device
+    if isinstance(dt, torch.Tensor):
+        _require_cuda(dt)
+        dt_t, shared = dt, 0
+    else:
+        dt_t, shared = torch.full((1,), float(dt), dtype=torch.float32, device=dev), 1
+    z = torch.empty((4, N), dtype=torch.float32, device=dev)
+    po = torch.empty((16, N), dtype=torch.float32, device=dev)
+    ko = torch.empty((16, N), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        rc = _lib.load().posekf_predict_f32(N, _ptr(gyro), _ptr(dt_t), shared, _ptr(x), _ptr(p), _ptr(q_mat),
+                                            _ptr(r_mat), _ptr(q_scale), _ptr(r_scale), _ptr(z), _ptr(po), _ptr(ko),
+                                            _stream())
+    _lib.check(rc, "posekf_predict_f32")
+    return z, po, ko
+
+
+def correct(mag, acc, acc_ref, mag_ref, z, p, k, *, want_flip=False, want_meas=False, algo: str = "qr2"):
+    """KalmanFilter.Correction (NB reference order Mag, Acc): -> (X [4,N], P [16,N], flip [N] u8 or
+    None, y [4,N] or None)."""
+    _require_cuda(mag, acc, acc_ref, mag_ref, z, p, k)
+    N = acc.shape[1]
+    dev = acc.device
+    shared = int(acc_ref.dim() == 1)
+    x = torch.empty((4, N), dtype=torch.float32, device=dev)
+    po = torch.empty((16, N), dtype=torch.float32, device=dev)
+    flip = torch.empty((N,), dtype=torch.uint8, device=dev) if want_flip else None
+    meas = torch.empty((4, N), dtype=torch.float32, device=dev) if want_meas else None
+    with torch.cuda.device(dev):
+        rc = _lib.load().posekf_correct_f32(N, _ptr(mag), _ptr(acc), _ptr(acc_ref), _ptr(mag_ref), shared, _ptr(z),
+                                            _ptr(p), _ptr(k), _ptr(x), _ptr(po), _ptr(flip), _ptr(meas),
+                                            _lib.WAHBA[algo], _stream())
+    _lib.check(rc, "posekf_correct_f32")
+    return x, po, flip, meas
+
+
+def rk4(q, dt, w):
+    """KalmanFilter.RungeKutta4 with dt in SECONDS: q [4,N], w [3,N] -> [4,N]."""
+    _require_cuda(q, w)
+    N = q.shape[1]
+    dev = q.device
+    if isinstance(dt, torch.Tensor):
+        _require_cuda(dt)
+        dt_t, shared = dt, 0
+    else:
+        dt_t, shared = torch.full((1,), float(dt), dtype=torch.float32, device=dev), 1
+    out = torch.empty_like(q)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.load().posekf_rk4_f32(N, _ptr(q), _ptr(dt_t), shared, _ptr(w), _ptr(out), _stream()),
+                   "posekf_rk4_f32")
+    return out
+
+
+def jacobian_a(w):
+    """GetJacobian_A: w [3,N] -> [16,N]."""
+    _require_cuda(w)
+    out = torch.empty((16, w.shape[1]), dtype=torch.float32, device=w.device)
+    with torch.cuda.device(w.device):
+        _lib.check(_lib.load().posekf_jacobians_f32(w.shape[1], _ptr(w), _ptr(out), None, None, _stream()),
+                   "posekf_jacobians_f32")
+    return out
+
+
+def jacobian_b(q):
+    """GetJacobian_B: q [4,N] -> [12,N] (4x3 row-major)."""
+    _require_cuda(q)
+    out = torch.empty((12, q.shape[1]), dtype=torch.float32, device=q.device)
+    with torch.cuda.device(q.device):
+        _lib.check(_lib.load().posekf_jacobians_f32(q.shape[1], None, None, _ptr(q), _ptr(out), _stream()),
+                   "posekf_jacobians_f32")
+    return out
+
+
+def comparator(q1, q2):
+    """KalmanFilter.Comparator: conj(q1) (x) q2, [4,N] each -> [4,N]."""
+    _require_cuda(q1, q2)
+    out = torch.empty_like(q1)
+    with torch.cuda.device(q1.device):
+        _lib.check(_lib.load().posekf_comparator_f32(q1.shape[1], _ptr(q1), _ptr(q2), _ptr(out), _stream()),
+                   "posekf_comparator_f32")
+    return out
+
+
+def lowpass(x, alpha: float, state=None):
+    """y <- alpha x + (1-alpha) y along time: x [T,3,N] -> (y [T,3,N], state [3,N])."""
+    _require_cuda(x, state)
+    T, _, N = x.shape
+    if state is None:
+        state = torch.zeros((3, N), dtype=torch.float32, device=x.device)
+    out = torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.load().posekf_lowpass_f32(N, T, _ptr(x), float(alpha), _ptr(state), _ptr(out), _stream()),
+                   "posekf_lowpass_f32")
+    return out, state
+
+
+def quat2rpy(q):
+    """UtilityFunctions.Quart2RPY: q [4,N] -> degrees [3,N]."""
+    _require_cuda(q)
+    out = torch.empty((3, q.shape[1]), dtype=torch.float32, device=q.device)
+    with torch.cuda.device(q.device):
+        _lib.check(_lib.load().posekf_quat2rpy_f32(q.shape[1], _ptr(q), _ptr(out), _stream()), "posekf_quat2rpy_f32")
+    return out
+
+
+def norm(v):
+    """UtilityFunctions.norm: v [k,N] -> [N]."""
+    _require_cuda(v)
+    out = torch.empty((v.shape[1],), dtype=torch.float32, device=v.device)
+    with torch.cuda.device(v.device):
+        _lib.check(_lib.load().posekf_norm_f32(v.shape[1], v.shape[0], _ptr(v), _ptr(out), _stream()),
+                   "posekf_norm_f32")
+    return out
+
+
+def fp32_peak_tflops(device: int = 0):
+    """Measured FFMA rate of this GPU right now (TFLOP/s, ms of the probe kernel)."""
+    import ctypes as C
+    tf, ms = C.c_double(), C.c_double()
+    _lib.check(_lib.load().posekf_fp32_peak_tflops(int(device), C.byref(tf), C.byref(ms)), "posekf_fp32_peak_tflops")
+    return tf.value, ms.value

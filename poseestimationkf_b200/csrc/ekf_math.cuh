@@ -1,0 +1,555 @@
+// ekf_math.cuh -- per-filter arithmetic of the quaternion EKF step, register resident.
+//
+// Everything here is a __host__ __device__ template over the scalar type F so that the *same*
+// source is (a) instantiated with F=float inside the sm_100a kernels (posekf_kernels.cu) and
+// (b) compiled by g++ with F=float / F=double in tests/hostsim (a CPU-only numerics probe used while
+// developing without a GPU; it is a test tool, never a product path).
+//
+// Reference behaviour being reproduced (file:line relative to the reference repository,
+// PKF = "Python Kalman Filter"):
+//   RK4 of q' = 0.5*Omega(w) q + normalise ........ PKF/ExtendedKalmanFilter.py:25-41
+//   A = 0.5*Omega(w), B(q) ......................... PKF/ExtendedKalmanFilter.py:43-56
+//   P = A P A^T + B Q B^T, S = P + R, K = P S^-1 ... PKF/ExtendedKalmanFilter.py:58-68
+//   Wahba: B = ka r_a b_a^T + km r_m b_m^T, SVD, det fix, R = U M V^T ... PKF/Wahba.py:8-17
+//   rotation matrix -> quaternion (3 branch) ....... PKF/Wahba.py:20-47
+//   q/-q comparator, X = z + K(y - z), P = P - K P, normalise ... PKF/ExtendedKalmanFilter.py:70-80
+//   low-pass y = a x + (1-a) y ..................... PKF/Test.py:27-33 ; C++ twin KalmanFilter.cpp:21-24
+//
+// Algebraic restructurings (exact in real arithmetic; they change rounding only):
+//   * RK4 on a linear constant-coefficient ODE is the degree-4 Taylor polynomial of exp(hA); with
+//     A^2 = -(|w|^2/4) I it collapses to  z = c0 x + c1 (A x).
+//   * With Q = q I3:  B Q B^T = (q/4)(|x|^2 I - x x^T).
+//   * With R = r I4:  K = P S^-1 = I - r S^-1  and  P - K P = r K, so only S^-1 (symmetric) is needed.
+//   * P is kept as its upper triangle (10 values).
+//   * rank(B_wahba) = 2 always (two observations), so the SVD is taken on the 2x2 core of a QR
+//     factorisation of both vector pairs (see wahba_qr2) -- this is also what makes fp32 safe when
+//     the reference's weights ka=|a_z|, km=1-|a_z| drive B towards rank 1.
+#pragma once
+
+#include <math.h>
+
+#if defined(__CUDACC__)
+#define PKF_HD __host__ __device__ __forceinline__
+#else
+#define PKF_HD inline
+#endif
+
+namespace pkf {
+
+// ------------------------------------------------------------------------------------------
+// scalar primitives
+// ------------------------------------------------------------------------------------------
+template <typename F> PKF_HD F fma_(F a, F b, F c) { return a * b + c; }
+template <typename F> PKF_HD F abs_(F a) { return a < F(0) ? -a : a; }
+template <typename F> PKF_HD F sqrt_(F a) { return (F)sqrt((double)a); }
+template <typename F> PKF_HD F rcp_(F a) { return F(1) / a; }
+template <typename F> PKF_HD F rsqrt_(F a) { return F(1) / (F)sqrt((double)a); }
+
+#if defined(__CUDA_ARCH__)
+template <> __device__ __forceinline__ float fma_<float>(float a, float b, float c) { return __fmaf_rn(a, b, c); }
+template <> __device__ __forceinline__ float abs_<float>(float a) { return fabsf(a); }
+template <> __device__ __forceinline__ float sqrt_<float>(float a) { return sqrtf(a); }
+// one MUFU each; ~1 ulp.  (IEEE division/rsqrt sequences cost 6-10 issue slots; the parity budget
+// of 1e-5 rad leaves two orders of magnitude of room for a 1e-7 relative error.)
+template <> __device__ __forceinline__ float rcp_<float>(float a) {
+  float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a)); return r;
+}
+template <> __device__ __forceinline__ float rsqrt_<float>(float a) {
+  float r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a)); return r;
+}
+#else
+template <> inline float fma_<float>(float a, float b, float c) { return fmaf(a, b, c); }
+template <> inline float sqrt_<float>(float a) { return sqrtf(a); }
+template <> inline float rsqrt_<float>(float a) { return 1.0f / sqrtf(a); }
+template <> inline double fma_<double>(double a, double b, double c) { return fma(a, b, c); }
+template <> inline double sqrt_<double>(double a) { return sqrt(a); }
+template <> inline double rsqrt_<double>(double a) { return 1.0 / sqrt(a); }
+#endif
+
+template <typename F> PKF_HD F sel_(bool c, F a, F b) { return c ? a : b; }
+
+// ------------------------------------------------------------------------------------------
+// types
+// ------------------------------------------------------------------------------------------
+template <typename F> struct Vec3 { F x, y, z; };
+template <typename F> struct Quat { F w, x, y, z; };
+
+// symmetric 4x4, upper triangle, row-major order 00 01 02 03 11 12 13 22 23 33
+template <typename F> struct Sym4 { F a00, a01, a02, a03, a11, a12, a13, a22, a23, a33; };
+
+template <typename F> struct Mat3 { F m[3][3]; };
+template <typename F> struct Mat4 { F m[4][4]; };
+
+// Per-filter constants of the Wahba stage derived from the reference vectors (acc_0, mag_0):
+// the right-handed frame E = [e1 e2 e3] from Gram-Schmidt on (r_a, r_m) and the 2x2 triangular
+// factor  [r_a r_m] = [e1 e2] [[s11 s12],[0 s22]].
+template <typename F> struct RefFrame {
+  Vec3<F> e1, e2, e3;
+  F s11, s12, s22;
+};
+
+template <typename F> PKF_HD F dot3(const Vec3<F>& a, const Vec3<F>& b) {
+  return fma_(a.z, b.z, fma_(a.y, b.y, a.x * b.x));
+}
+template <typename F> PKF_HD Vec3<F> cross3(const Vec3<F>& a, const Vec3<F>& b) {
+  Vec3<F> c;
+  c.x = fma_(a.y, b.z, -(a.z * b.y));
+  c.y = fma_(a.z, b.x, -(a.x * b.z));
+  c.z = fma_(a.x, b.y, -(a.y * b.x));
+  return c;
+}
+template <typename F> PKF_HD F dot4(const Quat<F>& a, const Quat<F>& b) {
+  return fma_(a.z, b.z, fma_(a.y, b.y, fma_(a.x, b.x, a.w * b.w)));
+}
+
+// QR (Gram-Schmidt) of the 3x2 matrix [a m]:  [a m] = [f1 f2] [[t11 t12],[0 t22]], f3 = f1 x f2.
+template <typename F> PKF_HD RefFrame<F> frame_from_pair(const Vec3<F>& a, const Vec3<F>& m) {
+  RefFrame<F> fr;
+  F na2 = dot3(a, a);
+  F ia = rsqrt_(na2);
+  fr.e1.x = a.x * ia; fr.e1.y = a.y * ia; fr.e1.z = a.z * ia;
+  fr.s11 = na2 * ia;
+  fr.s12 = dot3(m, fr.e1);
+  Vec3<F> mp;
+  mp.x = fma_(-fr.s12, fr.e1.x, m.x);
+  mp.y = fma_(-fr.s12, fr.e1.y, m.y);
+  mp.z = fma_(-fr.s12, fr.e1.z, m.z);
+  F np2 = dot3(mp, mp);
+  F ip = rsqrt_(np2);
+  fr.e2.x = mp.x * ip; fr.e2.y = mp.y * ip; fr.e2.z = mp.z * ip;
+  fr.s22 = np2 * ip;
+  fr.e3 = cross3(fr.e1, fr.e2);
+  return fr;
+}
+
+// ------------------------------------------------------------------------------------------
+// low-pass  y <- alpha x + (1-alpha) y          (PKF/Test.py:27-33, SRV/KalmanFilter.cpp:21-24)
+// ------------------------------------------------------------------------------------------
+template <typename F> PKF_HD void lowpass(Vec3<F>& y, const Vec3<F>& x, F alpha, F one_minus_alpha) {
+  y.x = fma_(alpha, x.x, one_minus_alpha * y.x);
+  y.y = fma_(alpha, x.y, one_minus_alpha * y.y);
+  y.z = fma_(alpha, x.z, one_minus_alpha * y.z);
+}
+
+// ------------------------------------------------------------------------------------------
+// RK4 step of q' = 0.5*Omega(w) q over h seconds, then normalise.
+//   (PKF/ExtendedKalmanFilter.py:25-41; hw = 0.5*w is passed in because the caller shares it with
+//    the covariance propagation.)
+// k1..k4 of the reference expand to  z = (1 - a2/2 + a2^2/24) q + h (1 - a2/6) (A q),
+// a2 = h^2 |hw|^2, because A^2 = -|hw|^2 I.
+// ------------------------------------------------------------------------------------------
+template <typename F> PKF_HD Quat<F> rk4_step(const Quat<F>& q, const Vec3<F>& hw, F h) {
+  Quat<F> u;   // u = A q
+  u.w = fma_(-hw.z, q.z, fma_(-hw.y, q.y, -(hw.x * q.x)));
+  u.x = fma_(-hw.y, q.z, fma_(hw.z, q.y, hw.x * q.w));
+  u.y = fma_(hw.x, q.z, fma_(-hw.z, q.x, hw.y * q.w));
+  u.z = fma_(-hw.x, q.y, fma_(hw.y, q.x, hw.z * q.w));
+  F a2 = (h * h) * dot3(hw, hw);
+  F c0 = fma_(a2, fma_(a2, F(1.0 / 24.0), F(-0.5)), F(1));
+  F c1 = h * fma_(a2, F(-1.0 / 6.0), F(1));
+  Quat<F> z;
+  z.w = fma_(c1, u.w, c0 * q.w);
+  z.x = fma_(c1, u.x, c0 * q.x);
+  z.y = fma_(c1, u.y, c0 * q.y);
+  z.z = fma_(c1, u.z, c0 * q.z);
+  F r = rsqrt_(dot4(z, z));
+  z.w *= r; z.x *= r; z.y *= r; z.z *= r;
+  return z;
+}
+
+// ------------------------------------------------------------------------------------------
+// Covariance propagation  P <- A P A^T + B(x) (q I3) B(x)^T,  A = 0.5*Omega(w)  (hw = 0.5 w),
+// x = state BEFORE the RK4 step.        (PKF/ExtendedKalmanFilter.py:59-61)
+//   B B^T = 0.25 (|x|^2 I - x x^T)  =>  second term = qq (|x|^2 I - x x^T), qq = q/4.
+// ------------------------------------------------------------------------------------------
+template <typename F>
+PKF_HD Sym4<F> propagate_cov(const Sym4<F>& P, const Vec3<F>& hw, const Quat<F>& x, F qq) {
+  const F X = hw.x, Y = hw.y, Z = hw.z;
+  // M = A P (full 4x4; P symmetric so P[k][j] is read from the upper triangle)
+  // rows of A: [0,-X,-Y,-Z], [X,0,Z,-Y], [Y,-Z,0,X], [Z,Y,-X,0]
+  const F p00 = P.a00, p01 = P.a01, p02 = P.a02, p03 = P.a03, p11 = P.a11, p12 = P.a12, p13 = P.a13,
+          p22 = P.a22, p23 = P.a23, p33 = P.a33;
+  F m00 = fma_(-Z, p03, fma_(-Y, p02, -(X * p01)));
+  F m01 = fma_(-Z, p13, fma_(-Y, p12, -(X * p11)));
+  F m02 = fma_(-Z, p23, fma_(-Y, p22, -(X * p12)));
+  F m03 = fma_(-Z, p33, fma_(-Y, p23, -(X * p13)));
+  F m10 = fma_(-Y, p03, fma_(Z, p02, X * p00));
+  F m11 = fma_(-Y, p13, fma_(Z, p12, X * p01));
+  F m12 = fma_(-Y, p23, fma_(Z, p22, X * p02));
+  F m13 = fma_(-Y, p33, fma_(Z, p23, X * p03));
+  F m20 = fma_(X, p03, fma_(-Z, p01, Y * p00));
+  F m21 = fma_(X, p13, fma_(-Z, p11, Y * p01));
+  F m22 = fma_(X, p23, fma_(-Z, p12, Y * p02));
+  F m23 = fma_(X, p33, fma_(-Z, p13, Y * p03));
+  F m30 = fma_(-X, p02, fma_(Y, p01, Z * p00));
+  F m31 = fma_(-X, p12, fma_(Y, p11, Z * p01));
+  F m32 = fma_(-X, p22, fma_(Y, p12, Z * p02));
+  F m33 = fma_(-X, p23, fma_(Y, p13, Z * p03));
+  // process-noise term, used as the start value of the N = M A^T accumulation chains
+  F yw = qq * x.w, yx = qq * x.x, yy = qq * x.y, yz = qq * x.z;
+  F s = fma_(yz, x.z, fma_(yy, x.y, fma_(yx, x.x, yw * x.w)));   // qq |x|^2
+  Sym4<F> N;
+  // N[i][j] = sum_k M[i][k] A[j][k]
+  //  j=0: -X M[i][1] - Y M[i][2] - Z M[i][3]     j=1:  X M[i][0] + Z M[i][2] - Y M[i][3]
+  //  j=2:  Y M[i][0] - Z M[i][1] + X M[i][3]     j=3:  Z M[i][0] + Y M[i][1] - X M[i][2]
+  N.a00 = fma_(-Z, m03, fma_(-Y, m02, fma_(-X, m01, fma_(-yw, x.w, s))));
+  N.a01 = fma_(-Y, m03, fma_(Z, m02, fma_(X, m00, -(yw * x.x))));
+  N.a02 = fma_(X, m03, fma_(-Z, m01, fma_(Y, m00, -(yw * x.y))));
+  N.a03 = fma_(-X, m02, fma_(Y, m01, fma_(Z, m00, -(yw * x.z))));
+  N.a11 = fma_(-Y, m13, fma_(Z, m12, fma_(X, m10, fma_(-yx, x.x, s))));
+  N.a12 = fma_(X, m13, fma_(-Z, m11, fma_(Y, m10, -(yx * x.y))));
+  N.a13 = fma_(-X, m12, fma_(Y, m11, fma_(Z, m10, -(yx * x.z))));
+  N.a22 = fma_(X, m23, fma_(-Z, m21, fma_(Y, m20, fma_(-yy, x.y, s))));
+  N.a23 = fma_(-X, m22, fma_(Y, m21, fma_(Z, m20, -(yy * x.z))));
+  N.a33 = fma_(-X, m32, fma_(Y, m31, fma_(Z, m30, fma_(-yz, x.z, s))));
+  return N;
+}
+
+// ------------------------------------------------------------------------------------------
+// Inverse of the symmetric positive-definite S = P + r I by LDL^T.  (replaces np.linalg.inv,
+// PKF/ExtendedKalmanFilter.py:63-65)
+// ------------------------------------------------------------------------------------------
+template <typename F> PKF_HD Sym4<F> spd_inverse_plus_diag(const Sym4<F>& P, F r) {
+  const F s00 = P.a00 + r, s11 = P.a11 + r, s22 = P.a22 + r, s33 = P.a33 + r;
+  const F s01 = P.a01, s02 = P.a02, s03 = P.a03, s12 = P.a12, s13 = P.a13, s23 = P.a23;
+  F i0 = rcp_(s00);
+  F l10 = s01 * i0, l20 = s02 * i0, l30 = s03 * i0;
+  F d1 = fma_(-l10, s01, s11);
+  F i1 = rcp_(d1);
+  F t21 = fma_(-l10, s02, s12);
+  F t31 = fma_(-l10, s03, s13);
+  F l21 = t21 * i1, l31 = t31 * i1;
+  F d2 = fma_(-l21, t21, fma_(-l20, s02, s22));
+  F i2 = rcp_(d2);
+  F t32 = fma_(-l21, t31, fma_(-l20, s03, s23));
+  F l32 = t32 * i2;
+  F d3 = fma_(-l32, t32, fma_(-l31, t31, fma_(-l30, s03, s33)));
+  F i3 = rcp_(d3);
+  // W = L^-1 (unit lower): w10=-l10, w21=-l21, w32=-l32, w20 = -l20 + l21 l10, ...
+  F w10 = -l10, w21 = -l21, w32 = -l32;
+  F w20 = fma_(-l21, w10, -l20);
+  F w31 = fma_(-l32, w21, -l31);
+  F w30 = fma_(-l32, w20, fma_(-l31, w10, -l30));
+  // S^-1 = W^T D^-1 W
+  F v30 = i3 * w30, v31 = i3 * w31, v32 = i3 * w32;
+  F v20 = i2 * w20, v21 = i2 * w21;
+  F v10 = i1 * w10;
+  Sym4<F> I;
+  I.a00 = fma_(w30, v30, fma_(w20, v20, fma_(w10, v10, i0)));
+  I.a01 = fma_(w30, v31, fma_(w20, v21, v10));
+  I.a02 = fma_(w30, v32, v20);
+  I.a03 = v30;
+  I.a11 = fma_(w31, v31, fma_(w21, v21, i1));
+  I.a12 = fma_(w31, v32, v21);
+  I.a13 = v31;
+  I.a22 = fma_(w32, v32, i2);
+  I.a23 = v32;
+  I.a33 = i3;
+  return I;
+}
+
+// ------------------------------------------------------------------------------------------
+// Wahba, rank-2 form.   B = ka r_a a^T + km r_m m^T = [e1 e2] C [f1 f2]^T  with
+//   C = [[s11 s12],[0 s22]] diag(ka,km) [[t11 0],[t12 t22]]   (2x2).
+// SVD of C = Uc S Vc^T  =>  U = [E2 Uc, e3], V = [F2 Vc, f3] and the reference's
+//   R = U diag(1,1,det U det V^T) V^T = E blockdiag(Uc Vc^T, det(Uc Vc^T)) F^T   (PKF/Wahba.py:14-16).
+// Uc Vc^T is the orthogonal polar factor of C, closed form for 2x2:
+//   sg = sign(det C) = sign(ka km)  (all other factors of det C are norms),
+//   p = c00 + sg c11, r = c10 - sg c01,  Uc Vc^T = [[p, -sg r],[r, sg p]] / hypot(p,r).
+// rank(C) < 2 (ka km == 0, or a || m, or r_a || r_m) is the case where LAPACK's null-space choice
+// decides the reference's answer ("parity unpinned"); here it yields the
+// limit of the rank-2 formula (or NaN if a vector is zero).
+// ------------------------------------------------------------------------------------------
+template <typename F>
+PKF_HD Mat3<F> wahba_qr2(const RefFrame<F>& E, const Vec3<F>& a, const Vec3<F>& m, F ka, F km) {
+  RefFrame<F> Fb = frame_from_pair(a, m);
+  F g = km * Fb.s12, hh = km * Fb.s22;
+  F c00 = fma_(E.s12, g, (E.s11 * ka) * Fb.s11);
+  F c01 = E.s12 * hh;
+  F c10 = E.s22 * g;
+  F c11 = E.s22 * hh;
+  bool neg = (ka * km) < F(0);
+  F sc11 = sel_(neg, -c11, c11), sc01 = sel_(neg, -c01, c01);
+  F p = c00 + sc11;
+  F r = c10 - sc01;
+  F inv = rsqrt_(fma_(p, p, r * r));
+  F cs = p * inv, sn = r * inv;
+  // W = E * blockdiag([[cs, -sg sn],[sn, sg cs]], sg)
+  F scs = sel_(neg, -cs, cs), ssn = sel_(neg, -sn, sn);
+  Vec3<F> w1, w2, w3;
+  w1.x = fma_(sn, E.e2.x, cs * E.e1.x); w1.y = fma_(sn, E.e2.y, cs * E.e1.y); w1.z = fma_(sn, E.e2.z, cs * E.e1.z);
+  w2.x = fma_(scs, E.e2.x, -(ssn * E.e1.x)); w2.y = fma_(scs, E.e2.y, -(ssn * E.e1.y)); w2.z = fma_(scs, E.e2.z, -(ssn * E.e1.z));
+  w3.x = sel_(neg, -E.e3.x, E.e3.x); w3.y = sel_(neg, -E.e3.y, E.e3.y); w3.z = sel_(neg, -E.e3.z, E.e3.z);
+  Mat3<F> R;
+  const Vec3<F>&f1 = Fb.e1, &f2 = Fb.e2, &f3 = Fb.e3;
+  R.m[0][0] = fma_(w3.x, f3.x, fma_(w2.x, f2.x, w1.x * f1.x));
+  R.m[0][1] = fma_(w3.x, f3.y, fma_(w2.x, f2.y, w1.x * f1.y));
+  R.m[0][2] = fma_(w3.x, f3.z, fma_(w2.x, f2.z, w1.x * f1.z));
+  R.m[1][0] = fma_(w3.y, f3.x, fma_(w2.y, f2.x, w1.y * f1.x));
+  R.m[1][1] = fma_(w3.y, f3.y, fma_(w2.y, f2.y, w1.y * f1.y));
+  R.m[1][2] = fma_(w3.y, f3.z, fma_(w2.y, f2.z, w1.y * f1.z));
+  R.m[2][0] = fma_(w3.z, f3.x, fma_(w2.z, f2.x, w1.z * f1.x));
+  R.m[2][1] = fma_(w3.z, f3.y, fma_(w2.z, f2.y, w1.z * f1.y));
+  R.m[2][2] = fma_(w3.z, f3.z, fma_(w2.z, f2.z, w1.z * f1.z));
+  return R;
+}
+
+// ------------------------------------------------------------------------------------------
+// Wahba, general form: B formed as the reference forms it, then a one-sided (Hestenes) Jacobi SVD
+// of the 3x3 in registers.  G <- B J1 J2 ... (columns made orthogonal), V <- J1 J2 ...;
+// singular values are the column norms.  With (u1,v1),(u2,v2) the two dominant pairs,
+//   U diag(1,1,det U det V) V^T = u1 v1^T + u2 v2^T + (u1 x u2)(v1 x v2)^T
+// holds for ANY orthogonal completion, so the third pair is never needed (PKF/Wahba.py:14-16).
+// `sweeps` cyclic sweeps over (0,1),(0,2),(1,2).
+// ------------------------------------------------------------------------------------------
+template <typename F> PKF_HD void jacobi_pair(Vec3<F>& gi, Vec3<F>& gj, Vec3<F>& vi, Vec3<F>& vj) {
+  F al = dot3(gi, gi), be = dot3(gj, gj), ga = dot3(gi, gj);
+  // tangent of the rotation that zeroes gi.gj:  t = sgn(d) 2 ga / (|d| + sqrt(d^2 + 4 ga^2)), d = be - al
+  F d = be - al;
+  F g2 = ga + ga;
+  F hyp = sqrt_(fma_(d, d, g2 * g2));
+  F den = abs_(d) + hyp;
+  F t = sel_(den > F(0), sel_(d < F(0), -g2, g2) * rcp_(den), F(0));
+  F c = rsqrt_(fma_(t, t, F(1)));
+  F s = c * t;
+  Vec3<F> ni, nj;
+  ni.x = fma_(-s, gj.x, c * gi.x); nj.x = fma_(s, gi.x, c * gj.x);
+  ni.y = fma_(-s, gj.y, c * gi.y); nj.y = fma_(s, gi.y, c * gj.y);
+  ni.z = fma_(-s, gj.z, c * gi.z); nj.z = fma_(s, gi.z, c * gj.z);
+  gi = ni; gj = nj;
+  ni.x = fma_(-s, vj.x, c * vi.x); nj.x = fma_(s, vi.x, c * vj.x);
+  ni.y = fma_(-s, vj.y, c * vi.y); nj.y = fma_(s, vi.y, c * vj.y);
+  ni.z = fma_(-s, vj.z, c * vi.z); nj.z = fma_(s, vi.z, c * vj.z);
+  vi = ni; vj = nj;
+}
+
+template <typename F> PKF_HD void swap_if(bool c, Vec3<F>& a, Vec3<F>& b) {
+  Vec3<F> t = a;
+  a.x = sel_(c, b.x, a.x); a.y = sel_(c, b.y, a.y); a.z = sel_(c, b.z, a.z);
+  b.x = sel_(c, t.x, b.x); b.y = sel_(c, t.y, b.y); b.z = sel_(c, t.z, b.z);
+}
+
+// Off-diagonal measure used by the stand-alone kernel's warp-voted early exit.
+template <typename F> PKF_HD F jacobi_offdiag(const Vec3<F>& g0, const Vec3<F>& g1, const Vec3<F>& g2) {
+  F a = abs_(dot3(g0, g1)), b = abs_(dot3(g0, g2)), c = abs_(dot3(g1, g2));
+  F m = a > b ? a : b;
+  return m > c ? m : c;
+}
+
+template <typename F>
+PKF_HD Mat3<F> rotation_from_svd_pairs(Vec3<F> g0, Vec3<F> g1, Vec3<F> g2, Vec3<F> v0, Vec3<F> v1, Vec3<F> v2) {
+  // bring the two largest columns to slots 0,1 (order among them is irrelevant)
+  F n0 = dot3(g0, g0), n1 = dot3(g1, g1), n2 = dot3(g2, g2);
+  bool s0 = (n0 < n1) && (n0 < n2);          // column 0 is the smallest -> swap with 2
+  bool s1 = !s0 && (n1 < n2);                // column 1 is the smallest -> swap with 2
+  swap_if(s0, g0, g2); swap_if(s0, v0, v2);
+  F t = n0; n0 = sel_(s0, n2, n0); n2 = sel_(s0, t, n2);
+  swap_if(s1, g1, g2); swap_if(s1, v1, v2);
+  t = n1; n1 = sel_(s1, n2, n1);
+  F i0 = rsqrt_(n0), i1 = rsqrt_(n1);
+  Vec3<F> u0, u1;
+  u0.x = g0.x * i0; u0.y = g0.y * i0; u0.z = g0.z * i0;
+  u1.x = g1.x * i1; u1.y = g1.y * i1; u1.z = g1.z * i1;
+  Vec3<F> u2 = cross3(u0, u1), w2 = cross3(v0, v1);
+  Mat3<F> R;
+  const F ux[3] = {u0.x, u0.y, u0.z}, uy[3] = {u1.x, u1.y, u1.z}, uz[3] = {u2.x, u2.y, u2.z};
+  const F vx[3] = {v0.x, v0.y, v0.z}, vy[3] = {v1.x, v1.y, v1.z}, vz[3] = {w2.x, w2.y, w2.z};
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int i = 0; i < 3; ++i) {
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int j = 0; j < 3; ++j) R.m[i][j] = fma_(uz[i], vz[j], fma_(uy[i], vy[j], ux[i] * vx[j]));
+  }
+  return R;
+}
+
+template <typename F>
+PKF_HD void wahba_form_b(const Vec3<F>& ra, const Vec3<F>& rm, const Vec3<F>& a, const Vec3<F>& m, F ka, F km,
+                         Vec3<F>& g0, Vec3<F>& g1, Vec3<F>& g2) {
+  // B[i][j] = ka ra[i] a[j] + km rm[i] m[j]; g_j = column j        (PKF/Wahba.py:11-13)
+  F kax = ka * a.x, kay = ka * a.y, kaz = ka * a.z, kmx = km * m.x, kmy = km * m.y, kmz = km * m.z;
+  g0.x = fma_(rm.x, kmx, ra.x * kax); g0.y = fma_(rm.y, kmx, ra.y * kax); g0.z = fma_(rm.z, kmx, ra.z * kax);
+  g1.x = fma_(rm.x, kmy, ra.x * kay); g1.y = fma_(rm.y, kmy, ra.y * kay); g1.z = fma_(rm.z, kmy, ra.z * kay);
+  g2.x = fma_(rm.x, kmz, ra.x * kaz); g2.y = fma_(rm.y, kmz, ra.y * kaz); g2.z = fma_(rm.z, kmz, ra.z * kaz);
+}
+
+template <typename F>
+PKF_HD Mat3<F> wahba_jacobi(const Vec3<F>& ra, const Vec3<F>& rm, const Vec3<F>& a, const Vec3<F>& m, F ka, F km,
+                            int sweeps) {
+  Vec3<F> g0, g1, g2;
+  wahba_form_b(ra, rm, a, m, ka, km, g0, g1, g2);
+  Vec3<F> v0 = {F(1), F(0), F(0)}, v1 = {F(0), F(1), F(0)}, v2 = {F(0), F(0), F(1)};
+  for (int s = 0; s < sweeps; ++s) {
+    jacobi_pair(g0, g1, v0, v1);
+    jacobi_pair(g0, g2, v0, v2);
+    jacobi_pair(g1, g2, v1, v2);
+  }
+  return rotation_from_svd_pairs(g0, g1, g2, v0, v1, v2);
+}
+
+// ------------------------------------------------------------------------------------------
+// Rotation matrix -> quaternion.                                    (PKF/Wahba.py:20-47)
+// The reference picks branch i in {x,y,z} by the strict maximum of tr1,tr2,tr3 (ties -> z) and
+// returns the quaternion whose component i is >= 0; it has no "w largest" branch, so close to the
+// identity its formula divides by a vanishing S (harmless in float64, not in float32).  Here the
+// components come from the best conditioned of the four Shepperd candidates, then the reference's
+// SIGN convention is applied from its own branch rule, so the value equals the reference's output
+// up to rounding.  At M == I exactly the reference returns [nan,nan,nan,0]; so does this.
+// `q` is returned with the reference sign; it is normalised (the reference's is unit to rounding
+// when M is a rotation).
+// ------------------------------------------------------------------------------------------
+template <typename F> PKF_HD Quat<F> rotation_to_quat_ref(const Mat3<F>& M) {
+  const F r00 = M.m[0][0], r11 = M.m[1][1], r22 = M.m[2][2];
+  // the reference's three traces, evaluated in the reference's order of operations
+  F tr1 = F(1) + r00 - r11 - r22;
+  F tr2 = F(1) - r00 + r11 - r22;
+  F tr3 = F(1) - r00 - r11 + r22;
+  F tr0 = F(1) + r00 + r11 + r22;
+  F dx = M.m[2][1] - M.m[1][2], dy = M.m[0][2] - M.m[2][0], dz = M.m[1][0] - M.m[0][1];
+  F sxy = M.m[0][1] + M.m[1][0], sxz = M.m[0][2] + M.m[2][0], syz = M.m[1][2] + M.m[2][1];
+  // reference branch (sign convention): 1 -> x, 2 -> y, else z
+  bool b1 = (tr1 > tr2) && (tr1 > tr3);
+  bool b2 = !b1 && (tr2 > tr1) && (tr2 > tr3);
+  // best-conditioned candidate among (w,x,y,z): the largest of the four traces (independent of the
+  // reference's tie rule, which only fixes the sign)
+  F mwx = tr0 > tr1 ? tr0 : tr1, myz = tr2 > tr3 ? tr2 : tr3;
+  bool lo = mwx > myz;                           // winner is w or x, else y or z
+  bool kw = lo && (tr0 > tr1), kx = lo && !(tr0 > tr1), ky = !lo && (tr2 > tr3);
+  Quat<F> c;
+  c.w = sel_(kw, tr0, sel_(kx, dx, sel_(ky, dy, dz)));
+  c.x = sel_(kw, dx, sel_(kx, tr1, sel_(ky, sxy, sxz)));
+  c.y = sel_(kw, dy, sel_(kx, sxy, sel_(ky, tr2, syz)));
+  c.z = sel_(kw, dz, sel_(kx, sxz, sel_(ky, syz, tr3)));
+  F inv = rsqrt_(dot4(c, c));
+  // sign: the reference's component i (= 0.25 S) is positive
+  F ci = sel_(b1, c.x, sel_(b2, c.y, c.z));
+  inv = sel_(ci < F(0), -inv, inv);
+  Quat<F> q;
+  q.w = c.w * inv; q.x = c.x * inv; q.y = c.y * inv; q.z = c.z * inv;
+  // exact identity: S = 0 in the reference's last branch -> 0/0, 0/0, 0/0, 0.25*0
+  bool ident = (tr1 == F(0)) && (tr2 == F(0)) && (tr3 == F(0)) && (dx == F(0)) && (dy == F(0)) && (dz == F(0));
+  F nanv = (F)NAN;
+  q.w = sel_(ident, nanv, q.w); q.x = sel_(ident, nanv, q.x); q.y = sel_(ident, nanv, q.y); q.z = sel_(ident, F(0), q.z);
+  return q;
+}
+
+// ------------------------------------------------------------------------------------------
+// One fused filter step (Prediction + Correction, PKF/main_file.py:39,43), scalar Q and R.
+// ------------------------------------------------------------------------------------------
+enum WahbaAlgo { WAHBA_QR2 = 0, WAHBA_JACOBI = 1 };
+constexpr int kJacobiSweepsFused = 4;
+
+template <typename F> struct FilterConst {
+  RefFrame<F> E;          // from (acc_0, mag_0)
+  Vec3<F> ra, rm;         // raw reference vectors (used by the Jacobi variant only)
+  F qq;                   // Q/4
+  F r;                    // R
+};
+
+template <typename F, int ALGO>
+PKF_HD void ekf_step(Quat<F>& x, Sym4<F>& P, const FilterConst<F>& fc, const Vec3<F>& gyro, const Vec3<F>& acc,
+                     const Vec3<F>& mag, F h, bool& flip) {
+  Vec3<F> hw;
+  hw.x = F(0.5) * gyro.x; hw.y = F(0.5) * gyro.y; hw.z = F(0.5) * gyro.z;
+  // ---- Prediction (PKF/ExtendedKalmanFilter.py:58-68) ----
+  Sym4<F> Pp = propagate_cov(P, hw, x, fc.qq);
+  Quat<F> z = rk4_step(x, hw, h);
+  Sym4<F> Si = spd_inverse_plus_diag(Pp, fc.r);
+  // ---- Correction (PKF/ExtendedKalmanFilter.py:70-80) ----
+  F ka = abs_(acc.z), km = F(1) - ka;                                         // :71
+  Mat3<F> Rm = (ALGO == WAHBA_QR2) ? wahba_qr2(fc.E, acc, mag, ka, km)
+                                   : wahba_jacobi(fc.ra, fc.rm, acc, mag, ka, km, kJacobiSweepsFused);
+  Quat<F> y = rotation_to_quat_ref(Rm);
+  flip = dot4(y, z) < F(0);                                                   // :73-74
+  y.w = sel_(flip, -y.w, y.w); y.x = sel_(flip, -y.x, y.x); y.y = sel_(flip, -y.y, y.y); y.z = sel_(flip, -y.z, y.z);
+  // X = z + K (y - z),  K = I - r S^-1   =>  X = y - r S^-1 (y - z)            :76-77
+  F e0 = y.w - z.w, e1 = y.x - z.x, e2 = y.y - z.y, e3 = y.z - z.z;
+  F u0 = fma_(Si.a03, e3, fma_(Si.a02, e2, fma_(Si.a01, e1, Si.a00 * e0)));
+  F u1 = fma_(Si.a13, e3, fma_(Si.a12, e2, fma_(Si.a11, e1, Si.a01 * e0)));
+  F u2 = fma_(Si.a23, e3, fma_(Si.a22, e2, fma_(Si.a12, e1, Si.a02 * e0)));
+  F u3 = fma_(Si.a33, e3, fma_(Si.a23, e2, fma_(Si.a13, e1, Si.a03 * e0)));
+  const F r = fc.r;
+  Quat<F> xn;
+  xn.w = fma_(-r, u0, y.w); xn.x = fma_(-r, u1, y.x); xn.y = fma_(-r, u2, y.y); xn.z = fma_(-r, u3, y.z);
+  F inv = rsqrt_(dot4(xn, xn));                                               // :79
+  x.w = xn.w * inv; x.x = xn.x * inv; x.y = xn.y * inv; x.z = xn.z * inv;
+  // P = P - K P = r K = r I - r^2 S^-1                                       :78
+  const F mr2 = -(r * r);
+  P.a00 = fma_(mr2, Si.a00, r); P.a01 = mr2 * Si.a01; P.a02 = mr2 * Si.a02; P.a03 = mr2 * Si.a03;
+  P.a11 = fma_(mr2, Si.a11, r); P.a12 = mr2 * Si.a12; P.a13 = mr2 * Si.a13;
+  P.a22 = fma_(mr2, Si.a22, r); P.a23 = mr2 * Si.a23;
+  P.a33 = fma_(mr2, Si.a33, r);
+}
+
+template <typename F>
+PKF_HD FilterConst<F> make_filter_const(const Vec3<F>& acc_ref, const Vec3<F>& mag_ref, F q, F r) {
+  FilterConst<F> fc;
+  fc.E = frame_from_pair(acc_ref, mag_ref);
+  fc.ra = acc_ref; fc.rm = mag_ref;
+  fc.qq = F(0.25) * q;
+  fc.r = r;
+  return fc;
+}
+
+// ------------------------------------------------------------------------------------------
+// General (full-matrix) forms used by the stand-alone Prediction / Correction entry points, which
+// must accept whatever the reference accepts: any 4x4 P and K, any 3x3 Q and 4x4 R.
+// ------------------------------------------------------------------------------------------
+template <typename F> PKF_HD void half_omega(const Vec3<F>& w, Mat4<F>& A) {   // PKF/ExtendedKalmanFilter.py:43-48
+  F X = F(0.5) * w.x, Y = F(0.5) * w.y, Z = F(0.5) * w.z;
+  A.m[0][0] = F(0); A.m[0][1] = -X; A.m[0][2] = -Y; A.m[0][3] = -Z;
+  A.m[1][0] = X; A.m[1][1] = F(0); A.m[1][2] = Z; A.m[1][3] = -Y;
+  A.m[2][0] = Y; A.m[2][1] = -Z; A.m[2][2] = F(0); A.m[2][3] = X;
+  A.m[3][0] = Z; A.m[3][1] = Y; A.m[3][2] = -X; A.m[3][3] = F(0);
+}
+
+// general 4x4 inverse by 2x2 sub-determinants (Laplace expansion); no pivoting needed for S = P + R
+template <typename F> PKF_HD void inverse4(const Mat4<F>& Min, Mat4<F>& Out) {
+  const F(*a)[4] = Min.m;
+  F s0 = a[0][0] * a[1][1] - a[1][0] * a[0][1];
+  F s1 = a[0][0] * a[1][2] - a[1][0] * a[0][2];
+  F s2 = a[0][0] * a[1][3] - a[1][0] * a[0][3];
+  F s3 = a[0][1] * a[1][2] - a[1][1] * a[0][2];
+  F s4 = a[0][1] * a[1][3] - a[1][1] * a[0][3];
+  F s5 = a[0][2] * a[1][3] - a[1][2] * a[0][3];
+  F c5 = a[2][2] * a[3][3] - a[3][2] * a[2][3];
+  F c4 = a[2][1] * a[3][3] - a[3][1] * a[2][3];
+  F c3 = a[2][1] * a[3][2] - a[3][1] * a[2][2];
+  F c2 = a[2][0] * a[3][3] - a[3][0] * a[2][3];
+  F c1 = a[2][0] * a[3][2] - a[3][0] * a[2][2];
+  F c0 = a[2][0] * a[3][1] - a[3][0] * a[2][1];
+  F det = s0 * c5 - s1 * c4 + s2 * c3 + s3 * c2 - s4 * c1 + s5 * c0;
+  F id = F(1) / det;
+  F(*b)[4] = Out.m;
+  b[0][0] = (a[1][1] * c5 - a[1][2] * c4 + a[1][3] * c3) * id;
+  b[0][1] = (-a[0][1] * c5 + a[0][2] * c4 - a[0][3] * c3) * id;
+  b[0][2] = (a[3][1] * s5 - a[3][2] * s4 + a[3][3] * s3) * id;
+  b[0][3] = (-a[2][1] * s5 + a[2][2] * s4 - a[2][3] * s3) * id;
+  b[1][0] = (-a[1][0] * c5 + a[1][2] * c2 - a[1][3] * c1) * id;
+  b[1][1] = (a[0][0] * c5 - a[0][2] * c2 + a[0][3] * c1) * id;
+  b[1][2] = (-a[3][0] * s5 + a[3][2] * s2 - a[3][3] * s1) * id;
+  b[1][3] = (a[2][0] * s5 - a[2][2] * s2 + a[2][3] * s1) * id;
+  b[2][0] = (a[1][0] * c4 - a[1][1] * c2 + a[1][3] * c0) * id;
+  b[2][1] = (-a[0][0] * c4 + a[0][1] * c2 - a[0][3] * c0) * id;
+  b[2][2] = (a[3][0] * s4 - a[3][1] * s2 + a[3][3] * s0) * id;
+  b[2][3] = (-a[2][0] * s4 + a[2][1] * s2 - a[2][3] * s0) * id;
+  b[3][0] = (-a[1][0] * c3 + a[1][1] * c1 - a[1][2] * c0) * id;
+  b[3][1] = (a[0][0] * c3 - a[0][1] * c1 + a[0][2] * c0) * id;
+  b[3][2] = (-a[3][0] * s3 + a[3][1] * s1 - a[3][2] * s0) * id;
+  b[3][3] = (a[2][0] * s3 - a[2][1] * s1 + a[2][2] * s0) * id;
+}
+
+// Quaternion -> roll/pitch/yaw in degrees, asin not clamped   (PKF/UtilityFunctions.py:3-14)
+template <typename F> PKF_HD Vec3<F> quat_to_rpy_deg(const Quat<F>& q) {
+  const F k = F(180.0 / 3.14159265358979323846);
+  Vec3<F> o;
+  o.x = (F)atan2((double)(F(2) * (q.w * q.x + q.y * q.z)), (double)(F(1) - F(2) * (q.x * q.x + q.y * q.y))) * k;
+  o.y = (F)asin((double)(F(2) * (q.w * q.y - q.z * q.x))) * k;
+  o.z = (F)atan2((double)(F(2) * (q.w * q.z + q.x * q.y)), (double)(F(1) - F(2) * (q.y * q.y + q.z * q.z))) * k;
+  return o;
+}
+
+}  // namespace pkf

@@ -1,0 +1,85 @@
+// hostsim.cpp -- CPU build of poseestimationkf_b200/csrc/ekf_math.cuh for numerics probing.
+//
+// TEST TOOL ONLY.  The product has no CPU path; this file exists so that the arithmetic of the
+// device header can be exercised in float32 (and float64) inside the GPU-less build container and
+// by the `-m "not gpu"` test-suite.  It is compiled by tests/hostsim/build.py with g++ and loaded
+// with ctypes by tests only.
+#include <cstdint>
+#include <cstddef>
+#include "../../poseestimationkf_b200/csrc/ekf_math.cuh"
+
+using namespace pkf;
+
+template <typename F, int ALGO>
+static void replay_t(int64_t N, int64_t T, const float* streams, const float* dt, int dt_per_step,
+                     const float* acc_ref, const float* mag_ref, const float* q, const float* r,
+                     float lpf_acc, float lpf_mag, double* out_traj, uint8_t* out_flip, double* out_P) {
+  for (int64_t n = 0; n < N; ++n) {
+    Vec3<F> ra = {(F)acc_ref[0 * N + n], (F)acc_ref[1 * N + n], (F)acc_ref[2 * N + n]};
+    Vec3<F> rm = {(F)mag_ref[0 * N + n], (F)mag_ref[1 * N + n], (F)mag_ref[2 * N + n]};
+    FilterConst<F> fc = make_filter_const<F>(ra, rm, (F)q[n], (F)r[n]);
+    Quat<F> x = {F(1), F(0), F(0), F(0)};
+    Sym4<F> P = {F(1), F(0), F(0), F(0), F(1), F(0), F(0), F(1), F(0), F(1)};
+    Vec3<F> la = {F(0), F(0), F(0)}, lm = {F(0), F(0), F(0)};
+    for (int64_t t = 0; t < T; ++t) {
+      const float* s = streams + (size_t)t * 9 * N + n;
+      Vec3<F> w = {(F)s[0 * N], (F)s[1 * N], (F)s[2 * N]};
+      Vec3<F> a = {(F)s[3 * N], (F)s[4 * N], (F)s[5 * N]};
+      Vec3<F> m = {(F)s[6 * N], (F)s[7 * N], (F)s[8 * N]};
+      if (lpf_acc >= 0.f) { lowpass<F>(la, a, (F)lpf_acc, F(1) - (F)lpf_acc); a = la; }
+      if (lpf_mag >= 0.f) { lowpass<F>(lm, m, (F)lpf_mag, F(1) - (F)lpf_mag); m = lm; }
+      F h = (F)(dt_per_step ? dt[t] : dt[0]);
+      bool flip;
+      ekf_step<F, ALGO>(x, P, fc, w, a, m, h, flip);
+      if (out_traj) {
+        double* o = out_traj + (size_t)t * 4 * N + n;
+        o[0 * N] = x.w; o[1 * N] = x.x; o[2 * N] = x.y; o[3 * N] = x.z;
+      }
+      if (out_flip) out_flip[(size_t)t * N + n] = flip;
+    }
+    if (out_P) {
+      const F p[10] = {P.a00, P.a01, P.a02, P.a03, P.a11, P.a12, P.a13, P.a22, P.a23, P.a33};
+      for (int k = 0; k < 10; ++k) out_P[(size_t)k * N + n] = p[k];
+    }
+  }
+}
+
+extern "C" {
+
+// precision: 0 = float32, 1 = float64 ; algo: 0 = QR2, 1 = Jacobi
+int hostsim_replay(int precision, int algo, int64_t N, int64_t T, const float* streams, const float* dt,
+                   int dt_per_step, const float* acc_ref, const float* mag_ref, const float* q, const float* r,
+                   float lpf_acc, float lpf_mag, double* out_traj, uint8_t* out_flip, double* out_P) {
+#define GO(F, A) replay_t<F, A>(N, T, streams, dt, dt_per_step, acc_ref, mag_ref, q, r, lpf_acc, lpf_mag, out_traj, out_flip, out_P)
+  if (precision == 0 && algo == 0) GO(float, WAHBA_QR2);
+  else if (precision == 0 && algo == 1) GO(float, WAHBA_JACOBI);
+  else if (precision == 1 && algo == 0) GO(double, WAHBA_QR2);
+  else if (precision == 1 && algo == 1) GO(double, WAHBA_JACOBI);
+  else return 1;
+#undef GO
+  return 0;
+}
+
+// Wahba only: inputs [3][N] each; out_q [4][N], out_R [9][N] (row-major entries) or null
+int hostsim_wahba(int precision, int algo, int sweeps, int64_t N, const float* acc_ref, const float* mag_ref,
+                  const float* acc, const float* mag, const float* ka, const float* km, double* out_q,
+                  double* out_R) {
+  for (int64_t n = 0; n < N; ++n) {
+    auto run = [&](auto tag) {
+      using F = decltype(tag);
+      Vec3<F> ra = {(F)acc_ref[n], (F)acc_ref[N + n], (F)acc_ref[2 * N + n]};
+      Vec3<F> rm = {(F)mag_ref[n], (F)mag_ref[N + n], (F)mag_ref[2 * N + n]};
+      Vec3<F> a = {(F)acc[n], (F)acc[N + n], (F)acc[2 * N + n]};
+      Vec3<F> m = {(F)mag[n], (F)mag[N + n], (F)mag[2 * N + n]};
+      Mat3<F> R = algo == 0 ? wahba_qr2<F>(frame_from_pair<F>(ra, rm), a, m, (F)ka[n], (F)km[n])
+                            : wahba_jacobi<F>(ra, rm, a, m, (F)ka[n], (F)km[n], sweeps);
+      Quat<F> qq = rotation_to_quat_ref<F>(R);
+      out_q[n] = qq.w; out_q[N + n] = qq.x; out_q[2 * N + n] = qq.y; out_q[3 * N + n] = qq.z;
+      if (out_R) for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) out_R[(size_t)(3 * i + j) * N + n] = R.m[i][j];
+    };
+    if (precision == 0) run(float(0)); else run(double(0));
+  }
+  return 0;
+}
+
+}  // extern "C"
