@@ -100,6 +100,22 @@ class ReplayState:
         return ReplayState(self.x.clone(), self.p.clone(), None if self.lpf is None else self.lpf.clone())
 
 
+_scalar_cache: dict = {}
+
+
+def _scalar_tensor(value: float, device) -> torch.Tensor:
+    """One-element float32 tensor holding `value` on `device`, cached so that repeated replay calls
+    launch nothing but the filter kernel."""
+    key = (float(value), str(device))
+    t = _scalar_cache.get(key)
+    if t is None:
+        if len(_scalar_cache) > 64:
+            _scalar_cache.clear()
+        t = torch.full((1,), float(value), dtype=torch.float32, device=device)
+        _scalar_cache[key] = t
+    return t
+
+
 def _per_filter(v, n, device):
     if isinstance(v, torch.Tensor):
         _require_cuda(v)
@@ -142,7 +158,7 @@ def replay(streams: torch.Tensor, acc_ref: torch.Tensor, mag_ref: torch.Tensor, 
             raise ValueError("dt tensor must be [T]")
         dt_t, per_step = dt, 1
     else:
-        dt_t, per_step = torch.full((1,), float(dt), dtype=torch.float32, device=dev), 0
+        dt_t, per_step = _scalar_tensor(dt, dev), 0
     q_t, r_t = _per_filter(q, N, dev), _per_filter(r, N, dev)
     if store_trajectory and out_traj is None:
         out_traj = torch.empty((T, 4, N), dtype=torch.float32, device=dev)

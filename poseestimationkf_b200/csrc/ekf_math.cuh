@@ -19,7 +19,7 @@
 //   * RK4 on a linear constant-coefficient ODE is the degree-4 Taylor polynomial of exp(hA); with
 //     A^2 = -(|w|^2/4) I it collapses to  z = c0 x + c1 (A x).
 //   * With Q = q I3:  B Q B^T = (q/4)(|x|^2 I - x x^T).
-//   * With R = r I4:  K = P S^-1 = I - r S^-1  and  P - K P = r K, so only S^-1 (symmetric) is needed.
+//   * With R = r I4:  K = P S^-1 = I - r S^-1 (symmetric) and  P - K P = r K  (see kalman_gain).
 //   * P is kept as its upper triangle (10 values).
 //   * rank(B_wahba) = 2 always (two observations), so the SVD is taken on the 2x2 core of a QR
 //     factorisation of both vector pairs (see wahba_qr2) -- this is also what makes fp32 safe when
@@ -206,46 +206,56 @@ PKF_HD Sym4<F> propagate_cov(const Sym4<F>& P, const Vec3<F>& hw, const Quat<F>&
 }
 
 // ------------------------------------------------------------------------------------------
-// Inverse of the symmetric positive-definite S = P + r I by LDL^T.  (replaces np.linalg.inv,
-// PKF/ExtendedKalmanFilter.py:63-65)
+// Kalman gain for R = r I:  K = P S^-1 = I - r S^-1,  S = P + r I  (symmetric positive definite).
+// (replaces np.linalg.inv + matmul, PKF/ExtendedKalmanFilter.py:63-66.)
+//
+// S = L D L^T with the pivots kept SPLIT as d_k = r + delta_k (delta_k is the pivot of P's own
+// elimination; it is never added to r and subtracted again).  With W = L^-1 = I + N (N strictly
+// lower), rho_k = r/d_k and kappa_k = delta_k/d_k = 1 - rho_k:
+//     K = I - W^T diag(rho) W   =>   K_ii = kappa_i - sum_{k>i} n_ki rho_k n_ki
+//                                    K_ij =        - (rho_j n_ji + sum_{k>j} n_ki rho_k n_kj)   (i<j)
+// Forming the diagonal from kappa (a quotient) instead of 1 - rho (a difference) is what keeps the
+// gain accurate to ~1e-7 relative when r >> P (K ~ P/r would otherwise cancel against I), i.e. for
+// every (Q,R) tuning of the 1e-3..1e3 sweep (tests/test_gpu_replay.py::test_qr_sweep...).
 // ------------------------------------------------------------------------------------------
-template <typename F> PKF_HD Sym4<F> spd_inverse_plus_diag(const Sym4<F>& P, F r) {
-  const F s00 = P.a00 + r, s11 = P.a11 + r, s22 = P.a22 + r, s33 = P.a33 + r;
-  const F s01 = P.a01, s02 = P.a02, s03 = P.a03, s12 = P.a12, s13 = P.a13, s23 = P.a23;
-  F i0 = rcp_(s00);
-  F l10 = s01 * i0, l20 = s02 * i0, l30 = s03 * i0;
-  F d1 = fma_(-l10, s01, s11);
-  F i1 = rcp_(d1);
-  F t21 = fma_(-l10, s02, s12);
-  F t31 = fma_(-l10, s03, s13);
+template <typename F> PKF_HD Sym4<F> kalman_gain(const Sym4<F>& P, F r) {
+  const F p01 = P.a01, p02 = P.a02, p03 = P.a03, p12 = P.a12, p13 = P.a13, p23 = P.a23;
+  F e0 = P.a00;                                   // delta_0
+  F i0 = rcp_(e0 + r);
+  F l10 = p01 * i0, l20 = p02 * i0, l30 = p03 * i0;
+  F e1 = fma_(-l10, p01, P.a11);
+  F i1 = rcp_(e1 + r);
+  F t21 = fma_(-l10, p02, p12);
+  F t31 = fma_(-l10, p03, p13);
   F l21 = t21 * i1, l31 = t31 * i1;
-  F d2 = fma_(-l21, t21, fma_(-l20, s02, s22));
-  F i2 = rcp_(d2);
-  F t32 = fma_(-l21, t31, fma_(-l20, s03, s23));
+  F e2 = fma_(-l21, t21, fma_(-l20, p02, P.a22));
+  F i2 = rcp_(e2 + r);
+  F t32 = fma_(-l21, t31, fma_(-l20, p03, p23));
   F l32 = t32 * i2;
-  F d3 = fma_(-l32, t32, fma_(-l31, t31, fma_(-l30, s03, s33)));
-  F i3 = rcp_(d3);
-  // W = L^-1 (unit lower): w10=-l10, w21=-l21, w32=-l32, w20 = -l20 + l21 l10, ...
-  F w10 = -l10, w21 = -l21, w32 = -l32;
-  F w20 = fma_(-l21, w10, -l20);
-  F w31 = fma_(-l32, w21, -l31);
-  F w30 = fma_(-l32, w20, fma_(-l31, w10, -l30));
-  // S^-1 = W^T D^-1 W
-  F v30 = i3 * w30, v31 = i3 * w31, v32 = i3 * w32;
-  F v20 = i2 * w20, v21 = i2 * w21;
-  F v10 = i1 * w10;
-  Sym4<F> I;
-  I.a00 = fma_(w30, v30, fma_(w20, v20, fma_(w10, v10, i0)));
-  I.a01 = fma_(w30, v31, fma_(w20, v21, v10));
-  I.a02 = fma_(w30, v32, v20);
-  I.a03 = v30;
-  I.a11 = fma_(w31, v31, fma_(w21, v21, i1));
-  I.a12 = fma_(w31, v32, v21);
-  I.a13 = v31;
-  I.a22 = fma_(w32, v32, i2);
-  I.a23 = v32;
-  I.a33 = i3;
-  return I;
+  F e3 = fma_(-l32, t32, fma_(-l31, t31, fma_(-l30, p03, P.a33)));
+  F i3 = rcp_(e3 + r);
+  // N = L^-1 - I
+  F n10 = -l10, n21 = -l21, n32 = -l32;
+  F n20 = fma_(-l21, n10, -l20);
+  F n31 = fma_(-l32, n21, -l31);
+  F n30 = fma_(-l32, n20, fma_(-l31, n10, -l30));
+  // v_kj = -rho_k n_kj
+  F m1 = -(r * i1), m2 = -(r * i2), m3 = -(r * i3);
+  F v30 = m3 * n30, v31 = m3 * n31, v32 = m3 * n32;
+  F v20 = m2 * n20, v21 = m2 * n21;
+  F v10 = m1 * n10;
+  Sym4<F> K;
+  K.a00 = fma_(n30, v30, fma_(n20, v20, fma_(n10, v10, e0 * i0)));
+  K.a01 = fma_(n30, v31, fma_(n20, v21, v10));
+  K.a02 = fma_(n30, v32, v20);
+  K.a03 = v30;
+  K.a11 = fma_(n31, v31, fma_(n21, v21, e1 * i1));
+  K.a12 = fma_(n31, v32, v21);
+  K.a13 = v31;
+  K.a22 = fma_(n32, v32, e2 * i2);
+  K.a23 = v32;
+  K.a33 = e3 * i3;
+  return K;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -457,7 +467,7 @@ PKF_HD void ekf_step(Quat<F>& x, Sym4<F>& P, const FilterConst<F>& fc, const Vec
   // ---- Prediction (PKF/ExtendedKalmanFilter.py:58-68) ----
   Sym4<F> Pp = propagate_cov(P, hw, x, fc.qq);
   Quat<F> z = rk4_step(x, hw, h);
-  Sym4<F> Si = spd_inverse_plus_diag(Pp, fc.r);
+  Sym4<F> K = kalman_gain(Pp, fc.r);                      // :63-66
   // ---- Correction (PKF/ExtendedKalmanFilter.py:70-80) ----
   F ka = abs_(acc.z), km = F(1) - ka;                                         // :71
   Mat3<F> Rm = (ALGO == WAHBA_QR2) ? wahba_qr2(fc.E, acc, mag, ka, km)
@@ -465,23 +475,21 @@ PKF_HD void ekf_step(Quat<F>& x, Sym4<F>& P, const FilterConst<F>& fc, const Vec
   Quat<F> y = rotation_to_quat_ref(Rm);
   flip = dot4(y, z) < F(0);                                                   // :73-74
   y.w = sel_(flip, -y.w, y.w); y.x = sel_(flip, -y.x, y.x); y.y = sel_(flip, -y.y, y.y); y.z = sel_(flip, -y.z, y.z);
-  // X = z + K (y - z),  K = I - r S^-1   =>  X = y - r S^-1 (y - z)            :76-77
+  // X = z + K (y - z)                                                        :76-77
   F e0 = y.w - z.w, e1 = y.x - z.x, e2 = y.y - z.y, e3 = y.z - z.z;
-  F u0 = fma_(Si.a03, e3, fma_(Si.a02, e2, fma_(Si.a01, e1, Si.a00 * e0)));
-  F u1 = fma_(Si.a13, e3, fma_(Si.a12, e2, fma_(Si.a11, e1, Si.a01 * e0)));
-  F u2 = fma_(Si.a23, e3, fma_(Si.a22, e2, fma_(Si.a12, e1, Si.a02 * e0)));
-  F u3 = fma_(Si.a33, e3, fma_(Si.a23, e2, fma_(Si.a13, e1, Si.a03 * e0)));
-  const F r = fc.r;
   Quat<F> xn;
-  xn.w = fma_(-r, u0, y.w); xn.x = fma_(-r, u1, y.x); xn.y = fma_(-r, u2, y.y); xn.z = fma_(-r, u3, y.z);
+  xn.w = fma_(K.a03, e3, fma_(K.a02, e2, fma_(K.a01, e1, fma_(K.a00, e0, z.w))));
+  xn.x = fma_(K.a13, e3, fma_(K.a12, e2, fma_(K.a11, e1, fma_(K.a01, e0, z.x))));
+  xn.y = fma_(K.a23, e3, fma_(K.a22, e2, fma_(K.a12, e1, fma_(K.a02, e0, z.y))));
+  xn.z = fma_(K.a33, e3, fma_(K.a23, e2, fma_(K.a13, e1, fma_(K.a03, e0, z.z))));
   F inv = rsqrt_(dot4(xn, xn));                                               // :79
   x.w = xn.w * inv; x.x = xn.x * inv; x.y = xn.y * inv; x.z = xn.z * inv;
-  // P = P - K P = r K = r I - r^2 S^-1                                       :78
-  const F mr2 = -(r * r);
-  P.a00 = fma_(mr2, Si.a00, r); P.a01 = mr2 * Si.a01; P.a02 = mr2 * Si.a02; P.a03 = mr2 * Si.a03;
-  P.a11 = fma_(mr2, Si.a11, r); P.a12 = mr2 * Si.a12; P.a13 = mr2 * Si.a13;
-  P.a22 = fma_(mr2, Si.a22, r); P.a23 = mr2 * Si.a23;
-  P.a33 = fma_(mr2, Si.a33, r);
+  // P = P - K P = r K  (R = r I)                                             :78
+  const F r = fc.r;
+  P.a00 = r * K.a00; P.a01 = r * K.a01; P.a02 = r * K.a02; P.a03 = r * K.a03;
+  P.a11 = r * K.a11; P.a12 = r * K.a12; P.a13 = r * K.a13;
+  P.a22 = r * K.a22; P.a23 = r * K.a23;
+  P.a33 = r * K.a33;
 }
 
 template <typename F>

@@ -24,7 +24,7 @@ def replay(streams, dt, acc_ref, mag_ref, q, r, *, precision="f32", algo="qr2", 
     Returns traj [T,4,N] f64, flips [T,N] bool, P [10,N] f64."""
     streams = np.ascontiguousarray(streams, dtype=np.float32)
     T, _, N = streams.shape
-    dt = np.atleast_1d(np.asarray(dt, dtype=np.float32))
+    dt = np.atleast_1d(np.asarray(dt, dtype=np.float64))   # f32 build rounds it to float32 itself
     acc_ref = np.ascontiguousarray(acc_ref, dtype=np.float32)
     mag_ref = np.ascontiguousarray(mag_ref, dtype=np.float32)
     q = np.ascontiguousarray(np.broadcast_to(np.asarray(q, dtype=np.float32), (N,)))
@@ -33,7 +33,7 @@ def replay(streams, dt, acc_ref, mag_ref, q, r, *, precision="f32", algo="qr2", 
     flips = np.empty((T, N), dtype=np.uint8)
     P = np.empty((10, N))
     rc = lib().hostsim_replay(C.c_int(0 if precision == "f32" else 1), C.c_int(0 if algo == "qr2" else 1),
-                              C.c_int64(N), C.c_int64(T), _p(streams, C.c_float), _p(dt, C.c_float),
+                              C.c_int64(N), C.c_int64(T), _p(streams, C.c_float), _p(dt, C.c_double),
                               C.c_int(int(dt.size > 1)), _p(acc_ref, C.c_float), _p(mag_ref, C.c_float),
                               _p(q, C.c_float), _p(r, C.c_float), C.c_float(lpf_acc), C.c_float(lpf_mag),
                               _p(traj, C.c_double), _p(flips, C.c_uint8), _p(P, C.c_double))

@@ -11,7 +11,7 @@
 using namespace pkf;
 
 template <typename F, int ALGO>
-static void replay_t(int64_t N, int64_t T, const float* streams, const float* dt, int dt_per_step,
+static void replay_t(int64_t N, int64_t T, const float* streams, const double* dt, int dt_per_step,
                      const float* acc_ref, const float* mag_ref, const float* q, const float* r,
                      float lpf_acc, float lpf_mag, double* out_traj, uint8_t* out_flip, double* out_P) {
   for (int64_t n = 0; n < N; ++n) {
@@ -47,7 +47,7 @@ static void replay_t(int64_t N, int64_t T, const float* streams, const float* dt
 extern "C" {
 
 // precision: 0 = float32, 1 = float64 ; algo: 0 = QR2, 1 = Jacobi
-int hostsim_replay(int precision, int algo, int64_t N, int64_t T, const float* streams, const float* dt,
+int hostsim_replay(int precision, int algo, int64_t N, int64_t T, const float* streams, const double* dt,
                    int dt_per_step, const float* acc_ref, const float* mag_ref, const float* q, const float* r,
                    float lpf_acc, float lpf_mag, double* out_traj, uint8_t* out_flip, double* out_P) {
 #define GO(F, A) replay_t<F, A>(N, T, streams, dt, dt_per_step, acc_ref, mag_ref, q, r, lpf_acc, lpf_mag, out_traj, out_flip, out_P)

@@ -1,0 +1,82 @@
+"""The C-ABI shared library builds, loads, and exports every symbol include/posekf.h declares.
+No kernel is launched here (no GPU in this tier)."""
+import ctypes
+import os
+import re
+
+from poseestimationkf_b200 import _lib, build
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    text = open(os.path.join(ROOT, "include", "posekf.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(posekf_\w+)\s*\(", text)))
+
+
+def test_library_builds_for_sm100a():
+    path = build.build()
+    assert os.path.exists(path)
+    assert "arch=compute_100a,code=sm_100a" in " ".join(build.NVCC_FLAGS) and "-lineinfo" in build.NVCC_FLAGS
+
+
+def test_every_declared_symbol_is_exported():
+    lib = _lib.load()
+    declared = _declared()
+    assert len(declared) >= 14
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/posekf.h but not exported"
+    assert sorted(_lib.EXPORTS) == declared          # the ctypes table covers the header exactly
+    assert lib.posekf_version().decode().startswith("posekf_b200")
+
+
+def test_zero_spills_reported_by_ptxas():
+    build.build()
+    log = open(os.path.join(os.path.dirname(build.LIB_PATH), "build_ptxas.log")).read() \
+        if os.path.exists(os.path.join(os.path.dirname(build.LIB_PATH), "build_ptxas.log")) else ""
+    if not log:                       # library was shipped prebuilt
+        build.build(force=True)
+        log = open(os.path.join(os.path.dirname(build.LIB_PATH), "build_ptxas.log")).read()
+    spills = re.findall(r"(\d+) bytes spill stores, (\d+) bytes spill loads", log)
+    assert spills and all(a == "0" and b == "0" for a, b in spills)
+    regs = [int(r) for r in re.findall(r"Used (\d+) registers", log)]
+    assert max(regs) <= 128          # 4 CTAs of 128 threads per SM
+
+
+def test_argument_validation_without_gpu():
+    lib = _lib.load()
+    # negative sizes / null pointers are rejected before any CUDA call
+    assert lib.posekf_replay_f32(-1, 1, None, 1, None, 0, None, None, None, None, -1.0, -1.0, None, None, None, None,
+                                 None, 0, 0, None) == _lib.EINVAL
+    assert lib.posekf_replay_f32(8, 4, None, 8, None, 0, None, None, None, None, -1.0, -1.0, None, None, None, None,
+                                 None, 0, 0, None) == _lib.EINVAL
+    assert lib.posekf_replay_f32(0, 4, None, 8, None, 0, None, None, None, None, -1.0, -1.0, None, None, None, None,
+                                 None, 0, 0, None) == 0          # empty batch is a no-op
+    assert lib.posekf_wahba_f32(4, None, None, 0, None, None, None, None, 0.5, 0.5, 0, None, None, 0, 0, None) == _lib.EINVAL
+    assert lib.posekf_rot2quat_f32(0, None, None, None) == 0
+    try:
+        _lib.check(_lib.EINVAL, "x")
+        raise AssertionError("check() must raise")
+    except _lib.PosekfError:
+        pass
+
+
+def test_product_has_no_cpu_path():
+    # the package refuses CPU tensors instead of silently computing on the host
+    import torch
+    from poseestimationkf_b200 import batched as B
+    s = torch.zeros((2, 9, 4))
+    r = torch.zeros((3, 4))
+    try:
+        B.replay(s, r, r, dt=0.01)
+        raise AssertionError("CPU tensors must be rejected")
+    except _lib.PosekfError:
+        pass
+    # and nothing under the package imports the oracle
+    pkg = os.path.join(ROOT, "poseestimationkf_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in src.replace("oracle consumes", "").replace("the oracle", "") or f == "synth.py", f

@@ -1,0 +1,160 @@
+"""Parity of the stand-alone operators and of the reference-named compat classes (GPU)."""
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import ekf_oracle as O
+from poseestimationkf_b200 import batched as B
+from poseestimationkf_b200 import compat
+
+pytestmark = pytest.mark.gpu
+
+
+def _dev(a, cuda):
+    return torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).to(cuda)
+
+
+def _cond(g, tag):
+    Bm = (g[f"{tag}_ka"][:, None, None] * g["acc_ref"][:, :, None].astype(np.float64) * g["acc"][:, None, :]
+          + g[f"{tag}_km"][:, None, None] * g["mag_ref"][:, :, None].astype(np.float64) * g["mag"][:, None, :])
+    s = np.linalg.svd(Bm, compute_uv=False)
+    return s[:, 0] / s[:, 1]
+
+
+@pytest.mark.parametrize("tag", ["half", "refw"])
+@pytest.mark.parametrize("algo", ["qr2", "jacobi"])
+def test_wahba_vs_reference_golden(golden_wahba, cuda, tag, algo):
+    g = golden_wahba
+    args = [_dev(g[k].T, cuda) for k in ("acc_ref", "mag_ref", "acc", "mag")]
+    R, q = B.wahba(*args, k_acc=_dev(g[f"{tag}_ka"], cuda), k_mag=_dev(g[f"{tag}_km"], cuda), want_rotation=True,
+                   algo=algo)
+    ang = O.quat_angle(q.cpu().numpy().T, g[f"{tag}_q"])
+    if algo == "qr2":
+        assert ang.max() < 2e-6, ang.max()
+        np.testing.assert_allclose(R.cpu().numpy().T.reshape(-1, 3, 3), g[f"{tag}_R"], atol=5e-6)
+    else:
+        assert (ang < 1e-6 + 4 * 6e-8 * _cond(g, tag)).all()
+    assert (np.sum(q.cpu().numpy().T * g[f"{tag}_q"], axis=1) < 0).sum() <= 2
+    if tag == "half":       # scalar weights and the reference-weights shortcut go through the same kernel
+        _, q2 = B.wahba(*args, k_acc=0.5, k_mag=0.5, algo=algo)
+        assert torch.equal(q2, q)
+    else:
+        _, q3 = B.wahba(*args, weights_from_acc=True, algo=algo)
+        assert O.quat_angle(q3.cpu().numpy().T, g["refw_q"]).max() < (2e-6 if algo == "qr2" else 1.0)
+
+
+def test_wahba_hand_check_and_shared_reference(cuda):
+    # the reference's own known answer (WahbaProblem_singularValue.py): R = diag(-1,-1,1)
+    ra, rm = _dev([0.0, 0.0, 1.0], cuda), _dev([-1.0, 0.0, 0.0], cuda)
+    acc, mag = _dev([[0.0], [0.0], [1.0]], cuda), _dev([[1.0], [0.0], [0.0]], cuda)
+    for algo in ("qr2", "jacobi"):
+        R, _ = B.wahba(ra, rm, acc, mag, k_acc=0.5, k_mag=0.5, want_rotation=True, algo=algo)
+        np.testing.assert_allclose(R.cpu().numpy().reshape(3, 3), np.diag([-1.0, -1.0, 1.0]), atol=1e-6)
+
+
+def test_rot2quat_including_identity_nan(golden_wahba, cuda):
+    g = golden_wahba
+    out = B.rot2quat(_dev(g["r2q_in"].reshape(-1, 9).T, cuda)).cpu().numpy().T
+    ref = g["r2q_out"]
+    ok = np.isfinite(ref).all(axis=1)
+    assert O.quat_angle(out[ok], ref[ok]).max() < 2e-6
+    assert (np.sum(out[ok] * ref[ok], axis=1) > 0).all()          # same sign convention
+    ident = out[64]                                                 # M == I -> [nan, nan, nan, 0] like the reference
+    assert np.isnan(ident[:3]).all() and ident[3] == 0.0
+    np.testing.assert_allclose(np.abs(out[65]), [0, 0, 0, 1], atol=1e-6)   # diag(-1,-1,1): 180 deg about z
+
+
+def test_stepwise_operators_vs_reference_golden(golden_step, cuda):
+    g = golden_step
+    M = g["x"].shape[0]
+    gyro, x = _dev(g["gyro"].T, cuda), _dev(g["x"].T, cuda)
+    P = _dev(g["P"].reshape(M, 16).T, cuda)
+    dt = _dev(g["dt_ns"] * 1e-9, cuda)
+    qm = _dev(np.identity(3).reshape(-1) * float(g["q_scale"]), cuda)
+    rm = _dev(np.identity(4).reshape(-1) * float(g["r_scale"]), cuda)
+    z, Pp, K = B.predict(gyro, dt, x, P, qm, rm)
+    assert O.quat_angle(z.cpu().numpy().T, g["z"]).max() < 1e-6
+    np.testing.assert_allclose(Pp.cpu().numpy().T.reshape(M, 4, 4), g["P_pred"], rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(K.cpu().numpy().T.reshape(M, 4, 4), g["K"], rtol=1e-3, atol=1e-4)
+    # Correction fed with the reference's own z, P, K so that only this operator is under test
+    X, Pc, flip, meas = B.correct(_dev(g["mag"].T, cuda), _dev(g["acc"].T, cuda), _dev(g["acc0"].T, cuda),
+                                  _dev(g["mag0"].T, cuda), _dev(g["z"].T, cuda), _dev(g["P_pred"].reshape(M, 16).T, cuda),
+                                  _dev(g["K"].reshape(M, 16).T, cuda), want_flip=True, want_meas=True)
+    assert O.quat_angle(X.cpu().numpy().T, g["X"]).max() < 2e-6
+    assert (np.sum(X.cpu().numpy().T * g["X"], axis=1) > 0).all()
+    np.testing.assert_allclose(Pc.cpu().numpy().T.reshape(M, 4, 4), g["P_corr"], rtol=1e-3, atol=2e-5)
+    np.testing.assert_allclose(B.jacobian_a(gyro).cpu().numpy().T.reshape(M, 4, 4), g["JA"], rtol=1e-7)
+    np.testing.assert_allclose(B.jacobian_b(x).cpu().numpy().T.reshape(M, 4, 3), g["JB"], rtol=1e-7)
+    np.testing.assert_allclose(B.comparator(x, _dev(g["z"].T, cuda)).cpu().numpy().T, g["comparator"], atol=1e-6)
+    assert O.quat_angle(B.rk4(x, dt, gyro).cpu().numpy().T, g["rk4"]).max() < 1e-6
+    np.testing.assert_allclose(B.quat2rpy(x).cpu().numpy().T, g["rpy"], atol=2e-3)      # degrees
+    np.testing.assert_allclose(B.norm(_dev(g["P"][:, 0, :].T, cuda)).cpu().numpy(), g["norm"], rtol=1e-6)
+
+
+def test_rk4_known_answer(golden_rk4, cuda):
+    # Quarternions.py: omega=[3pi/2,pi,pi/2] rad/s for 1 s -> converges to the analytic exponential
+    w = _dev(golden_rk4["omega"][:, None], cuda)
+    for n_it in (1, 10, 100, 1000):
+        q = _dev([[1.0], [0.0], [0.0], [0.0]], cuda)
+        for _ in range(n_it):
+            q = B.rk4(q, 1.0 / n_it, w)
+        assert O.quat_angle(q.cpu().numpy().T, golden_rk4[f"steps_{n_it}"][None]).max() < (3e-5 if n_it == 1000 else 2e-6)
+
+
+def test_lowpass_operator(cuda):
+    x = torch.randn((200, 3, 300), device=cuda)
+    y, state = B.lowpass(x, 0.1)
+    ref = np.stack([O.lowpass_scalar(x[:, :, n].cpu().numpy(), 0.1) for n in range(0, 300, 37)], axis=-1)
+    np.testing.assert_allclose(y[:, :, ::37].cpu().numpy(), ref, rtol=1e-4, atol=1e-5)
+    assert torch.equal(state, y[-1])
+    # chunked low-pass carries its state
+    y1, s1 = B.lowpass(x[:77].contiguous(), 0.1)
+    y2, _ = B.lowpass(x[77:].contiguous(), 0.1, state=s1)
+    assert torch.equal(torch.cat([y1, y2]), y)
+
+
+def test_compat_modules_run_the_reference_loop(golden_traj, cuda):
+    """The loop body of Python Kalman Filter/main_file.py:19-47, verbatim, on the drop-in modules."""
+    sys.path.insert(0, compat.PATH)
+    try:
+        from ExtendedKalmanFilter import KalmanFilter
+        from Wahba import Wahba
+        from UtilityFunctions import DimensionalSplit, norm, Quart2RPY
+        g = golden_traj
+        n, T = 2, 60
+        S = g["noisy_streams"].astype(np.float64)
+        t_ns = np.arange(T + 1, dtype=np.int64) * 10 ** 7
+        acc_0, mag_0 = g["noisy_acc_ref"][:, n].astype(np.float64), g["noisy_mag_ref"][:, n].astype(np.float64)
+        w = Wahba(acc_0, mag_0)
+        k = KalmanFilter(t_ns[0], mag_0, acc_0, 0.5)
+        k.setQ(1)
+        k.setR(0.1)
+        P = np.identity(4)
+        X = np.asarray([1., 0., 0., 0.])
+        X_k = [X]
+        for i in range(T):
+            z_k, P, K_k = k.Prediction(S[i, 0:3, n], t_ns[i + 1], X, P)
+            wahbaquart = w.getQuarternion(S[i, 3:6, n], S[i, 6:9, n], 0.5, 0.5)
+            X, P = k.Correction(S[i, 6:9, n], S[i, 3:6, n], z_k, P, K_k)
+            X_k.append(X)
+        got = np.array(X_k[1:])
+        assert O.quat_angle(got, g["noisy_X"][:T, n]).max() < 1e-5
+        assert wahbaquart.shape == (4,) and abs(norm(wahbaquart) - 1) < 1e-6
+        Filt = DimensionalSplit(X_k)
+        assert len(Filt) == 4 and len(Filt[0]) == T + 1
+        assert k.Q[0, 0] == 1.0 and abs(k.R[0, 0] - 0.1) < 1e-15 and k.previousT == t_ns[T]
+        k.setQ(2); k.setQ(3)
+        assert k.Q[1, 1] == 6.0                                     # cumulative, like the reference
+        np.testing.assert_allclose(Quart2RPY(X), O.quat_to_rpy_deg(X), atol=2e-3)
+        R = w.getRotation(S[5, 3:6, n], S[5, 6:9, n], 0.5, 0.5)
+        np.testing.assert_allclose(R @ R.T, np.identity(3), atol=1e-5)
+        np.testing.assert_allclose(Wahba.RotationMatrix2Quart(R), w.getQuarternion(S[5, 3:6, n], S[5, 6:9, n], 0.5, 0.5), atol=1e-6)
+        assert k.GetJacobian_A(S[0, 0:3, n]).shape == (4, 4) and k.GetJacobian_B(X).shape == (4, 3)
+        np.testing.assert_allclose(KalmanFilter.RungeKutta4(X, 10 ** 7, S[0, 0:3, n]), O.rk4(X, 10 ** 7, S[0, 0:3, n]), atol=1e-6)
+        assert abs(k.Comparator(X, X)[0] - 1.0) < 1e-6
+    finally:
+        sys.path.remove(compat.PATH)
+        for m in ("ExtendedKalmanFilter", "Wahba", "UtilityFunctions", "_bridge"):
+            sys.modules.pop(m, None)

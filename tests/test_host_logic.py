@@ -1,0 +1,102 @@
+"""Host-side logic: layout helpers, synthetic generator, sharding arithmetic, world_size-2 gather
+over gloo.  CPU only."""
+import os
+import socket
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from poseestimationkf_b200 import batched as B
+from poseestimationkf_b200 import sharding as SH
+from poseestimationkf_b200.synth import make_imu
+
+
+def test_tri_full_roundtrip():
+    A = torch.randn(5, 4, 4)
+    P = A @ A.transpose(1, 2)
+    tri = B.tri_from_full(P)
+    assert tri.shape == (10, 5)
+    torch.testing.assert_close(B.full_from_tri(tri), P)
+    x = torch.arange(12.0).reshape(3, 4)
+    torch.testing.assert_close(B.aos(B.soa(x)), x)
+
+
+def test_initial_state_matches_reference_defaults():
+    st = B.ReplayState.initial(3, "cpu", with_lpf=True)
+    assert st.x.t().tolist() == [[1.0, 0.0, 0.0, 0.0]] * 3           # main_file.py:26
+    torch.testing.assert_close(st.covariance(), torch.eye(4).expand(3, 4, 4))   # main_file.py:23
+    assert st.lpf.abs().sum() == 0                                    # KalmanFilter.cpp:16-18
+
+
+def test_synth_properties():
+    imu = make_imu(64, 300, seed=5, sigma=0.01, keep_truth=True)
+    S = imu.streams
+    assert S.shape == (300, 9, 64) and S.dtype == torch.float32
+    for sl in (slice(3, 6), slice(6, 9)):
+        n = torch.linalg.vector_norm(S[:, sl].double(), dim=1)
+        assert (n - 1).abs().max() < 1e-6
+    az0 = imu.acc_ref[2].abs()
+    assert az0.min() > 0.02 and az0.max() < 0.98
+    # deterministic in the seed, different across seeds
+    again = make_imu(64, 300, seed=5, sigma=0.01)
+    assert torch.equal(again.streams, S)
+    assert not torch.equal(make_imu(64, 300, seed=6, sigma=0.01).streams, S)
+    # measurements are the references seen through the true attitude: ref ~= R(q) meas
+    q = imu.q_true[-1].T.numpy()
+    w, x, y, z = q.T
+    R = np.stack([np.stack([1 - 2 * (y * y + z * z), 2 * (x * y - w * z), 2 * (x * z + w * y)], -1),
+                  np.stack([2 * (x * y + w * z), 1 - 2 * (x * x + z * z), 2 * (y * z - w * x)], -1),
+                  np.stack([2 * (x * z - w * y), 2 * (y * z + w * x), 1 - 2 * (x * x + y * y)], -1)], 1)
+    back = np.einsum("nij,nj->ni", R, S[-1, 3:6].T.double().numpy())
+    assert np.abs(back - imu.acc_ref.T.double().numpy()).max() < 0.08     # sigma = 0.01 noise on both ends
+
+
+def test_shard_bounds_cover_and_align():
+    for n in (0, 1, 127, 128, 129, 1000, 1 << 20, 16777216, 16777216 + 5):
+        for world in (1, 2, 3, 4, 8):
+            spans = [SH.shard_bounds(n, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            for (b0, e0), (b1, e1) in zip(spans, spans[1:]):
+                assert e0 == b1 and b0 <= e0
+            assert all(b % SH.ALIGN == 0 for b, _ in spans if b < n)
+            sizes = SH.shard_sizes(n, world)
+            assert sum(sizes) == n and max(sizes) - min(sizes) < 2 * SH.ALIGN
+    assert SH.shard_sizes(16777216, 8) == [2097152] * 8
+
+
+def test_time_chunks():
+    assert list(SH.time_chunks(10, 4)) == [(0, 4), (4, 8), (8, 10)]
+    assert list(SH.time_chunks(0, 4)) == []
+    assert SH.chunk_steps_for_budget(1 << 20, 8 << 30) == (8 << 30) // ((1 << 20) * 36)
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _gather_worker(rank, world, port, n, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        b, e = SH.shard_bounds(n, rank, world)
+        full = torch.arange(4 * n, dtype=torch.float32).reshape(4, n)
+        got = SH.gather_states(full[:, b:e].contiguous(), n)
+        slow = SH.max_over_ranks(float(rank + 1), "cpu")
+        torch.save({"ok": torch.equal(got, full), "slow": slow}, os.path.join(out_dir, f"r{rank}.pt"))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gather_states_world2_gloo(tmp_path):
+    world, n = 2, 1000            # ragged: 1000 = 7*128 + 104 -> shards of 512 and 488
+    mp.spawn(_gather_worker, args=(world, _free_port(), n, str(tmp_path)), nprocs=world, join=True)
+    for r in range(world):
+        res = torch.load(os.path.join(str(tmp_path), f"r{r}.pt"))
+        assert res["ok"] and res["slow"] == 2.0
