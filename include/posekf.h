@@ -62,12 +62,17 @@ const char* posekf_version(void);
  *               (The reference passes integer ns timestamps and differences them,
  *               PKF/ExtendedKalmanFilter.py:32,62; ns do not fit float32, so the caller differences.)
  *   acc_ref, mag_ref  [3][Ns] : the log's acc_0 / mag_0 (Wahba reference vectors, PKF/Wahba.py:4-6)
- *   q_scale, r_scale  [N] : Q = q*I3, R = r*I4 as produced by setQ/setR (PKF/ExtendedKalmanFilter.py:12-15)
+ *   q_scale, r_scale  [N] : Q = q*I3, R = r*I4 as produced by setQ/setR (PKF/ExtendedKalmanFilter.py:12-15);
+ *               r must be > 0 (the kernel carries the covariance in units of r), q >= 0
  *   lpf_alpha_acc/mag  low-pass coefficient, < 0 disables the stage
  *   state_x     [4][N]  in: X before the first step, out: X after the last step
- *   state_p     [10][N] in/out: upper triangle of P in the order 00 01 02 03 11 12 13 22 23 33
+ *   state_p     [10][N] in/out: upper triangle of P / r  (the covariance IN UNITS OF THE FILTER'S r; after
+ *               an update this equals the Kalman gain) in the order 00 01 02 03 11 12 13 22 23 33.
+ *               The kernel works in this scaled form, so storing it unscaled would make a chunked
+ *               replay differ from an unchunked one by an ulp; callers multiply by r to obtain P.
  *   state_lpf   [6][N]  in/out low-pass state (acc xyz, mag xyz); may be NULL when both alphas < 0
- *   out_traj    [T][4][N] state after every step, or NULL
+ *   out_traj    [T][N][4] state after every step (one 16-byte quaternion per filter-step, i.e. the
+ *               reference's X_k list, PKF/main_file.py:44, for every filter), 16-byte aligned, or NULL
  *   out_flip    [T][N] uint8, 1 where the comparator negated the Wahba quaternion
  *               (PKF/ExtendedKalmanFilter.py:73-75), or NULL
  *   wahba_algo  POSEKF_WAHBA_*
@@ -82,8 +87,9 @@ int posekf_replay_f32(int64_t n_filters, int64_t n_steps, const float* streams, 
 /* Same replay with HOST buffers: streams_host [T][9][N] is streamed through the device in time
  * chunks (double-buffered H2D copies overlapped with the filter kernel, state carried across
  * chunks on the device), results are copied back.  This is the call an offline-replay user makes.
- *   out_x_host [4][N], out_p_host [10][N] (may be NULL), out_traj_host [T][4][N] (may be NULL).
- *   x0_host / p0_host may be NULL (X=[1,0,0,0], P=I4: PKF/main_file.py:23,26).
+ *   out_x_host [4][N], out_p_host [10][N] = upper triangle of P itself, unscaled (may be NULL), out_traj_host [T][N][4] (may be NULL).
+ *   x0_host / p0_host ([4][N] / [10][N] upper triangle of P, unscaled) may be NULL (X=[1,0,0,0], P=I4:
+ *   PKF/main_file.py:23,26).
  *   chunk_steps  steps per chunk (0 = choose so that one chunk is about 1 GiB).
  *   device      CUDA device ordinal.
  * Host buffers should be page-locked (cudaHostAlloc / cudaHostRegister) for full PCIe rate. */

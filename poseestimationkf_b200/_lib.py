@@ -46,8 +46,8 @@ def load(build_if_missing: bool = True) -> C.CDLL:
     global _lib
     if _lib is not None:
         return _lib
-    path = _build.LIB_PATH
-    if build_if_missing and _build.needs_build():
+    path = os.environ.get("POSEKF_LIB", _build.LIB_PATH)      # override: experiment builds (tools/)
+    if path == _build.LIB_PATH and build_if_missing and _build.needs_build():
         try:
             _build.build()
         except Exception as exc:  # no nvcc on this machine: use the shipped .so if there is one

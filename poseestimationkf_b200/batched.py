@@ -8,7 +8,7 @@ operations as `KalmanFilter.Prediction/Correction`, `Wahba.getRotation/getQuarte
 streams only; all arithmetic happens in libposekf_b200.so (include/posekf.h).
 
 Layout: batched arrays are component-major `[k, N]` float32 CUDA tensors (filter index fastest);
-IMU streams are `[T, 9, N]` (gyro xyz, acc xyz, mag xyz).  Helpers convert from/to the reference's
+IMU streams are `[T, 9, N]` (gyro xyz, acc xyz, mag xyz); stored trajectories are `[T, N, 4]`.  Helpers convert from/to the reference's
 per-filter `[N, k]` / `[N, 4, 4]` shapes.
 """
 from __future__ import annotations
@@ -77,27 +77,35 @@ def aos(a: torch.Tensor, *shape) -> torch.Tensor:
 @dataclass
 class ReplayState:
     """Filter state carried between `replay` calls (time-chunked replay, checkpoint/resume).
-    x [4,N], p [10,N] packed upper triangle of P, lpf [6,N] or None."""
+    x [4,N]; p [10,N] packed upper triangle of P/r (the covariance in units of each filter's r --
+    the form the kernel works in, so that chunked and unchunked replays are bit-identical);
+    r: the float or [N] tensor the scaling refers to; lpf [6,N] or None."""
     x: torch.Tensor
     p: torch.Tensor
+    r: object = 0.1
     lpf: torch.Tensor | None = None
 
     @staticmethod
-    def initial(n_filters: int, device, with_lpf: bool = False) -> "ReplayState":
-        """X=[1,0,0,0], P=I4 (Python Kalman Filter/main_file.py:23,26); low-pass state 0
-        (Kalman Filter Server/PoseEstimator/KalmanFilter.cpp:16-18)."""
+    def initial(n_filters: int, device, r=0.1, with_lpf: bool = False, P0: torch.Tensor | None = None) -> "ReplayState":
+        """X=[1,0,0,0], P=I4 (Python Kalman Filter/main_file.py:23,26) unless P0 [N,4,4] is given;
+        low-pass state 0 (Kalman Filter Server/PoseEstimator/KalmanFilter.cpp:16-18)."""
         x = torch.zeros((4, n_filters), dtype=torch.float32, device=device)
         x[0] = 1.0
-        p = torch.zeros((10, n_filters), dtype=torch.float32, device=device)
-        p[[0, 4, 7, 9]] = 1.0
+        if P0 is None:
+            p = torch.zeros((10, n_filters), dtype=torch.float32, device=device)
+            p[[0, 4, 7, 9]] = 1.0
+        else:
+            p = tri_from_full(P0.to(device=device, dtype=torch.float32))
+        p = p / (r if isinstance(r, torch.Tensor) else float(r))
         lpf = torch.zeros((6, n_filters), dtype=torch.float32, device=device) if with_lpf else None
-        return ReplayState(x, p, lpf)
+        return ReplayState(x, p.contiguous(), r, lpf)
 
     def covariance(self) -> torch.Tensor:
-        return full_from_tri(self.p)
+        """P [N,4,4] (unscaled)."""
+        return full_from_tri(self.p * (self.r if isinstance(self.r, torch.Tensor) else float(self.r)))
 
     def clone(self) -> "ReplayState":
-        return ReplayState(self.x.clone(), self.p.clone(), None if self.lpf is None else self.lpf.clone())
+        return ReplayState(self.x.clone(), self.p.clone(), self.r, None if self.lpf is None else self.lpf.clone())
 
 
 _scalar_cache: dict = {}
@@ -134,7 +142,7 @@ def replay(streams: torch.Tensor, acc_ref: torch.Tensor, mag_ref: torch.Tensor, 
     streams [T,9,Ns]; acc_ref, mag_ref [3,Ns]; dt: float seconds or [T] float32 CUDA tensor;
     q, r: floats or [N] tensors (Q=q*I3, R=r*I4).  `n_filters` > Ns replays every trajectory
     N/Ns times (filter n reads column n % Ns) -- the Q/R sweep layout.  `state` is updated in place
-    (created with the reference's initial values when None).  Returns (state, traj [T,4,N] or None,
+    (created with the reference's initial values when None).  Returns (state, traj [T,N,4] or None,
     flips [T,N] uint8 or None)."""
     _require_cuda(streams, acc_ref, mag_ref, out_traj)
     if streams.dim() != 3 or streams.shape[1] != 9:
@@ -145,8 +153,11 @@ def replay(streams: torch.Tensor, acc_ref: torch.Tensor, mag_ref: torch.Tensor, 
         raise ValueError("acc_ref / mag_ref must be [3, Ns]")
     dev = streams.device
     use_lpf = lpf_alpha_acc is not None or lpf_alpha_mag is not None
+    if not isinstance(r, torch.Tensor) and not float(r) > 0.0:
+        raise ValueError("r must be > 0 (the kernel carries the covariance in units of r)")
     if state is None:
-        state = ReplayState.initial(N, dev, with_lpf=use_lpf)
+        state = ReplayState.initial(N, dev, r=r, with_lpf=use_lpf)
+    state.r = r
     if use_lpf and state.lpf is None:
         state.lpf = torch.zeros((6, N), dtype=torch.float32, device=dev)
     _require_cuda(state.x, state.p, state.lpf)
@@ -161,9 +172,9 @@ def replay(streams: torch.Tensor, acc_ref: torch.Tensor, mag_ref: torch.Tensor, 
         dt_t, per_step = _scalar_tensor(dt, dev), 0
     q_t, r_t = _per_filter(q, N, dev), _per_filter(r, N, dev)
     if store_trajectory and out_traj is None:
-        out_traj = torch.empty((T, 4, N), dtype=torch.float32, device=dev)
-    if out_traj is not None and out_traj.shape != (T, 4, N):
-        raise ValueError("out_traj must be [T, 4, N]")
+        out_traj = torch.empty((T, N, 4), dtype=torch.float32, device=dev)
+    if out_traj is not None and out_traj.shape != (T, N, 4):
+        raise ValueError("out_traj must be [T, N, 4]")
     flips = torch.empty((T, N), dtype=torch.uint8, device=dev) if store_flips else None
     with torch.cuda.device(dev):
         rc = _lib.load().posekf_replay_f32(
@@ -181,7 +192,7 @@ def replay_host(streams, acc_ref, mag_ref, *, dt: float, q, r, lpf_alpha_acc=Non
     """End-to-end replay from HOST memory (CPU torch tensors, ideally pinned): the stream is pushed
     through the GPU in double-buffered time chunks and the final state (and optionally the
     trajectory) is copied back.  streams [T,9,N] float32 CPU; acc_ref/mag_ref [3,N]; q, r [N].
-    Returns (x [4,N], p [10,N], traj [T,4,N] or None) as CPU tensors."""
+    Returns (x [4,N], p [10,N], traj [T,N,4] or None) as CPU tensors."""
     for t in (streams, acc_ref, mag_ref, q, r):
         if t.is_cuda or t.dtype != torch.float32 or not t.is_contiguous():
             raise ValueError("replay_host takes contiguous float32 CPU tensors")
@@ -189,7 +200,7 @@ def replay_host(streams, acc_ref, mag_ref, *, dt: float, q, r, lpf_alpha_acc=Non
     pin = streams.is_pinned()
     x = torch.empty((4, N), dtype=torch.float32, pin_memory=pin)
     p = torch.empty((10, N), dtype=torch.float32, pin_memory=pin)
-    traj = torch.empty((T, 4, N), dtype=torch.float32, pin_memory=pin) if store_trajectory else None
+    traj = torch.empty((T, N, 4), dtype=torch.float32, pin_memory=pin) if store_trajectory else None
     rc = _lib.load().posekf_replay_host_f32(
         N, T, _ptr(streams), float(dt), _ptr(acc_ref), _ptr(mag_ref), _ptr(q), _ptr(r),
         -1.0 if lpf_alpha_acc is None else float(lpf_alpha_acc),

@@ -212,38 +212,39 @@ PKF_HD Sym4<F> propagate_cov(const Sym4<F>& P, const Vec3<F>& hw, const Quat<F>&
 // S = L D L^T with the pivots kept SPLIT as d_k = r + delta_k (delta_k is the pivot of P's own
 // elimination; it is never added to r and subtracted again).  With W = L^-1 = I + N (N strictly
 // lower), rho_k = r/d_k and kappa_k = delta_k/d_k = 1 - rho_k:
+// (The fused step keeps the covariance in units of r -- see ekf_step -- so r = 1 here.)
 //     K = I - W^T diag(rho) W   =>   K_ii = kappa_i - sum_{k>i} n_ki rho_k n_ki
 //                                    K_ij =        - (rho_j n_ji + sum_{k>j} n_ki rho_k n_kj)   (i<j)
 // Forming the diagonal from kappa (a quotient) instead of 1 - rho (a difference) is what keeps the
 // gain accurate to ~1e-7 relative when r >> P (K ~ P/r would otherwise cancel against I), i.e. for
 // every (Q,R) tuning of the 1e-3..1e3 sweep (tests/test_gpu_replay.py::test_qr_sweep...).
 // ------------------------------------------------------------------------------------------
-template <typename F> PKF_HD Sym4<F> kalman_gain(const Sym4<F>& P, F r) {
+template <typename F> PKF_HD Sym4<F> kalman_gain_unit(const Sym4<F>& P) {
+  // P is the predicted covariance IN UNITS OF r (P/r), so S = P + I and rho_k = 1/d_k.
   const F p01 = P.a01, p02 = P.a02, p03 = P.a03, p12 = P.a12, p13 = P.a13, p23 = P.a23;
   F e0 = P.a00;                                   // delta_0
-  F i0 = rcp_(e0 + r);
+  F i0 = rcp_(e0 + F(1));
   F l10 = p01 * i0, l20 = p02 * i0, l30 = p03 * i0;
   F e1 = fma_(-l10, p01, P.a11);
-  F i1 = rcp_(e1 + r);
+  F i1 = rcp_(e1 + F(1));
   F t21 = fma_(-l10, p02, p12);
   F t31 = fma_(-l10, p03, p13);
   F l21 = t21 * i1, l31 = t31 * i1;
   F e2 = fma_(-l21, t21, fma_(-l20, p02, P.a22));
-  F i2 = rcp_(e2 + r);
+  F i2 = rcp_(e2 + F(1));
   F t32 = fma_(-l21, t31, fma_(-l20, p03, p23));
   F l32 = t32 * i2;
   F e3 = fma_(-l32, t32, fma_(-l31, t31, fma_(-l30, p03, P.a33)));
-  F i3 = rcp_(e3 + r);
+  F i3 = rcp_(e3 + F(1));
   // N = L^-1 - I
   F n10 = -l10, n21 = -l21, n32 = -l32;
   F n20 = fma_(-l21, n10, -l20);
   F n31 = fma_(-l32, n21, -l31);
   F n30 = fma_(-l32, n20, fma_(-l31, n10, -l30));
   // v_kj = -rho_k n_kj
-  F m1 = -(r * i1), m2 = -(r * i2), m3 = -(r * i3);
-  F v30 = m3 * n30, v31 = m3 * n31, v32 = m3 * n32;
-  F v20 = m2 * n20, v21 = m2 * n21;
-  F v10 = m1 * n10;
+  F v30 = -(i3 * n30), v31 = -(i3 * n31), v32 = -(i3 * n32);
+  F v20 = -(i2 * n20), v21 = -(i2 * n21);
+  F v10 = -(i1 * n10);
   Sym4<F> K;
   K.a00 = fma_(n30, v30, fma_(n20, v20, fma_(n10, v10, e0 * i0)));
   K.a01 = fma_(n30, v31, fma_(n20, v21, v10));
@@ -278,18 +279,19 @@ PKF_HD Mat3<F> wahba_qr2(const RefFrame<F>& E, const Vec3<F>& a, const Vec3<F>& 
   F c01 = E.s12 * hh;
   F c10 = E.s22 * g;
   F c11 = E.s22 * hh;
-  bool neg = (ka * km) < F(0);
-  F sc11 = sel_(neg, -c11, c11), sc01 = sel_(neg, -c01, c01);
-  F p = c00 + sc11;
-  F r = c10 - sc01;
+  // sg = sign(ka km) is +1 whenever both weights are positive (always for normalised accelerometer
+  // input: ka = |a_z| <= 1); the reflected case is a rarely taken branch.
+  const bool neg = (ka * km) < F(0);
+  if (neg) { c11 = -c11; c01 = -c01; }
+  F p = c00 + c11;
+  F r = c10 - c01;
   F inv = rsqrt_(fma_(p, p, r * r));
   F cs = p * inv, sn = r * inv;
   // W = E * blockdiag([[cs, -sg sn],[sn, sg cs]], sg)
-  F scs = sel_(neg, -cs, cs), ssn = sel_(neg, -sn, sn);
-  Vec3<F> w1, w2, w3;
+  Vec3<F> w1, w2, w3 = E.e3;
   w1.x = fma_(sn, E.e2.x, cs * E.e1.x); w1.y = fma_(sn, E.e2.y, cs * E.e1.y); w1.z = fma_(sn, E.e2.z, cs * E.e1.z);
-  w2.x = fma_(scs, E.e2.x, -(ssn * E.e1.x)); w2.y = fma_(scs, E.e2.y, -(ssn * E.e1.y)); w2.z = fma_(scs, E.e2.z, -(ssn * E.e1.z));
-  w3.x = sel_(neg, -E.e3.x, E.e3.x); w3.y = sel_(neg, -E.e3.y, E.e3.y); w3.z = sel_(neg, -E.e3.z, E.e3.z);
+  w2.x = fma_(cs, E.e2.x, -(sn * E.e1.x)); w2.y = fma_(cs, E.e2.y, -(sn * E.e1.y)); w2.z = fma_(cs, E.e2.z, -(sn * E.e1.z));
+  if (neg) { w2.x = -w2.x; w2.y = -w2.y; w2.z = -w2.z; w3.x = -w3.x; w3.y = -w3.y; w3.z = -w3.z; }
   Mat3<F> R;
   const Vec3<F>&f1 = Fb.e1, &f2 = Fb.e2, &f3 = Fb.e3;
   R.m[0][0] = fma_(w3.x, f3.x, fma_(w2.x, f2.x, w1.x * f1.x));
@@ -447,7 +449,48 @@ template <typename F> PKF_HD Quat<F> rotation_to_quat_ref(const Mat3<F>& M) {
 }
 
 // ------------------------------------------------------------------------------------------
+// Rotation matrix -> quaternion ALIGNED WITH A PREDICTION z (fused-step form).
+// For a rotation M = R(y) the symmetric 4x4 matrix built from the four Shepperd candidates is
+// 4 y y^T (rows: [tr0 dx dy dz], [dx tr1 sxy sxz], [dy sxy tr2 syz], [dz sxz syz tr3]), so
+//     (4 y y^T) z = 4 (y.z) y
+// is y with the sign that makes y.z >= 0 -- exactly the vector the reference has after its
+// q/-q fix (PKF/ExtendedKalmanFilter.py:73-75) -- obtained without any compare/select and
+// conditioned by |y.z| (~1 in a tracking filter) instead of by the largest trace.  The caller
+// falls back to rotation_to_quat_ref when |y.z| is small (prediction and measurement ~180 deg
+// apart in 4-D, i.e. unrelated).  Returns the un-normalised 4 (y.z) y and its squared norm
+// 16 (y.z)^2 through n2.
+// ------------------------------------------------------------------------------------------
+template <typename F> PKF_HD Quat<F> rotation_to_quat_aligned(const Mat3<F>& M, const Quat<F>& z, F& n2) {
+  const F r00 = M.m[0][0], r11 = M.m[1][1], r22 = M.m[2][2];
+  F a = r00 + r11, b = r00 - r11, p1 = F(1) + r22, m1 = F(1) - r22;
+  F tr0 = p1 + a, tr3 = p1 - a, tr1 = m1 + b, tr2 = m1 - b;
+  F dx = M.m[2][1] - M.m[1][2], dy = M.m[0][2] - M.m[2][0], dz = M.m[1][0] - M.m[0][1];
+  F sxy = M.m[0][1] + M.m[1][0], sxz = M.m[0][2] + M.m[2][0], syz = M.m[1][2] + M.m[2][1];
+  Quat<F> c;
+  c.w = fma_(dz, z.z, fma_(dy, z.y, fma_(dx, z.x, tr0 * z.w)));
+  c.x = fma_(sxz, z.z, fma_(sxy, z.y, fma_(tr1, z.x, dx * z.w)));
+  c.y = fma_(syz, z.z, fma_(tr2, z.y, fma_(sxy, z.x, dy * z.w)));
+  c.z = fma_(tr3, z.z, fma_(syz, z.y, fma_(sxz, z.x, dz * z.w)));
+  n2 = dot4(c, c);
+  return c;
+}
+
+// The reference's q/-q decision for a measurement whose aligned form is y (y.z >= 0): the
+// reference's raw quaternion has component i >= 0 (i = its branch), so it negated iff y_i < 0.
+template <typename F> PKF_HD bool reference_flip(const Mat3<F>& M, const Quat<F>& y) {
+  const F r00 = M.m[0][0], r11 = M.m[1][1], r22 = M.m[2][2];
+  F tr1 = F(1) + r00 - r11 - r22, tr2 = F(1) - r00 + r11 - r22, tr3 = F(1) - r00 - r11 + r22;
+  bool b1 = (tr1 > tr2) && (tr1 > tr3);
+  bool b2 = !b1 && (tr2 > tr1) && (tr2 > tr3);
+  return sel_(b1, y.x, sel_(b2, y.y, y.z)) < F(0);
+}
+
+// ------------------------------------------------------------------------------------------
 // One fused filter step (Prediction + Correction, PKF/main_file.py:39,43), scalar Q and R.
+// The covariance argument P is carried IN UNITS OF r (P/r): with R = r I the whole recursion is
+// homogeneous in r --  P/r <- A (P/r) A^T + (q/4r)(|x|^2 I - x x^T),  K = (P/r)(P/r + I)^-1,
+// P_post/r = K -- so the scaled form saves the r multiplications and makes the post-update
+// covariance literally equal to the gain.  Callers convert at launch boundaries (r > 0 required).
 // ------------------------------------------------------------------------------------------
 enum WahbaAlgo { WAHBA_QR2 = 0, WAHBA_JACOBI = 1 };
 constexpr int kJacobiSweepsFused = 4;
@@ -455,26 +498,37 @@ constexpr int kJacobiSweepsFused = 4;
 template <typename F> struct FilterConst {
   RefFrame<F> E;          // from (acc_0, mag_0)
   Vec3<F> ra, rm;         // raw reference vectors (used by the Jacobi variant only)
-  F qq;                   // Q/4
-  F r;                    // R
+  F g;                    // Q/(4R): process noise in units of r
 };
 
-template <typename F, int ALGO>
+template <typename F, int ALGO, bool WANT_FLIP>
 PKF_HD void ekf_step(Quat<F>& x, Sym4<F>& P, const FilterConst<F>& fc, const Vec3<F>& gyro, const Vec3<F>& acc,
                      const Vec3<F>& mag, F h, bool& flip) {
   Vec3<F> hw;
   hw.x = F(0.5) * gyro.x; hw.y = F(0.5) * gyro.y; hw.z = F(0.5) * gyro.z;
   // ---- Prediction (PKF/ExtendedKalmanFilter.py:58-68) ----
-  Sym4<F> Pp = propagate_cov(P, hw, x, fc.qq);
-  Quat<F> z = rk4_step(x, hw, h);
-  Sym4<F> K = kalman_gain(Pp, fc.r);                      // :63-66
+  Sym4<F> Pp = propagate_cov(P, hw, x, fc.g);                                 // :59-61 (in units of r)
+  Quat<F> z = rk4_step(x, hw, h);                                             // :62
+  Sym4<F> K = kalman_gain_unit(Pp);                                           // :63-66
   // ---- Correction (PKF/ExtendedKalmanFilter.py:70-80) ----
   F ka = abs_(acc.z), km = F(1) - ka;                                         // :71
   Mat3<F> Rm = (ALGO == WAHBA_QR2) ? wahba_qr2(fc.E, acc, mag, ka, km)
                                    : wahba_jacobi(fc.ra, fc.rm, acc, mag, ka, km, kJacobiSweepsFused);
-  Quat<F> y = rotation_to_quat_ref(Rm);
-  flip = dot4(y, z) < F(0);                                                   // :73-74
-  y.w = sel_(flip, -y.w, y.w); y.x = sel_(flip, -y.x, y.x); y.y = sel_(flip, -y.y, y.y); y.z = sel_(flip, -y.z, y.z);
+  // measurement quaternion with the comparator's sign already applied            :73-75
+  F n2;
+  Quat<F> y = rotation_to_quat_aligned(Rm, z, n2);
+  if (n2 < F(0.16)) {
+    // |y.z| < 0.1: prediction and measurement are unrelated (never in a tracking filter; can happen
+    // on the first sample of a badly initialised one).  Use the selection-based conversion.
+    y = rotation_to_quat_ref(Rm);
+    F d = dot4(y, z);
+    F sg = sel_(d < F(0), F(-1), F(1));
+    y.w *= sg; y.x *= sg; y.y *= sg; y.z *= sg;
+  } else {
+    F inv = rsqrt_(n2);
+    y.w *= inv; y.x *= inv; y.y *= inv; y.z *= inv;
+  }
+  flip = WANT_FLIP ? reference_flip(Rm, y) : false;
   // X = z + K (y - z)                                                        :76-77
   F e0 = y.w - z.w, e1 = y.x - z.x, e2 = y.y - z.y, e3 = y.z - z.z;
   Quat<F> xn;
@@ -484,12 +538,8 @@ PKF_HD void ekf_step(Quat<F>& x, Sym4<F>& P, const FilterConst<F>& fc, const Vec
   xn.z = fma_(K.a33, e3, fma_(K.a23, e2, fma_(K.a13, e1, fma_(K.a03, e0, z.z))));
   F inv = rsqrt_(dot4(xn, xn));                                               // :79
   x.w = xn.w * inv; x.x = xn.x * inv; x.y = xn.y * inv; x.z = xn.z * inv;
-  // P = P - K P = r K  (R = r I)                                             :78
-  const F r = fc.r;
-  P.a00 = r * K.a00; P.a01 = r * K.a01; P.a02 = r * K.a02; P.a03 = r * K.a03;
-  P.a11 = r * K.a11; P.a12 = r * K.a12; P.a13 = r * K.a13;
-  P.a22 = r * K.a22; P.a23 = r * K.a23;
-  P.a33 = r * K.a33;
+  // P = P - K P = r K  (R = r I): in units of r the new covariance IS the gain     :78
+  P = K;
 }
 
 template <typename F>
@@ -497,8 +547,7 @@ PKF_HD FilterConst<F> make_filter_const(const Vec3<F>& acc_ref, const Vec3<F>& m
   FilterConst<F> fc;
   fc.E = frame_from_pair(acc_ref, mag_ref);
   fc.ra = acc_ref; fc.rm = mag_ref;
-  fc.qq = F(0.25) * q;
-  fc.r = r;
+  fc.g = (F(0.25) * q) / r;
   return fc;
 }
 

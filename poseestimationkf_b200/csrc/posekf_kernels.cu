@@ -26,9 +26,20 @@ using namespace pkf;
 
 namespace {
 
-constexpr int kThreads = 128;   // filters per CTA (4 warps); 4 CTAs/SM at <=128 registers
-constexpr int kTmaSteps = 2;    // TC: timesteps per TMA tile
-constexpr int kTmaStages = 4;   // ring depth
+// tunables (overridable with -D for experiments; the defaults are what ships)
+#ifndef PKF_TMA_STEPS
+#define PKF_TMA_STEPS 2
+#endif
+#ifndef PKF_TMA_STAGES
+#define PKF_TMA_STAGES 3
+#endif
+#ifndef PKF_MIN_CTAS
+#define PKF_MIN_CTAS 6
+#endif
+constexpr int kThreads = 128;                  // filters per CTA (4 warps)
+constexpr int kMinCtasPerSm = PKF_MIN_CTAS;    // 6 CTAs/SM (24 warps) <=> <=80 registers per thread
+constexpr int kTmaSteps = PKF_TMA_STEPS;       // TC: timesteps per TMA tile
+constexpr int kTmaStages = PKF_TMA_STAGES;     // ring depth
 constexpr int kChannels = 9;
 
 #define PKF_CUDA_TRY(expr)                           \
@@ -117,7 +128,7 @@ template <bool LPF> __device__ __forceinline__ void load_filter(const ReplayPara
   Vec3<float> rm = {p.mag_ref[col], p.mag_ref[Ns + col], p.mag_ref[2 * Ns + col]};
   f.fc = make_filter_const<float>(ra, rm, p.q_scale[n], p.r_scale[n]);
   f.x = {p.state_x[n], p.state_x[N + n], p.state_x[2 * N + n], p.state_x[3 * N + n]};
-  const float* sp = p.state_p + n;
+  const float* sp = p.state_p + n;   // P/r: the step works in units of r (see ekf_step), so does the state buffer
   f.P = {sp[0], sp[N], sp[2 * N], sp[3 * N], sp[4 * N], sp[5 * N], sp[6 * N], sp[7 * N], sp[8 * N], sp[9 * N]};
   if (LPF) {
     const float* sl = p.state_lpf + n;
@@ -138,47 +149,54 @@ template <bool LPF> __device__ __forceinline__ void store_filter(const ReplayPar
   }
 }
 
-template <int ALGO, bool LPF>
+// One filter step + optional outputs.  AUX = the launch has a trajectory and/or flip output.
+template <int ALGO, bool LPF, bool AUX>
 __device__ __forceinline__ void filter_step(const ReplayParams& p, FilterRegs& f, const float (&s)[kChannels], float h,
-                                            int64_t t, int64_t n) {
+                                            float4* __restrict__& traj, uint8_t* __restrict__& flips) {
   Vec3<float> w = {s[0], s[1], s[2]}, a = {s[3], s[4], s[5]}, m = {s[6], s[7], s[8]};
   if (LPF) {   // SRV/KalmanFilter.cpp:285,298 -- filtered values feed Wahba, not renormalised
     if (p.alpha_acc >= 0.f) { lowpass<float>(f.la, a, p.alpha_acc, 1.f - p.alpha_acc); a = f.la; }
     if (p.alpha_mag >= 0.f) { lowpass<float>(f.lm, m, p.alpha_mag, 1.f - p.alpha_mag); m = f.lm; }
   }
   bool flip;
-  ekf_step<float, ALGO>(f.x, f.P, f.fc, w, a, m, h, flip);
-  if (p.out_traj) {
-    float* o = p.out_traj + (t * 4) * p.N + n;
-    stg_stream(o, f.x.w); stg_stream(o + p.N, f.x.x); stg_stream(o + 2 * p.N, f.x.y); stg_stream(o + 3 * p.N, f.x.z);
+  ekf_step<float, ALGO, AUX>(f.x, f.P, f.fc, w, a, m, h, flip);
+  if (AUX) {
+    if (traj) {   // [T][N][4]: one 16-byte store per filter-step, consecutive filters consecutive
+      asm volatile("st.global.cs.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(traj), "f"(f.x.w), "f"(f.x.x), "f"(f.x.y), "f"(f.x.z)
+                   : "memory");
+      traj += p.N;
+    }
+    if (flips) { *flips = flip ? 1 : 0; flips += p.N; }
   }
-  if (p.out_flip) p.out_flip[t * p.N + n] = flip ? 1 : 0;
 }
 
 // ---------------------------------------------------------------------------------------------
 // Replay, LDG staging: coalesced loads straight to registers, next step prefetched while the
 // current one is computed.
 // ---------------------------------------------------------------------------------------------
-template <int ALGO, bool LPF>
-__global__ void __launch_bounds__(kThreads, 4) replay_ldg_kernel(const ReplayParams p) {
+template <int ALGO, bool LPF, bool AUX>
+__global__ void __launch_bounds__(kThreads, ALGO == WAHBA_JACOBI ? 4 : kMinCtasPerSm) replay_ldg_kernel(const ReplayParams p) {
   const int64_t n = (int64_t)blockIdx.x * kThreads + threadIdx.x;
   if (n >= p.N) return;
   const int64_t Ns = p.Ns;
   const int64_t col = (Ns == p.N) ? n : (n % Ns);
   FilterRegs f;
   load_filter<LPF>(p, n, col, f);
+  float4* traj = (AUX && p.out_traj) ? reinterpret_cast<float4*>(p.out_traj) + n : nullptr;
+  uint8_t* flips = (AUX && p.out_flip) ? p.out_flip + n : nullptr;
   const float* s = p.streams + col;
   const int64_t step_stride = kChannels * Ns;
   float cur[kChannels], nxt[kChannels];
 #pragma unroll
   for (int c = 0; c < kChannels; ++c) cur[c] = ldg_stream(s + c * Ns);
   const float dt0 = p.dt[0];
-  for (int64_t t = 0; t < p.T; ++t) {
-    const float* sn = s + ((t + 1 < p.T) ? (t + 1) : t) * step_stride;
+  const int T = (int)p.T;
+  for (int t = 0; t < T; ++t) {
+    if (t + 1 < T) s += step_stride;
 #pragma unroll
-    for (int c = 0; c < kChannels; ++c) nxt[c] = ldg_stream(sn + c * Ns);
+    for (int c = 0; c < kChannels; ++c) nxt[c] = ldg_stream(s + c * Ns);
     const float h = p.dt_per_step ? __ldg(p.dt + t) : dt0;
-    filter_step<ALGO, LPF>(p, f, cur, h, t, n);
+    filter_step<ALGO, LPF, AUX>(p, f, cur, h, traj, flips);
 #pragma unroll
     for (int c = 0; c < kChannels; ++c) cur[c] = nxt[c];
   }
@@ -198,8 +216,8 @@ struct __align__(128) TmaSmem {
 };
 constexpr uint32_t kTileBytes = kTmaSteps * kChannels * kThreads * sizeof(float);
 
-template <int ALGO, bool LPF>
-__global__ void __launch_bounds__(kThreads, 4)
+template <int ALGO, bool LPF, bool AUX>
+__global__ void __launch_bounds__(kThreads, kMinCtasPerSm)
     replay_tma_kernel(const ReplayParams p, const __grid_constant__ CUtensorMap tmap) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   TmaSmem& sm = *reinterpret_cast<TmaSmem*>(smem_raw);
@@ -207,8 +225,9 @@ __global__ void __launch_bounds__(kThreads, 4)
   const int64_t n0 = (int64_t)blockIdx.x * kThreads;
   const int64_t n = n0 + tid;
   const bool valid = n < p.N;
-  const int64_t col0 = (p.Ns == p.N) ? n0 : (n0 % p.Ns);
-  const int64_t n_chunks = (p.T + kTmaSteps - 1) / kTmaSteps;
+  const int col0 = (int)((p.Ns == p.N) ? n0 : (n0 % p.Ns));
+  const int T = (int)p.T;
+  const int n_chunks = (T + kTmaSteps - 1) / kTmaSteps;
 
   if (tid == 0) {
 #pragma unroll
@@ -222,36 +241,40 @@ __global__ void __launch_bounds__(kThreads, 4)
     for (int s = 0; s < kTmaStages; ++s) {
       if (s < n_chunks) {
         mbar_expect_tx(&sm.full[s], kTileBytes);
-        tma_load_3d(&sm.tile[s][0][0][0], &tmap, &sm.full[s], (int)col0, 0, s * kTmaSteps);
+        tma_load_3d(&sm.tile[s][0][0][0], &tmap, &sm.full[s], col0, 0, s * kTmaSteps);
       }
     }
   }
 
   FilterRegs f;
-  if (valid) load_filter<LPF>(p, n, col0 + tid, f);
+  if (valid) load_filter<LPF>(p, n, (int64_t)col0 + tid, f);
+  float4* traj = (AUX && valid && p.out_traj) ? reinterpret_cast<float4*>(p.out_traj) + n : nullptr;
+  uint8_t* flips = (AUX && valid && p.out_flip) ? p.out_flip + n : nullptr;
   const float dt0 = p.dt[0];
 
   int stage = 0;
   uint32_t parity = 0;
-  for (int64_t k = 0; k < n_chunks; ++k) {
-    // producer: refill the tile every warp released in the previous iteration
+  for (int k = 0; k < n_chunks; ++k) {
+    // producer: refill the tile that every warp released in the previous iteration
     if (tid == 0 && k >= 1 && (k - 1 + kTmaStages) < n_chunks) {
-      const int ps = (stage + kTmaStages - 1) % kTmaStages;
-      const uint32_t pp = (uint32_t)(((k - 1) / kTmaStages) & 1);
+      const int ps = (stage == 0) ? kTmaStages - 1 : stage - 1;
+      const uint32_t pp = (stage == 0) ? (parity ^ 1u) : parity;     // parity of iteration k-1
       mbar_wait(&sm.empty[ps], pp);
       mbar_expect_tx(&sm.full[ps], kTileBytes);
-      tma_load_3d(&sm.tile[ps][0][0][0], &tmap, &sm.full[ps], (int)col0, 0, (int)((k - 1 + kTmaStages) * kTmaSteps));
+      tma_load_3d(&sm.tile[ps][0][0][0], &tmap, &sm.full[ps], col0, 0, (k - 1 + kTmaStages) * kTmaSteps);
     }
     mbar_wait(&sm.full[stage], parity);
+    if (valid) {
+      const int steps = min(kTmaSteps, T - k * kTmaSteps);     // < kTmaSteps only in the last chunk
 #pragma unroll
-    for (int tt = 0; tt < kTmaSteps; ++tt) {
-      const int64_t t = k * kTmaSteps + tt;
-      if (t < p.T && valid) {
-        float s[kChannels];
+      for (int tt = 0; tt < kTmaSteps; ++tt) {
+        if (tt < steps) {
+          float s[kChannels];
 #pragma unroll
-        for (int c = 0; c < kChannels; ++c) s[c] = sm.tile[stage][tt][c][tid];
-        const float h = p.dt_per_step ? __ldg(p.dt + t) : dt0;
-        filter_step<ALGO, LPF>(p, f, s, h, t, n);
+          for (int c = 0; c < kChannels; ++c) s[c] = sm.tile[stage][tt][c][tid];
+          const float h = p.dt_per_step ? __ldg(p.dt + k * kTmaSteps + tt) : dt0;
+          filter_step<ALGO, LPF, AUX>(p, f, s, h, traj, flips);
+        }
       }
     }
     __syncwarp();
@@ -598,10 +621,10 @@ bool tma_eligible(const ReplayParams& p) {
   return true;
 }
 
-template <int ALGO, bool LPF> int launch_replay(const ReplayParams& p, bool use_tma, cudaStream_t st) {
+template <int ALGO, bool LPF, bool AUX> int launch_replay(const ReplayParams& p, bool use_tma, cudaStream_t st) {
   const unsigned grid = (unsigned)((p.N + kThreads - 1) / kThreads);
   if (!use_tma) {
-    replay_ldg_kernel<ALGO, LPF><<<grid, kThreads, 0, st>>>(p);
+    replay_ldg_kernel<ALGO, LPF, AUX><<<grid, kThreads, 0, st>>>(p);
     return launch_status();
   }
   EncodeTiledFn enc = get_encode_fn();
@@ -615,14 +638,16 @@ template <int ALGO, bool LPF> int launch_replay(const ReplayParams& p, bool use_
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return POSEKF_EALIGN;
-  auto kern = replay_tma_kernel<ALGO, LPF>;
-  static bool attr_set = false;   // idempotent; worst case set twice
-  if (!attr_set) {
-    PKF_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TmaSmem)));
-    attr_set = true;
-  }
+  auto kern = replay_tma_kernel<ALGO, LPF, AUX>;
+  // idempotent; set on every launch (cheap) so that it holds on every device of a multi-GPU process
+  PKF_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TmaSmem)));
   kern<<<grid, kThreads, sizeof(TmaSmem), st>>>(p, tmap);
   return launch_status();
+}
+
+template <int ALGO, bool LPF> int launch_replay_aux(const ReplayParams& p, bool use_tma, cudaStream_t st) {
+  const bool aux = p.out_traj != nullptr || p.out_flip != nullptr;
+  return aux ? launch_replay<ALGO, LPF, true>(p, use_tma, st) : launch_replay<ALGO, LPF, false>(p, use_tma, st);
 }
 
 int replay_dispatch(const ReplayParams& p, int algo, int staging, cudaStream_t st) {
@@ -632,8 +657,8 @@ int replay_dispatch(const ReplayParams& p, int algo, int staging, cudaStream_t s
   else if (staging == POSEKF_STAGE_TMA) { if (!tma_eligible(p)) return POSEKF_EALIGN; use_tma = true; }
   else if (staging == POSEKF_STAGE_AUTO) use_tma = tma_eligible(p);
   else return POSEKF_EINVAL;
-  if (algo == POSEKF_WAHBA_QR2) return lpf ? launch_replay<WAHBA_QR2, true>(p, use_tma, st) : launch_replay<WAHBA_QR2, false>(p, use_tma, st);
-  if (algo == POSEKF_WAHBA_JACOBI) return lpf ? launch_replay<WAHBA_JACOBI, true>(p, use_tma, st) : launch_replay<WAHBA_JACOBI, false>(p, use_tma, st);
+  if (algo == POSEKF_WAHBA_QR2) return lpf ? launch_replay_aux<WAHBA_QR2, true>(p, use_tma, st) : launch_replay_aux<WAHBA_QR2, false>(p, use_tma, st);
+  if (algo == POSEKF_WAHBA_JACOBI) return lpf ? launch_replay_aux<WAHBA_JACOBI, true>(p, use_tma, st) : launch_replay_aux<WAHBA_JACOBI, false>(p, use_tma, st);
   return POSEKF_EINVAL;
 }
 
@@ -658,7 +683,8 @@ int posekf_replay_f32(int64_t n_filters, int64_t n_steps, const float* streams, 
   if (n_streams > n_filters || (n_filters % n_streams) != 0) return POSEKF_EINVAL;
   const bool lpf = lpf_alpha_acc >= 0.f || lpf_alpha_mag >= 0.f;
   if (lpf && !state_lpf) return POSEKF_EINVAL;
-  if ((n_filters + kThreads - 1) / kThreads > 0x7fffffffLL) return POSEKF_EINVAL;
+  if ((n_filters + kThreads - 1) / kThreads > 0x7fffffffLL || n_steps > 0x7fffffffLL) return POSEKF_EINVAL;
+  if (out_traj && (reinterpret_cast<uintptr_t>(out_traj) & 15) != 0) return POSEKF_EALIGN;
   ReplayParams p;
   p.N = n_filters; p.T = n_steps; p.Ns = n_streams; p.streams = streams; p.dt = dt; p.dt_per_step = dt_per_step;
   p.acc_ref = acc_ref; p.mag_ref = mag_ref; p.q_scale = q_scale; p.r_scale = r_scale;
@@ -746,14 +772,17 @@ int posekf_replay_host_f32(int64_t N, int64_t T, const float* streams_host, floa
     } else {
       TRY(cudaMemcpyAsync(d_x, x0_host, (size_t)4 * N * sizeof(float), cudaMemcpyHostToDevice, s_comp));
     }
-    if (!p0_host) {
-      init.assign((size_t)10 * N, 0.f);
-      const int diag[4] = {0, 4, 7, 9};
-      for (int d = 0; d < 4; ++d) std::fill(init.begin() + (size_t)diag[d] * N, init.begin() + (size_t)(diag[d] + 1) * N, 1.f);
-      TRY(cudaMemcpy(d_p, init.data(), (size_t)10 * N * sizeof(float), cudaMemcpyHostToDevice));
-    } else {
-      TRY(cudaMemcpyAsync(d_p, p0_host, (size_t)10 * N * sizeof(float), cudaMemcpyHostToDevice, s_comp));
+    // the device state holds P/r
+    init.assign((size_t)10 * N, 0.f);
+    const int diag[4] = {0, 4, 7, 9};
+    for (int k = 0; k < 10; ++k) {
+      const bool on_diag = (k == diag[0] || k == diag[1] || k == diag[2] || k == diag[3]);
+      for (int64_t i = 0; i < N; ++i) {
+        const float p0 = p0_host ? p0_host[(size_t)k * N + i] : (on_diag ? 1.f : 0.f);
+        init[(size_t)k * N + i] = p0 / r_scale_host[i];
+      }
     }
+    TRY(cudaMemcpy(d_p, init.data(), (size_t)10 * N * sizeof(float), cudaMemcpyHostToDevice));
   }
   const int64_t n_chunks = (T + chunk_steps - 1) / chunk_steps;
   for (int64_t c = 0; c < n_chunks; ++c) {
@@ -783,6 +812,9 @@ int posekf_replay_host_f32(int64_t N, int64_t T, const float* streams_host, floa
   TRY(cudaStreamSynchronize(s_comp));
   TRY(cudaStreamSynchronize(s_out));
   TRY(cudaStreamSynchronize(s_copy));
+  if (out_p_host)
+    for (int k = 0; k < 10; ++k)
+      for (int64_t i = 0; i < N; ++i) out_p_host[(size_t)k * N + i] *= r_scale_host[i];
 #undef TRY
   cleanup();
   return 0;

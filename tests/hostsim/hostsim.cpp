@@ -19,7 +19,8 @@ static void replay_t(int64_t N, int64_t T, const float* streams, const double* d
     Vec3<F> rm = {(F)mag_ref[0 * N + n], (F)mag_ref[1 * N + n], (F)mag_ref[2 * N + n]};
     FilterConst<F> fc = make_filter_const<F>(ra, rm, (F)q[n], (F)r[n]);
     Quat<F> x = {F(1), F(0), F(0), F(0)};
-    Sym4<F> P = {F(1), F(0), F(0), F(0), F(1), F(0), F(0), F(1), F(0), F(1)};
+    const F ir = F(1) / (F)r[n];   // the step carries P/r
+    Sym4<F> P = {ir, F(0), F(0), F(0), ir, F(0), F(0), ir, F(0), ir};
     Vec3<F> la = {F(0), F(0), F(0)}, lm = {F(0), F(0), F(0)};
     for (int64_t t = 0; t < T; ++t) {
       const float* s = streams + (size_t)t * 9 * N + n;
@@ -30,7 +31,7 @@ static void replay_t(int64_t N, int64_t T, const float* streams, const double* d
       if (lpf_mag >= 0.f) { lowpass<F>(lm, m, (F)lpf_mag, F(1) - (F)lpf_mag); m = lm; }
       F h = (F)(dt_per_step ? dt[t] : dt[0]);
       bool flip;
-      ekf_step<F, ALGO>(x, P, fc, w, a, m, h, flip);
+      ekf_step<F, ALGO, true>(x, P, fc, w, a, m, h, flip);
       if (out_traj) {
         double* o = out_traj + (size_t)t * 4 * N + n;
         o[0 * N] = x.w; o[1 * N] = x.x; o[2 * N] = x.y; o[3 * N] = x.z;
@@ -39,7 +40,7 @@ static void replay_t(int64_t N, int64_t T, const float* streams, const double* d
     }
     if (out_P) {
       const F p[10] = {P.a00, P.a01, P.a02, P.a03, P.a11, P.a12, P.a13, P.a22, P.a23, P.a33};
-      for (int k = 0; k < 10; ++k) out_P[(size_t)k * N + n] = p[k];
+      for (int k = 0; k < 10; ++k) out_P[(size_t)k * N + n] = (F)r[n] * p[k];
     }
   }
 }

@@ -25,9 +25,10 @@ def test_tri_full_roundtrip():
 
 
 def test_initial_state_matches_reference_defaults():
-    st = B.ReplayState.initial(3, "cpu", with_lpf=True)
+    st = B.ReplayState.initial(3, "cpu", r=0.1, with_lpf=True)
     assert st.x.t().tolist() == [[1.0, 0.0, 0.0, 0.0]] * 3           # main_file.py:26
     torch.testing.assert_close(st.covariance(), torch.eye(4).expand(3, 4, 4))   # main_file.py:23
+    torch.testing.assert_close(st.p[[0, 4, 7, 9]], torch.full((4, 3), 10.0))     # stored in units of r
     assert st.lpf.abs().sum() == 0                                    # KalmanFilter.cpp:16-18
 
 

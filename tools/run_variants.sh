@@ -1,0 +1,7 @@
+#!/bin/bash
+# runs tools/devbench.py against every library in tools/variants (on the GPU box)
+cd "$(dirname "$0")/.."
+for so in tools/variants/*.so; do
+  tag=$(basename $so .so)
+  POSEKF_LIB=$so python tools/devbench.py --variants tma:qr2,ldg:qr2 --tag $tag 2>&1 | grep variant
+done
