@@ -95,6 +95,25 @@ def cpu_baseline(target_seconds: float, cores: int | None = None):
             "single_core_value": single}
 
 
+def cpu_baseline_compiled(n_filters: int = 16384, n_steps: int = 500):
+    """The same path as an optimised CPU program would run it: oracle/ekf_oracle.c (float64, dense 4x4
+    algebra + Jacobi SVD as the reference's numpy calls do, gcc -O2), one pthread per host core.
+    Reported beside `cpu_baseline` (the reference's own Python implementation) for context."""
+    import numpy as np
+    from oracle import c_oracle as CO
+    from poseestimationkf_b200.synth import make_imu
+    cores = os.cpu_count() or 1
+    imu = make_imu(n_filters, n_steps, seed=5, sigma=0.01)
+    S = imu.streams.numpy()
+    ar, mr = imu.acc_ref.numpy(), imu.mag_ref.numpy()
+    CO.replay(S[:50], 1e7, ar, mr, 1.0, 0.1, store=False, flips=False, threads=cores)
+    t0 = time.perf_counter()
+    CO.replay(S, 1e7, ar, mr, 1.0, 0.1, store=False, flips=False, threads=cores)
+    wall = time.perf_counter() - t0
+    return {"value": n_filters * n_steps / wall, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{n_filters} filters x {n_steps} steps, float64 C restatement (oracle/ekf_oracle.c), {cores} pthreads"}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -344,6 +363,10 @@ def run_ours(args):
     }
     if not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(args.cpu_seconds)
+        try:
+            line["cpu_baseline_compiled"] = cpu_baseline_compiled()
+        except Exception as exc:      # the C checker is optional infrastructure
+            line["cpu_baseline_compiled"] = {"unavailable": str(exc)}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
