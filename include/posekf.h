@@ -75,6 +75,11 @@ const char* posekf_version(void);
  *               reference's X_k list, PKF/main_file.py:44, for every filter), 16-byte aligned, or NULL
  *   out_flip    [T][N] uint8, 1 where the comparator negated the Wahba quaternion
  *               (PKF/ExtendedKalmanFilter.py:73-75), or NULL
+ *   truth       [T][Ns][4] reference track (ground truth, a Wahba-only or gyro-only track, another
+ *               run's out_traj ...) for the on-device tuning objective, 16-byte aligned, or NULL
+ *   loss_acc    [N] in/out, required with truth: loss_acc[n] += sum_t 1 - (X_t . truth_t)^2  (sin^2 of
+ *               the quaternion angle).  Lets a Q/R sweep return its loss surface without storing
+ *               trajectories (the tuning workflow of the reference's README, knobs main_file.py:21-22).
  *   wahba_algo  POSEKF_WAHBA_*
  *   staging     POSEKF_STAGE_*
  */
@@ -82,7 +87,7 @@ int posekf_replay_f32(int64_t n_filters, int64_t n_steps, const float* streams, 
                       const float* dt, int dt_per_step, const float* acc_ref, const float* mag_ref,
                       const float* q_scale, const float* r_scale, float lpf_alpha_acc, float lpf_alpha_mag,
                       float* state_x, float* state_p, float* state_lpf, float* out_traj, uint8_t* out_flip,
-                      int wahba_algo, int staging, void* stream);
+                      const float* truth, float* loss_acc, int wahba_algo, int staging, void* stream);
 
 /* Same replay with HOST buffers: streams_host [T][9][N] is streamed through the device in time
  * chunks (double-buffered H2D copies overlapped with the filter kernel, state carried across
@@ -114,6 +119,37 @@ int posekf_wahba_f32(int64_t n, const float* acc_ref, const float* mag_ref, int 
                      const float* mag, const float* k_acc, const float* k_mag, float k_acc_s, float k_mag_s,
                      int weights_from_acc, float* out_rot, float* out_quat, int wahba_algo, int jacobi_sweeps,
                      void* stream);
+
+/* Comparison tracks of the tuning workflow (the curves the reference plots beside the filter,
+ * PKF/main_file.py:40-46,50-52 and Results/*.png): for N filters over T steps of the same stream
+ * layout as posekf_replay_f32,
+ *   out_gyro  [T][N][4]  gyro-only attitude: RK4 without correction from gyro_state (X=[1,0,0,0] when
+ *             gyro_state is NULL)   -- SRV/KalmanFilter.cpp:149 `Quarternion_Gyro_pure`
+ *   out_wahba [T][N][4]  Wahba-only attitude per sample, reference sign convention
+ *             -- PKF/main_file.py:40 getQuarternion(acc, mag, k_acc=.5, k_mag=.5); weights_from_acc != 0
+ *             selects the filter's own |acc_z|, 1-|acc_z| instead
+ *   gyro_state [4][N] in/out (carried across time chunks) or NULL.   Either output may be NULL. */
+int posekf_tracks_f32(int64_t n_filters, int64_t n_steps, const float* streams, int64_t n_streams, const float* dt,
+                      int dt_per_step, const float* acc_ref, const float* mag_ref, float k_acc, float k_mag,
+                      int weights_from_acc, float* gyro_state, float* out_gyro, float* out_wahba, int wahba_algo,
+                      void* stream);
+
+/* Raw-sensor pre-processing in front of the filter (online pipeline, SRV/Parser.cpp:229-267):
+ * per filter and gyro sample, linearly interpolate the accel / mag samples that bracket the gyro
+ * timestamp  y = (y2 - y1)/(t2 - t1)*(t3 - t1) + y1  (LinearInterpolationSensor, :259-267), normalise
+ * (NormalizeValues, :221-228), optionally low-pass with alpha (SRV/KalmanFilter.cpp:279-303; < 0 = off;
+ * then leave lpf off in posekf_replay_f32) and write the [T][9][N] stream of posekf_replay_f32.
+ *   gyro [T][3][N]; raw_prev, raw_next [T][6][N] (acc xyz, mag xyz before / after the gyro timestamp);
+ *   tspan [T][4][N] seconds: acc (t2-t1), acc (t3-t1), mag (t2-t1), mag (t3-t1) -- differenced from the
+ *   integer ns timestamps by the caller; lpf_state [6][N] in/out (start at 0) or NULL. */
+int posekf_preprocess_f32(int64_t n_filters, int64_t n_steps, const float* gyro, const float* raw_prev,
+                          const float* raw_next, const float* tspan, float lpf_alpha_acc, float lpf_alpha_mag,
+                          float* lpf_state, float* out_streams, void* stream);
+
+/* Quart2RPY over a stored trajectory: traj [M][4] (e.g. out_traj with M = T*N) -> degrees [M][3].
+ * PKF/UtilityFunctions.py:3-14; C++ twin SRV/KalmanFilter.cpp:194-233 (which clamps asin; this does not,
+ * like the Python oracle). */
+int posekf_traj2rpy_f32(int64_t m, const float* traj, float* out_rpy_deg, void* stream);
 
 /* Wahba.RotationMatrix2Quart for N matrices: rot [9][N] -> quat [4][N].   PKF/Wahba.py:20-47 */
 int posekf_rot2quat_f32(int64_t n, const float* rot, float* out_quat, void* stream);

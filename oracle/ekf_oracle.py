@@ -245,6 +245,21 @@ def lowpass_scalar(x, alpha, y0=None):
     return out
 
 
+def interpolate_normalise(y1, y2, t1, t2, t3):
+    """Linear interpolation of a sensor sample pair to the gyro timestamp, then normalisation.
+    (`Kalman Filter Server/PoseEstimator/Parser.cpp:259-267` LinearInterpolationSensor and :221-228
+    NormalizeValues, as sequenced by ExecuteKalmanFilter :229-242.)  The C++ server cannot be compiled
+    here (Eigen + Windows headers), so this restatement is NOT pinned by executing the reference:
+    parity for this pre-processing row is "unpinned" (formula restatement only).
+    y1, y2: [...,3]; t1, t2, t3: integer ns (broadcastable)."""
+    y1 = np.asarray(y1, dtype=np.float64)
+    y2 = np.asarray(y2, dtype=np.float64)
+    t1, t2, t3 = (np.asarray(t, dtype=np.float64)[..., None] for t in (t1, t2, t3))
+    v = (y2 - y1) / (t2 - t1) * (t3 - t1) + y1
+    den = np.sqrt(v[..., 0] * v[..., 0] + v[..., 1] * v[..., 1] + v[..., 2] * v[..., 2])
+    return v / den[..., None]
+
+
 # --------------------------------------------------------------------------------------------
 # Batched (vectorised over filters) float64 form: the fast checker
 # --------------------------------------------------------------------------------------------

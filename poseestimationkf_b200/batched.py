@@ -84,6 +84,7 @@ class ReplayState:
     p: torch.Tensor
     r: object = 0.1
     lpf: torch.Tensor | None = None
+    loss: torch.Tensor | None = None     # [N] accumulated tuning objective (see replay(truth=...))
 
     @staticmethod
     def initial(n_filters: int, device, r=0.1, with_lpf: bool = False, P0: torch.Tensor | None = None) -> "ReplayState":
@@ -136,14 +137,17 @@ def _per_filter(v, n, device):
 def replay(streams: torch.Tensor, acc_ref: torch.Tensor, mag_ref: torch.Tensor, *, dt, q=1.0, r=0.1,
            state: ReplayState | None = None, n_filters: int | None = None, lpf_alpha_acc: float | None = None,
            lpf_alpha_mag: float | None = None, out_traj: torch.Tensor | None = None, store_trajectory: bool = False,
-           store_flips: bool = False, wahba: str = "qr2", staging: str = "auto"):
+           store_flips: bool = False, truth: torch.Tensor | None = None, loss: torch.Tensor | None = None,
+           wahba: str = "qr2", staging: str = "auto"):
     """Run T Prediction+Correction steps for N filters in one kernel launch.
 
     streams [T,9,Ns]; acc_ref, mag_ref [3,Ns]; dt: float seconds or [T] float32 CUDA tensor;
     q, r: floats or [N] tensors (Q=q*I3, R=r*I4).  `n_filters` > Ns replays every trajectory
     N/Ns times (filter n reads column n % Ns) -- the Q/R sweep layout.  `state` is updated in place
-    (created with the reference's initial values when None).  Returns (state, traj [T,N,4] or None,
-    flips [T,N] uint8 or None)."""
+    (created with the reference's initial values when None).  `truth` [T,Ns,4] enables the on-device
+    tuning objective: `loss` [N] (created zeroed when None; pass it back in for chunked replays) is
+    incremented by sum_t 1-(X_t.truth_t)^2 and is available as `state.loss`.
+    Returns (state, traj [T,N,4] or None, flips [T,N] uint8 or None)."""
     _require_cuda(streams, acc_ref, mag_ref, out_traj)
     if streams.dim() != 3 or streams.shape[1] != 9:
         raise ValueError("streams must be [T, 9, Ns]")
@@ -176,13 +180,20 @@ def replay(streams: torch.Tensor, acc_ref: torch.Tensor, mag_ref: torch.Tensor, 
     if out_traj is not None and out_traj.shape != (T, N, 4):
         raise ValueError("out_traj must be [T, N, 4]")
     flips = torch.empty((T, N), dtype=torch.uint8, device=dev) if store_flips else None
+    if truth is not None:
+        _require_cuda(truth, loss)
+        if truth.shape != (T, Ns, 4):
+            raise ValueError("truth must be [T, Ns, 4]")
+        if loss is None:
+            loss = torch.zeros((N,), dtype=torch.float32, device=dev)
+        state.loss = loss
     with torch.cuda.device(dev):
         rc = _lib.load().posekf_replay_f32(
             N, T, _ptr(streams), Ns, _ptr(dt_t), per_step, _ptr(acc_ref), _ptr(mag_ref), _ptr(q_t), _ptr(r_t),
             -1.0 if lpf_alpha_acc is None else float(lpf_alpha_acc),
             -1.0 if lpf_alpha_mag is None else float(lpf_alpha_mag),
-            _ptr(state.x), _ptr(state.p), _ptr(state.lpf), _ptr(out_traj), _ptr(flips),
-            _lib.WAHBA[wahba], _lib.STAGING[staging], _stream())
+            _ptr(state.x), _ptr(state.p), _ptr(state.lpf), _ptr(out_traj), _ptr(flips), _ptr(truth),
+            _ptr(loss if truth is not None else None), _lib.WAHBA[wahba], _lib.STAGING[staging], _stream())
     _lib.check(rc, "posekf_replay_f32")
     return state, out_traj, flips
 
@@ -239,6 +250,64 @@ def wahba(acc_ref, mag_ref, acc, mag, *, k_acc=None, k_mag=None, weights_from_ac
                                           _lib.WAHBA[algo], int(jacobi_sweeps), _stream())
     _lib.check(rc, "posekf_wahba_f32")
     return R, qt
+
+
+def tracks(streams, acc_ref, mag_ref, *, dt, n_filters=None, k_acc=0.5, k_mag=0.5, weights_from_acc=False,
+           gyro_state=None, want_gyro=True, want_wahba=True, algo: str = "qr2"):
+    """Gyro-only and Wahba-only comparison tracks (the curves main_file.py plots beside the filter).
+    Returns (gyro [T,N,4] or None, wahba [T,N,4] or None, gyro_state [4,N])."""
+    _require_cuda(streams, acc_ref, mag_ref, gyro_state)
+    T, _, Ns = streams.shape
+    N = Ns if n_filters is None else int(n_filters)
+    dev = streams.device
+    if isinstance(dt, torch.Tensor):
+        _require_cuda(dt)
+        dt_t, per_step = dt, 1
+    else:
+        dt_t, per_step = _scalar_tensor(dt, dev), 0
+    if gyro_state is None:
+        gyro_state = torch.zeros((4, N), dtype=torch.float32, device=dev)
+        gyro_state[0] = 1.0
+    og = torch.empty((T, N, 4), dtype=torch.float32, device=dev) if want_gyro else None
+    ow = torch.empty((T, N, 4), dtype=torch.float32, device=dev) if want_wahba else None
+    with torch.cuda.device(dev):
+        rc = _lib.load().posekf_tracks_f32(N, T, _ptr(streams), Ns, _ptr(dt_t), per_step, _ptr(acc_ref), _ptr(mag_ref),
+                                           float(k_acc), float(k_mag), int(weights_from_acc), _ptr(gyro_state), _ptr(og),
+                                           _ptr(ow), _lib.WAHBA[algo], _stream())
+    _lib.check(rc, "posekf_tracks_f32")
+    return og, ow, gyro_state
+
+
+def preprocess(gyro, raw_prev, raw_next, tspan, *, lpf_alpha_acc=None, lpf_alpha_mag=None, lpf_state=None, out=None):
+    """Raw-sensor pre-processing (interpolate accel/mag to the gyro timestamp, normalise, optional
+    low-pass): gyro [T,3,N], raw_prev/raw_next [T,6,N], tspan [T,4,N] seconds -> streams [T,9,N]
+    (and the low-pass state [6,N])."""
+    _require_cuda(gyro, raw_prev, raw_next, tspan, lpf_state, out)
+    T, _, N = gyro.shape
+    if raw_prev.shape != (T, 6, N) or raw_next.shape != (T, 6, N) or tspan.shape != (T, 4, N):
+        raise ValueError("raw_prev/raw_next must be [T,6,N] and tspan [T,4,N]")
+    use_lpf = lpf_alpha_acc is not None or lpf_alpha_mag is not None
+    if use_lpf and lpf_state is None:
+        lpf_state = torch.zeros((6, N), dtype=torch.float32, device=gyro.device)
+    if out is None:
+        out = torch.empty((T, 9, N), dtype=torch.float32, device=gyro.device)
+    with torch.cuda.device(gyro.device):
+        rc = _lib.load().posekf_preprocess_f32(N, T, _ptr(gyro), _ptr(raw_prev), _ptr(raw_next), _ptr(tspan),
+                                               -1.0 if lpf_alpha_acc is None else float(lpf_alpha_acc),
+                                               -1.0 if lpf_alpha_mag is None else float(lpf_alpha_mag),
+                                               _ptr(lpf_state), _ptr(out), _stream())
+    _lib.check(rc, "posekf_preprocess_f32")
+    return out, lpf_state
+
+
+def traj2rpy(traj):
+    """Quart2RPY over a stored trajectory [..., 4] -> degrees [..., 3]."""
+    _require_cuda(traj)
+    out = torch.empty(traj.shape[:-1] + (3,), dtype=torch.float32, device=traj.device)
+    with torch.cuda.device(traj.device):
+        _lib.check(_lib.load().posekf_traj2rpy_f32(traj.numel() // 4, _ptr(traj), _ptr(out), _stream()),
+                   "posekf_traj2rpy_f32")
+    return out
 
 
 def rot2quat(rot):

@@ -113,6 +113,8 @@ struct ReplayParams {
   float* state_lpf;
   float* out_traj;
   uint8_t* out_flip;
+  const float* truth;   // [T][Ns][4] reference track for the tuning objective, or null
+  float* loss_acc;      // [N] in/out: sum over steps of 1 - (x . truth)^2
 };
 
 struct FilterRegs {
@@ -150,9 +152,26 @@ template <bool LPF> __device__ __forceinline__ void store_filter(const ReplayPar
 }
 
 // One filter step + optional outputs.  AUX = the launch has a trajectory and/or flip output.
+struct AuxPtrs {
+  float4* traj;          // this filter's slot in out_traj, advanced by N per step
+  uint8_t* flips;
+  const float4* truth;   // this filter's column in the reference track, advanced by Ns per step
+  float loss;
+};
+
+template <bool AUX> __device__ __forceinline__ AuxPtrs make_aux(const ReplayParams& p, int64_t n, int64_t col, bool valid) {
+  AuxPtrs a = {nullptr, nullptr, nullptr, 0.f};
+  if (AUX && valid) {
+    if (p.out_traj) a.traj = reinterpret_cast<float4*>(p.out_traj) + n;
+    if (p.out_flip) a.flips = p.out_flip + n;
+    if (p.truth) { a.truth = reinterpret_cast<const float4*>(p.truth) + col; a.loss = p.loss_acc[n]; }
+  }
+  return a;
+}
+
 template <int ALGO, bool LPF, bool AUX>
 __device__ __forceinline__ void filter_step(const ReplayParams& p, FilterRegs& f, const float (&s)[kChannels], float h,
-                                            float4* __restrict__& traj, uint8_t* __restrict__& flips) {
+                                            AuxPtrs& aux) {
   Vec3<float> w = {s[0], s[1], s[2]}, a = {s[3], s[4], s[5]}, m = {s[6], s[7], s[8]};
   if (LPF) {   // SRV/KalmanFilter.cpp:285,298 -- filtered values feed Wahba, not renormalised
     if (p.alpha_acc >= 0.f) { lowpass<float>(f.la, a, p.alpha_acc, 1.f - p.alpha_acc); a = f.la; }
@@ -161,12 +180,19 @@ __device__ __forceinline__ void filter_step(const ReplayParams& p, FilterRegs& f
   bool flip;
   ekf_step<float, ALGO, AUX>(f.x, f.P, f.fc, w, a, m, h, flip);
   if (AUX) {
-    if (traj) {   // [T][N][4]: one 16-byte store per filter-step, consecutive filters consecutive
-      asm volatile("st.global.cs.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(traj), "f"(f.x.w), "f"(f.x.x), "f"(f.x.y), "f"(f.x.z)
+    if (aux.traj) {   // [T][N][4]: one 16-byte store per filter-step, consecutive filters consecutive
+      asm volatile("st.global.cs.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(aux.traj), "f"(f.x.w), "f"(f.x.x), "f"(f.x.y),
+                   "f"(f.x.z)
                    : "memory");
-      traj += p.N;
+      aux.traj += p.N;
     }
-    if (flips) { *flips = flip ? 1 : 0; flips += p.N; }
+    if (aux.flips) { *aux.flips = flip ? 1 : 0; aux.flips += p.N; }
+    if (aux.truth) {  // tuning objective: sin^2 of the angle between the estimate and the reference track
+      const float4 qt = __ldg(aux.truth);
+      aux.truth += p.Ns;
+      const float d = fmaf(f.x.z, qt.w, fmaf(f.x.y, qt.z, fmaf(f.x.x, qt.y, f.x.w * qt.x)));
+      aux.loss += fmaf(-d, d, 1.f);
+    }
   }
 }
 
@@ -182,8 +208,7 @@ __global__ void __launch_bounds__(kThreads, ALGO == WAHBA_JACOBI ? 4 : kMinCtasP
   const int64_t col = (Ns == p.N) ? n : (n % Ns);
   FilterRegs f;
   load_filter<LPF>(p, n, col, f);
-  float4* traj = (AUX && p.out_traj) ? reinterpret_cast<float4*>(p.out_traj) + n : nullptr;
-  uint8_t* flips = (AUX && p.out_flip) ? p.out_flip + n : nullptr;
+  AuxPtrs aux = make_aux<AUX>(p, n, col, true);
   const float* s = p.streams + col;
   const int64_t step_stride = kChannels * Ns;
   float cur[kChannels], nxt[kChannels];
@@ -196,11 +221,12 @@ __global__ void __launch_bounds__(kThreads, ALGO == WAHBA_JACOBI ? 4 : kMinCtasP
 #pragma unroll
     for (int c = 0; c < kChannels; ++c) nxt[c] = ldg_stream(s + c * Ns);
     const float h = p.dt_per_step ? __ldg(p.dt + t) : dt0;
-    filter_step<ALGO, LPF, AUX>(p, f, cur, h, traj, flips);
+    filter_step<ALGO, LPF, AUX>(p, f, cur, h, aux);
 #pragma unroll
     for (int c = 0; c < kChannels; ++c) cur[c] = nxt[c];
   }
   store_filter<LPF>(p, n, f);
+  if (AUX && aux.truth) p.loss_acc[n] = aux.loss;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -248,8 +274,7 @@ __global__ void __launch_bounds__(kThreads, kMinCtasPerSm)
 
   FilterRegs f;
   if (valid) load_filter<LPF>(p, n, (int64_t)col0 + tid, f);
-  float4* traj = (AUX && valid && p.out_traj) ? reinterpret_cast<float4*>(p.out_traj) + n : nullptr;
-  uint8_t* flips = (AUX && valid && p.out_flip) ? p.out_flip + n : nullptr;
+  AuxPtrs aux = make_aux<AUX>(p, n, (int64_t)col0 + tid, valid);
   const float dt0 = p.dt[0];
 
   int stage = 0;
@@ -273,7 +298,7 @@ __global__ void __launch_bounds__(kThreads, kMinCtasPerSm)
 #pragma unroll
           for (int c = 0; c < kChannels; ++c) s[c] = sm.tile[stage][tt][c][tid];
           const float h = p.dt_per_step ? __ldg(p.dt + k * kTmaSteps + tt) : dt0;
-          filter_step<ALGO, LPF, AUX>(p, f, s, h, traj, flips);
+          filter_step<ALGO, LPF, AUX>(p, f, s, h, aux);
         }
       }
     }
@@ -282,6 +307,7 @@ __global__ void __launch_bounds__(kThreads, kMinCtasPerSm)
     if (++stage == kTmaStages) { stage = 0; parity ^= 1; }
   }
   if (valid) store_filter<LPF>(p, n, f);
+  if (AUX && valid && aux.truth) p.loss_acc[n] = aux.loss;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -349,6 +375,125 @@ template <int ALGO> __global__ void __launch_bounds__(256) wahba_kernel(const Wa
     stg_stream(p.out_quat + n, q.w); stg_stream(p.out_quat + N + n, q.x);
     stg_stream(p.out_quat + 2 * N + n, q.y); stg_stream(p.out_quat + 3 * N + n, q.z);
   }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Comparison tracks of the tuning workflow (what Results/*.png overlays): the gyro-only attitude
+// (RK4 without correction: SRV/KalmanFilter.cpp:149, `Quarternion_Gyro_pure`) and the Wahba-only
+// attitude per sample (PKF/main_file.py:40: getQuarternion(acc, mag, .5, .5), raw sign convention).
+// ---------------------------------------------------------------------------------------------
+struct TracksParams {
+  int64_t N, T, Ns;
+  const float *streams, *dt;
+  int dt_per_step;
+  const float *acc_ref, *mag_ref;
+  float k_acc, k_mag;
+  int weights_from_acc;
+  float* gyro_state;   // [4][N] in/out, or null
+  float* out_gyro;     // [T][N][4] or null
+  float* out_wahba;    // [T][N][4] or null
+};
+
+template <int ALGO> __global__ void __launch_bounds__(128) tracks_kernel(const TracksParams p) {
+  const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= p.N) return;
+  const int64_t N = p.N, Ns = p.Ns, col = (Ns == N) ? n : (n % Ns);
+  Vec3<float> ra = {p.acc_ref[col], p.acc_ref[Ns + col], p.acc_ref[2 * Ns + col]};
+  Vec3<float> rm = {p.mag_ref[col], p.mag_ref[Ns + col], p.mag_ref[2 * Ns + col]};
+  const RefFrame<float> E = frame_from_pair<float>(ra, rm);
+  Quat<float> g = {1.f, 0.f, 0.f, 0.f};
+  if (p.gyro_state) g = {p.gyro_state[n], p.gyro_state[N + n], p.gyro_state[2 * N + n], p.gyro_state[3 * N + n]};
+  const float* s = p.streams + col;
+  float4* og = p.out_gyro ? reinterpret_cast<float4*>(p.out_gyro) + n : nullptr;
+  float4* ow = p.out_wahba ? reinterpret_cast<float4*>(p.out_wahba) + n : nullptr;
+  const float dt0 = p.dt[0];
+  for (int64_t t = 0; t < p.T; ++t, s += kChannels * Ns) {
+    const float h = p.dt_per_step ? __ldg(p.dt + t) : dt0;
+    if (og || p.gyro_state) {
+      Vec3<float> hw = {0.5f * ldg_stream(s), 0.5f * ldg_stream(s + Ns), 0.5f * ldg_stream(s + 2 * Ns)};
+      g = rk4_step<float>(g, hw, h);
+      if (og) { *og = make_float4(g.w, g.x, g.y, g.z); og += N; }
+    }
+    if (ow) {
+      Vec3<float> a = {ldg_stream(s + 3 * Ns), ldg_stream(s + 4 * Ns), ldg_stream(s + 5 * Ns)};
+      Vec3<float> m = {ldg_stream(s + 6 * Ns), ldg_stream(s + 7 * Ns), ldg_stream(s + 8 * Ns)};
+      float ka = p.k_acc, km = p.k_mag;
+      if (p.weights_from_acc) { ka = fabsf(a.z); km = 1.f - ka; }
+      Mat3<float> R = (ALGO == WAHBA_QR2) ? wahba_qr2<float>(E, a, m, ka, km) : wahba_jacobi<float>(ra, rm, a, m, ka, km, 6);
+      Quat<float> q = rotation_to_quat_ref<float>(R);
+      *ow = make_float4(q.w, q.x, q.y, q.z);
+      ow += N;
+    }
+  }
+  if (p.gyro_state) { p.gyro_state[n] = g.w; p.gyro_state[N + n] = g.x; p.gyro_state[2 * N + n] = g.y; p.gyro_state[3 * N + n] = g.z; }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Raw-sensor pre-processing of the online pipeline (the step in front of the filter): linear
+// interpolation of the accel / mag samples that bracket the gyro timestamp, normalisation, and the
+// optional alpha low-pass -- SRV/Parser.cpp:229-267 (ExecuteKalmanFilter, LinearInterpolationSensor),
+// :221-228 (NormalizeValues), SRV/KalmanFilter.cpp:279-303 (low-pass inside Set*Measurements).
+// Writes the [T][9][N] stream the replay kernel consumes.
+// ---------------------------------------------------------------------------------------------
+struct PreprocessParams {
+  int64_t N, T;
+  const float* gyro;        // [T][3][N]
+  const float* raw_prev;    // [T][6][N]  acc xyz, mag xyz : sample before the gyro timestamp (y1)
+  const float* raw_next;    // [T][6][N]  sample after (y2)
+  const float* tspan;       // [T][4][N]  seconds: acc (t2-t1), acc (t3-t1), mag (t2-t1), mag (t3-t1)
+  float alpha_acc, alpha_mag;
+  float* lpf_state;         // [6][N] in/out or null
+  float* out_streams;       // [T][9][N]
+};
+
+__global__ void __launch_bounds__(256) preprocess_kernel(const PreprocessParams p) {
+  const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= p.N) return;
+  const int64_t N = p.N;
+  const bool lpa = p.alpha_acc >= 0.f, lpm = p.alpha_mag >= 0.f;
+  Vec3<float> la = {0.f, 0.f, 0.f}, lm = {0.f, 0.f, 0.f};
+  if (p.lpf_state) {
+    la = {p.lpf_state[n], p.lpf_state[N + n], p.lpf_state[2 * N + n]};
+    lm = {p.lpf_state[3 * N + n], p.lpf_state[4 * N + n], p.lpf_state[5 * N + n]};
+  }
+  for (int64_t t = 0; t < p.T; ++t) {
+    const float* y1 = p.raw_prev + t * 6 * N + n;
+    const float* y2 = p.raw_next + t * 6 * N + n;
+    const float* ts = p.tspan + t * 4 * N + n;
+    float* o = p.out_streams + t * 9 * N + n;
+    const float* g = p.gyro + t * 3 * N + n;
+    o[0] = ldg_stream(g); o[N] = ldg_stream(g + N); o[2 * N] = ldg_stream(g + 2 * N);
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {                      // s = 0 accel, 1 mag
+      const float t21 = ldg_stream(ts + (2 * s) * N), t31 = ldg_stream(ts + (2 * s + 1) * N);
+      float v[3];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const float a = ldg_stream(y1 + (3 * s + c) * N), b = ldg_stream(y2 + (3 * s + c) * N);
+        v[c] = (b - a) / t21 * t31 + a;                // Parser.cpp:264, same operation order
+      }
+      const float den = sqrtf(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);     // Parser.cpp:223-227
+      Vec3<float> u = {v[0] / den, v[1] / den, v[2] / den};
+      if (s == 0 && lpa) { lowpass<float>(la, u, p.alpha_acc, 1.f - p.alpha_acc); u = la; }
+      if (s == 1 && lpm) { lowpass<float>(lm, u, p.alpha_mag, 1.f - p.alpha_mag); u = lm; }
+      o[(3 + 3 * s) * N] = u.x; o[(4 + 3 * s) * N] = u.y; o[(5 + 3 * s) * N] = u.z;
+    }
+  }
+  if (p.lpf_state) {
+    p.lpf_state[n] = la.x; p.lpf_state[N + n] = la.y; p.lpf_state[2 * N + n] = la.z;
+    p.lpf_state[3 * N + n] = lm.x; p.lpf_state[4 * N + n] = lm.y; p.lpf_state[5 * N + n] = lm.z;
+  }
+}
+
+// trajectory [M][4] -> roll/pitch/yaw degrees [M][3]   (PKF/UtilityFunctions.py:3-14 per row)
+__global__ void __launch_bounds__(256) traj2rpy_kernel(int64_t M, const float4* __restrict__ q, float* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= M) return;
+  const float4 v = q[i];
+  const float w = v.x, x = v.y, y = v.z, z = v.w, k = 57.29577951308232f;
+  out[3 * i] = atan2f(2.f * (w * x + y * z), 1.f - 2.f * (x * x + y * y)) * k;
+  out[3 * i + 1] = asinf(2.f * (w * y - z * x)) * k;
+  out[3 * i + 2] = atan2f(2.f * (w * z + x * y), 1.f - 2.f * (y * y + z * z)) * k;
 }
 
 __global__ void __launch_bounds__(256) rot2quat_kernel(int64_t N, const float* __restrict__ rot, float* __restrict__ out) {
@@ -646,7 +791,7 @@ template <int ALGO, bool LPF, bool AUX> int launch_replay(const ReplayParams& p,
 }
 
 template <int ALGO, bool LPF> int launch_replay_aux(const ReplayParams& p, bool use_tma, cudaStream_t st) {
-  const bool aux = p.out_traj != nullptr || p.out_flip != nullptr;
+  const bool aux = p.out_traj != nullptr || p.out_flip != nullptr || p.truth != nullptr;
   return aux ? launch_replay<ALGO, LPF, true>(p, use_tma, st) : launch_replay<ALGO, LPF, false>(p, use_tma, st);
 }
 
@@ -676,7 +821,8 @@ const char* posekf_version(void) { return "posekf_b200 0.1 sm_100a"; }
 int posekf_replay_f32(int64_t n_filters, int64_t n_steps, const float* streams, int64_t n_streams, const float* dt,
                       int dt_per_step, const float* acc_ref, const float* mag_ref, const float* q_scale,
                       const float* r_scale, float lpf_alpha_acc, float lpf_alpha_mag, float* state_x, float* state_p,
-                      float* state_lpf, float* out_traj, uint8_t* out_flip, int wahba_algo, int staging, void* stream) {
+                      float* state_lpf, float* out_traj, uint8_t* out_flip, const float* truth, float* loss_acc,
+                      int wahba_algo, int staging, void* stream) {
   if (n_filters < 0 || n_steps < 0 || n_streams <= 0 && n_filters > 0) return POSEKF_EINVAL;
   if (n_filters == 0 || n_steps == 0) return 0;
   if (!streams || !dt || !acc_ref || !mag_ref || !q_scale || !r_scale || !state_x || !state_p) return POSEKF_EINVAL;
@@ -685,11 +831,13 @@ int posekf_replay_f32(int64_t n_filters, int64_t n_steps, const float* streams, 
   if (lpf && !state_lpf) return POSEKF_EINVAL;
   if ((n_filters + kThreads - 1) / kThreads > 0x7fffffffLL || n_steps > 0x7fffffffLL) return POSEKF_EINVAL;
   if (out_traj && (reinterpret_cast<uintptr_t>(out_traj) & 15) != 0) return POSEKF_EALIGN;
+  if (truth && (!loss_acc || (reinterpret_cast<uintptr_t>(truth) & 15) != 0)) return truth && !loss_acc ? POSEKF_EINVAL : POSEKF_EALIGN;
   ReplayParams p;
   p.N = n_filters; p.T = n_steps; p.Ns = n_streams; p.streams = streams; p.dt = dt; p.dt_per_step = dt_per_step;
   p.acc_ref = acc_ref; p.mag_ref = mag_ref; p.q_scale = q_scale; p.r_scale = r_scale;
   p.alpha_acc = lpf_alpha_acc; p.alpha_mag = lpf_alpha_mag;
   p.state_x = state_x; p.state_p = state_p; p.state_lpf = state_lpf; p.out_traj = out_traj; p.out_flip = out_flip;
+  p.truth = truth; p.loss_acc = loss_acc;
   return replay_dispatch(p, wahba_algo, staging, (cudaStream_t)stream);
 }
 
@@ -795,8 +943,8 @@ int posekf_replay_host_f32(int64_t N, int64_t T, const float* streams_host, floa
     TRY(cudaStreamWaitEvent(s_comp, ev_in[b], 0));
     if (traj && c >= 2) TRY(cudaStreamWaitEvent(s_comp, ev_tfree[b], 0));  // D2H of chunk c-2 done with d_traj[b]
     rc = posekf_replay_f32(N, tc, d_in[b], N, d_dt, 0, d_ref, d_ref + 3 * N, d_qr, d_qr + N, lpf_alpha_acc,
-                           lpf_alpha_mag, d_x, d_p, d_lpf, traj ? d_traj[b] : nullptr, nullptr, wahba_algo,
-                           POSEKF_STAGE_AUTO, s_comp);
+                           lpf_alpha_mag, d_x, d_p, d_lpf, traj ? d_traj[b] : nullptr, nullptr, nullptr, nullptr,
+                           wahba_algo, POSEKF_STAGE_AUTO, s_comp);
     if (rc != 0) { cleanup(); return rc; }
     TRY(cudaEventRecord(ev_free[b], s_comp));
     if (traj) {
@@ -834,6 +982,48 @@ int posekf_wahba_f32(int64_t n, const float* acc_ref, const float* mag_ref, int 
   if (wahba_algo == POSEKF_WAHBA_QR2) wahba_kernel<WAHBA_QR2><<<blocks_for(n, 256), 256, 0, st>>>(p);
   else if (wahba_algo == POSEKF_WAHBA_JACOBI) wahba_kernel<WAHBA_JACOBI><<<blocks_for(n, 256), 256, 0, st>>>(p);
   else return POSEKF_EINVAL;
+  return launch_status();
+}
+
+int posekf_tracks_f32(int64_t n_filters, int64_t n_steps, const float* streams, int64_t n_streams, const float* dt,
+                      int dt_per_step, const float* acc_ref, const float* mag_ref, float k_acc, float k_mag,
+                      int weights_from_acc, float* gyro_state, float* out_gyro, float* out_wahba, int wahba_algo,
+                      void* stream) {
+  if (n_filters < 0 || n_steps < 0) return POSEKF_EINVAL;
+  if (n_filters == 0 || n_steps == 0) return 0;
+  if (!streams || !dt || n_streams <= 0 || n_streams > n_filters || (n_filters % n_streams) != 0) return POSEKF_EINVAL;
+  if (!out_gyro && !out_wahba && !gyro_state) return POSEKF_EINVAL;
+  if (out_wahba && (!acc_ref || !mag_ref)) return POSEKF_EINVAL;
+  if (((reinterpret_cast<uintptr_t>(out_gyro) | reinterpret_cast<uintptr_t>(out_wahba)) & 15) != 0) return POSEKF_EALIGN;
+  static const float zero3[3] = {0.f, 0.f, 0.f};
+  (void)zero3;
+  TracksParams p{n_filters, n_steps, n_streams, streams, dt, dt_per_step, acc_ref ? acc_ref : streams,
+                 mag_ref ? mag_ref : streams, k_acc, k_mag, weights_from_acc, gyro_state, out_gyro, out_wahba};
+  cudaStream_t st = (cudaStream_t)stream;
+  if (wahba_algo == POSEKF_WAHBA_QR2) tracks_kernel<WAHBA_QR2><<<blocks_for(n_filters, 128), 128, 0, st>>>(p);
+  else if (wahba_algo == POSEKF_WAHBA_JACOBI) tracks_kernel<WAHBA_JACOBI><<<blocks_for(n_filters, 128), 128, 0, st>>>(p);
+  else return POSEKF_EINVAL;
+  return launch_status();
+}
+
+int posekf_preprocess_f32(int64_t n_filters, int64_t n_steps, const float* gyro, const float* raw_prev,
+                          const float* raw_next, const float* tspan, float lpf_alpha_acc, float lpf_alpha_mag,
+                          float* lpf_state, float* out_streams, void* stream) {
+  if (n_filters < 0 || n_steps < 0) return POSEKF_EINVAL;
+  if (n_filters == 0 || n_steps == 0) return 0;
+  if (!gyro || !raw_prev || !raw_next || !tspan || !out_streams) return POSEKF_EINVAL;
+  if ((lpf_alpha_acc >= 0.f || lpf_alpha_mag >= 0.f) && !lpf_state) return POSEKF_EINVAL;
+  PreprocessParams p{n_filters, n_steps, gyro, raw_prev, raw_next, tspan, lpf_alpha_acc, lpf_alpha_mag, lpf_state, out_streams};
+  preprocess_kernel<<<blocks_for(n_filters, 256), 256, 0, (cudaStream_t)stream>>>(p);
+  return launch_status();
+}
+
+int posekf_traj2rpy_f32(int64_t m, const float* traj, float* out_rpy_deg, void* stream) {
+  if (m < 0) return POSEKF_EINVAL;
+  if (m == 0) return 0;
+  if (!traj || !out_rpy_deg) return POSEKF_EINVAL;
+  if ((reinterpret_cast<uintptr_t>(traj) & 15) != 0) return POSEKF_EALIGN;
+  traj2rpy_kernel<<<blocks_for(m, 256), 256, 0, (cudaStream_t)stream>>>(m, reinterpret_cast<const float4*>(traj), out_rpy_deg);
   return launch_status();
 }
 

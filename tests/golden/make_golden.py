@@ -161,7 +161,44 @@ def rk4_known_answer():
     return res
 
 
+def log_format():
+    """A log in the server's text format (written by poseestimationkf_b200.logio from a short reference
+    run) parsed by THE REFERENCE'S OWN READER: ReadFile.getData opens a hard-coded Windows path
+    (ReadFile.py:24), so `open` is redirected for that one call."""
+    import builtins
+    from poseestimationkf_b200 import logio
+    T = 40
+    imu = make_imu(1, T, seed=55, sigma=0.01)
+    S = imu.streams.numpy().astype(np.float64)[:, :, 0]
+    a0, m0 = imu.acc_ref.numpy()[:, 0].astype(np.float64), imu.mag_ref.numpy()[:, 0].astype(np.float64)
+    t0 = 123456789000
+    t_ns = t0 + (np.arange(T) + 1) * 10_000_000
+    X, _, Y, _ = drive(np.concatenate([[t0], t_ns]), S[:, 0:3], S[:, 3:6], S[:, 6:9], a0, m0, 1.0, 0.1)
+    qg = []
+    q = np.asarray([1.0, 0.0, 0.0, 0.0])
+    for i in range(T):
+        q = KalmanFilter.RungeKutta4(q, 10_000_000, S[i, 0:3])
+        qg.append(q)
+    path = os.path.join(HERE, "sample_log.txt")
+    logio.write_log(path, acc_0=a0, mag_0=m0, t0_ns=t0, t_ns=t_ns, gyro=S[:, 0:3], mag_1=S[:, 6:9], acc_1=S[:, 3:6],
+                    x_k=X, wahba_quart=Y, q_gyro=qg)
+    import ReadFile                                   # the reference's reader
+    real_open = builtins.open
+
+    def redirected(name, *a, **k):
+        return real_open(path if str(name).endswith("KalmanFilter.txt") else name, *a, **k)
+    builtins.open = redirected
+    try:
+        g = ReadFile.getData()
+    finally:
+        builtins.open = real_open
+    np.savez_compressed(os.path.join(HERE, "log_parsed.npz"), mag_0=g.mag_0, mag_1=g.mag_1, acc_0=g.acc_0, acc_1=g.acc_1,
+                        gyro=g.gyro, timestamp=g.timestamp, quart_wahba=g.quart_wahba, quart_xk=g.quart_xk,
+                        quart_gyro=g.quart_gyro, X_full_precision=X)
+
+
 if __name__ == "__main__":
+    log_format()
     trajectories()
     wahba_cases()
     stepwise()

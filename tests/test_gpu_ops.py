@@ -158,3 +158,87 @@ def test_compat_modules_run_the_reference_loop(golden_traj, cuda):
         sys.path.remove(compat.PATH)
         for m in ("ExtendedKalmanFilter", "Wahba", "UtilityFunctions", "_bridge"):
             sys.modules.pop(m, None)
+
+
+def test_comparison_tracks_and_tuning_objective(cuda):
+    """gyro-only + Wahba-only tracks, RPY of a trajectory, on-device loss of a sweep."""
+    from poseestimationkf_b200.synth import make_imu
+    Ns, T = 256, 200
+    imu = make_imu(Ns, T, seed=31, sigma=0.01, device=cuda, keep_truth=True)
+    gyro, wah, gstate = B.tracks(imu.streams, imu.acc_ref, imu.mag_ref, dt=imu.dt)
+    S = imu.streams.cpu().numpy().astype(np.float64)
+    a0, m0 = imu.acc_ref.cpu().numpy().T.astype(np.float64), imu.mag_ref.cpu().numpy().T.astype(np.float64)
+    # oracle: pure RK4 chain and per-sample getQuarternion(acc, mag, .5, .5)  (main_file.py:40)
+    for n in (0, 100, 255):
+        q = np.asarray([1.0, 0.0, 0.0, 0.0])
+        w = O.OracleWahba(a0[n], m0[n])
+        for t in range(T):
+            q = O.rk4(q, 10 ** 7, S[t, 0:3, n])
+            assert O.quat_angle(gyro[t, n].cpu().numpy(), q) < 1e-5
+            yw = w.quaternion(S[t, 3:6, n], S[t, 6:9, n], 0.5, 0.5)
+            got = wah[t, n].cpu().numpy()
+            assert O.quat_angle(got, yw) < 2e-6 and np.dot(got, yw) > 0       # same raw sign convention
+    assert torch.equal(gstate.t().contiguous(), gyro[-1])
+    # chunked gyro track carries its state
+    g1, _, st = B.tracks(imu.streams[:77].contiguous(), imu.acc_ref, imu.mag_ref, dt=imu.dt, want_wahba=False)
+    g2, _, _ = B.tracks(imu.streams[77:].contiguous(), imu.acc_ref, imu.mag_ref, dt=imu.dt, want_wahba=False, gyro_state=st)
+    assert torch.equal(torch.cat([g1, g2]), gyro)
+    # RPY of a stored trajectory
+    rpy = B.traj2rpy(wah)
+    ref = np.stack([O.quat_to_rpy_deg(wah[5, n].cpu().numpy().astype(np.float64)) for n in range(8)])
+    np.testing.assert_allclose(rpy[5, :8].cpu().numpy(), ref, atol=5e-3)
+    # tuning objective of a small (Q,R) grid against ground truth, no trajectory stored
+    truth = imu.q_true.permute(0, 2, 1).to(torch.float32).contiguous()           # [T, Ns, 4]
+    grid = [(q, r) for q in (0.01, 1.0, 100.0) for r in (0.01, 0.1, 10.0)]
+    G = len(grid)
+    q_t = _dev(np.repeat([q for q, _ in grid], Ns), cuda)
+    r_t = _dev(np.repeat([r for _, r in grid], Ns), cuda)
+    st, traj, _ = B.replay(imu.streams, imu.acc_ref, imu.mag_ref, dt=imu.dt, q=q_t, r=r_t, n_filters=G * Ns, truth=truth,
+                           store_trajectory=True)
+    d = (traj.reshape(T, G, Ns, 4).double() * truth.double()[:, None]).sum(-1)
+    want = (1 - d * d).sum(0).reshape(-1)
+    torch.testing.assert_close(st.loss.double(), want, rtol=2e-3, atol=1e-7)
+    # same loss without storing the trajectory, accumulated over two time chunks
+    st2 = B.ReplayState.initial(G * Ns, cuda, r=r_t)
+    loss = None
+    for t0, t1 in ((0, 90), (90, T)):
+        B.replay(imu.streams[t0:t1].contiguous(), imu.acc_ref, imu.mag_ref, dt=imu.dt, q=q_t, r=r_t, n_filters=G * Ns,
+                 state=st2, truth=truth[t0:t1].contiguous(), loss=loss)
+        loss = st2.loss
+    torch.testing.assert_close(loss, st.loss, rtol=1e-5, atol=1e-9)
+    surface = loss.reshape(G, Ns).mean(1)
+    assert torch.isfinite(surface).all() and surface.min() > 0
+
+
+def test_preprocess_and_log_replay(cuda):
+    """raw-sensor pre-processing kernel vs its float64 restatement, and a replay driven
+    from a log in the reference's text format."""
+    import os
+    from poseestimationkf_b200 import logio
+    rng = np.random.default_rng(3)
+    T, N = 60, 300
+    y1 = rng.normal(size=(T, 6, N)); y2 = y1 + 0.05 * rng.normal(size=(T, 6, N))
+    t1 = rng.integers(0, 10 ** 6, (T, 2, N)); span = rng.integers(5 * 10 ** 6, 2 * 10 ** 7, (T, 2, N))
+    t2 = t1 + span; t3 = t1 + (span * rng.uniform(0.05, 0.95, (T, 2, N))).astype(np.int64)
+    gyro = rng.normal(size=(T, 3, N))
+    tspan = np.stack([(t2 - t1)[:, 0], (t3 - t1)[:, 0], (t2 - t1)[:, 1], (t3 - t1)[:, 1]], axis=1) * 1e-9
+    out, _ = B.preprocess(_dev(gyro, cuda), _dev(y1, cuda), _dev(y2, cuda), _dev(tspan, cuda))
+    f32 = lambda a: a.astype(np.float32).astype(np.float64)
+    for s, sl in enumerate((slice(0, 3), slice(3, 6))):
+        ref = O.interpolate_normalise(f32(y1)[:, sl].transpose(0, 2, 1), f32(y2)[:, sl].transpose(0, 2, 1),
+                                      t1[:, s], t2[:, s], t3[:, s])                     # [T, N, 3]
+        got = out[:, 3 + 3 * s:6 + 3 * s].cpu().numpy().transpose(0, 2, 1)
+        np.testing.assert_allclose(got, ref, atol=3e-6)
+    np.testing.assert_array_equal(out[:, 0:3].cpu().numpy(), gyro.astype(np.float32))
+    # with the low-pass stage: equals the stand-alone low-pass operator applied to the plain output
+    out_lp, st = B.preprocess(_dev(gyro, cuda), _dev(y1, cuda), _dev(y2, cuda), _dev(tspan, cuda), lpf_alpha_acc=0.1,
+                              lpf_alpha_mag=0.1)
+    acc_lp, _ = B.lowpass(out[:, 3:6].contiguous(), 0.1)
+    torch.testing.assert_close(out_lp[:, 3:6], acc_lp, rtol=1e-6, atol=1e-7)
+    # replay from the text log: X_k column of the log (6 decimals) is the reference's own result
+    d = logio.read_log(os.path.join(os.path.dirname(__file__), "golden", "sample_log.txt"))
+    streams, acc_ref, mag_ref, dt = d.to_streams(device=cuda)
+    _, traj, _ = B.replay(streams, acc_ref, mag_ref, dt=dt, q=1.0, r=0.1, store_trajectory=True)
+    logged = np.asarray(d.quart_xk[1:])
+    assert np.abs(traj[:, 0].cpu().numpy() - logged).max() < 2e-5        # log precision is 1e-6 per component;
+    # inputs were themselves rounded to 6 decimals by the writer, hence the looser bound

@@ -226,7 +226,18 @@ def test_full_length_parity_against_c_oracle(cuda):
         assert ang.max() < TOL, ang.max()
         assert (np.sum(got * ref["X"], axis=-1) > 0).all()
         mism = flips.cpu().numpy().astype(bool) != ref["flips"]
-        assert mism.sum() <= 8, mism.sum()          # near-ties of the 3-branch sign rule only (8.2 M steps)
+        # The q/-q decision may differ only where the reference's 3-branch sign rule (PKF/Wahba.py:28,35,41)
+        # sits on a numerical tie of its two largest traces tr_i = 4 q_i^2: verify that for every mismatch.
+        assert mism.sum() <= 40, mism.sum()         # ~1e-6 of 8.2 M steps
+        tt, nn = np.nonzero(mism)
+        if len(tt):
+            S = imu.streams.cpu().numpy()
+            ar, mr = imu.acc_ref.cpu().numpy()[:, nn], imu.mag_ref.cpu().numpy()[:, nn]
+            acc, mag = S[tt, 3:6, nn].T, S[tt, 6:9, nn].T
+            ka = np.abs(acc[2]).astype(np.float64)
+            _, qw = CO.wahba(ar, mr, acc, mag, ka, 1 - ka)
+            tr = np.sort(4 * qw[:, 1:] ** 2, axis=1)
+            assert ((tr[:, 2] - tr[:, 1]) < 2e-6).all(), (tr[:, 2] - tr[:, 1]).max()
         az = np.abs(imu.streams[:, 5].cpu().numpy())
         inside = (az >= 0.02) & (az <= 0.98)
         print(f"sigma={sigma}: max {ang.max():.2e} rad, inside 0.02<=|a_z|<=0.98: {ang[inside].max():.2e}, "

@@ -101,3 +101,33 @@ def test_gather_states_world2_gloo(tmp_path):
     for r in range(world):
         res = torch.load(os.path.join(str(tmp_path), f"r{r}.pt"))
         assert res["ok"] and res["slow"] == 2.0
+
+
+def test_log_reader_matches_the_reference_reader():
+    """tests/golden/sample_log.txt was parsed by the reference's own ReadFile.getData (make_golden.py);
+    logio.read_log must give exactly the same lists, and write_log must reproduce the file."""
+    from poseestimationkf_b200 import compat, logio
+    gold = np.load(os.path.join(os.path.dirname(__file__), "golden", "log_parsed.npz"))
+    path = os.path.join(os.path.dirname(__file__), "golden", "sample_log.txt")
+    d = logio.read_log(path)
+    for name in ("mag_0", "mag_1", "acc_0", "acc_1", "gyro", "timestamp", "quart_wahba", "quart_xk", "quart_gyro"):
+        np.testing.assert_array_equal(np.asarray(getattr(d, name)), gold[name], err_msg=name)
+    assert len(d.timestamp) == d.n_steps() + 1 and len(d.quart_xk) == d.n_steps() + 1      # T0 and the initial lines
+    # the writer regenerates the file byte for byte from the parsed content
+    lines = logio.format_log(acc_0=d.acc_0, mag_0=d.mag_0, t0_ns=d.timestamp[0][0], t_ns=[t[0] for t in d.timestamp[1:]],
+                             gyro=d.gyro, mag_1=d.mag_1, acc_1=d.acc_1, x_k=d.quart_xk[1:], wahba_quart=d.quart_wahba[1:],
+                             q_gyro=d.quart_gyro[1:])
+    assert lines == open(path).read().splitlines()
+    # compat module with the reference's class name
+    sys.path.insert(0, compat.PATH)
+    try:
+        from ReadFile import getData
+        g = getData(path)
+        assert g.acc_1 == d.acc_1 and g.timestamp == d.timestamp and g.getArray("x : 1,2", 2) == [1.0, 2.0]
+    finally:
+        sys.path.remove(compat.PATH)
+        sys.modules.pop("ReadFile", None)
+    streams, acc_ref, mag_ref, dt = d.to_streams(device="cpu")
+    assert streams.shape == (d.n_steps(), 9, 1) and dt.shape == (d.n_steps(),)
+    np.testing.assert_allclose(dt.numpy(), 0.01, rtol=1e-6)
+    np.testing.assert_allclose(streams[:, 3:6, 0].numpy(), np.asarray(d.acc_1), rtol=1e-6)
