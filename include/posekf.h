@@ -66,6 +66,11 @@ const char* posekf_version(void);
  *               r must be > 0 (the kernel carries the covariance in units of r), q >= 0
  *   lpf_alpha_acc/mag  low-pass coefficient, < 0 disables the stage
  *   state_x     [4][N]  in: X before the first step, out: X after the last step
+ *   state_x_lo  [4][N] in/out or NULL.  Non-NULL selects the COMPENSATED state: X is carried as two floats
+ *               (state_x + state_x_lo) so that corrections below half an ulp of the state are not lost.
+ *               Needed for R >> Q tunings over thousands of steps (gain ~1e-7: a single-float state
+ *               stops following its measurement; 2.4e-5 rad from the reference after 5000 steps at
+ *               Q=1e-3, R=1e3, 2e-7 with this variant); costs ~7 % more instructions.  Start at 0.
  *   state_p     [10][N] in/out: upper triangle of P / r  (the covariance IN UNITS OF THE FILTER'S r; after
  *               an update this equals the Kalman gain) in the order 00 01 02 03 11 12 13 22 23 33.
  *               The kernel works in this scaled form, so storing it unscaled would make a chunked
@@ -77,8 +82,8 @@ const char* posekf_version(void);
  *               (PKF/ExtendedKalmanFilter.py:73-75), or NULL
  *   truth       [T][Ns][4] reference track (ground truth, a Wahba-only or gyro-only track, another
  *               run's out_traj ...) for the on-device tuning objective, 16-byte aligned, or NULL
- *   loss_acc    [N] in/out, required with truth: loss_acc[n] += sum_t 1 - (X_t . truth_t)^2  (sin^2 of
- *               the quaternion angle).  Lets a Q/R sweep return its loss surface without storing
+ *   loss_acc    [N] in/out, required with truth: loss_acc[n] += sum_t |X_t ^ truth_t|^2 = 1 - (X_t . truth_t)^2
+ *               (sin^2 of the quaternion angle, evaluated as the squared wedge product).  Lets a Q/R sweep return its loss surface without storing
  *               trajectories (the tuning workflow of the reference's README, knobs main_file.py:21-22).
  *   wahba_algo  POSEKF_WAHBA_*
  *   staging     POSEKF_STAGE_*
@@ -86,8 +91,9 @@ const char* posekf_version(void);
 int posekf_replay_f32(int64_t n_filters, int64_t n_steps, const float* streams, int64_t n_streams,
                       const float* dt, int dt_per_step, const float* acc_ref, const float* mag_ref,
                       const float* q_scale, const float* r_scale, float lpf_alpha_acc, float lpf_alpha_mag,
-                      float* state_x, float* state_p, float* state_lpf, float* out_traj, uint8_t* out_flip,
-                      const float* truth, float* loss_acc, int wahba_algo, int staging, void* stream);
+                      float* state_x, float* state_x_lo, float* state_p, float* state_lpf, float* out_traj,
+                      uint8_t* out_flip, const float* truth, float* loss_acc, int wahba_algo, int staging,
+                      void* stream);
 
 /* Same replay with HOST buffers: streams_host [T][9][N] is streamed through the device in time
  * chunks (double-buffered H2D copies overlapped with the filter kernel, state carried across

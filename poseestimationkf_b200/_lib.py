@@ -17,7 +17,7 @@ STAGING = {"auto": 0, "ldg": 1, "tma": 2}
 
 _SIGNATURES = {
     "posekf_replay_f32": [_i64, _i64, _vp, _i64, _vp, _int, _vp, _vp, _vp, _vp, _f32, _f32, _vp, _vp, _vp, _vp, _vp,
-                          _vp, _vp, _int, _int, _vp],
+                          _vp, _vp, _vp, _int, _int, _vp],
     "posekf_replay_host_f32": [_i64, _i64, _vp, _f32, _vp, _vp, _vp, _vp, _f32, _f32, _vp, _vp, _vp, _vp, _vp, _i64,
                                _int, _int],
     "posekf_wahba_f32": [_i64, _vp, _vp, _int, _vp, _vp, _vp, _vp, _f32, _f32, _int, _vp, _vp, _int, _int, _vp],

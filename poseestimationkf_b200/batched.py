@@ -85,6 +85,7 @@ class ReplayState:
     r: object = 0.1
     lpf: torch.Tensor | None = None
     loss: torch.Tensor | None = None     # [N] accumulated tuning objective (see replay(truth=...))
+    x_lo: torch.Tensor | None = None     # [4,N] low-order part of the compensated (two-float) state
 
     @staticmethod
     def initial(n_filters: int, device, r=0.1, with_lpf: bool = False, P0: torch.Tensor | None = None) -> "ReplayState":
@@ -106,7 +107,8 @@ class ReplayState:
         return full_from_tri(self.p * (self.r if isinstance(self.r, torch.Tensor) else float(self.r)))
 
     def clone(self) -> "ReplayState":
-        return ReplayState(self.x.clone(), self.p.clone(), self.r, None if self.lpf is None else self.lpf.clone())
+        c = lambda t: None if t is None else t.clone()
+        return ReplayState(self.x.clone(), self.p.clone(), self.r, c(self.lpf), c(self.loss), c(self.x_lo))
 
 
 _scalar_cache: dict = {}
@@ -138,7 +140,7 @@ def replay(streams: torch.Tensor, acc_ref: torch.Tensor, mag_ref: torch.Tensor, 
            state: ReplayState | None = None, n_filters: int | None = None, lpf_alpha_acc: float | None = None,
            lpf_alpha_mag: float | None = None, out_traj: torch.Tensor | None = None, store_trajectory: bool = False,
            store_flips: bool = False, truth: torch.Tensor | None = None, loss: torch.Tensor | None = None,
-           wahba: str = "qr2", staging: str = "auto"):
+           precise_state: bool | None = None, wahba: str = "qr2", staging: str = "auto"):
     """Run T Prediction+Correction steps for N filters in one kernel launch.
 
     streams [T,9,Ns]; acc_ref, mag_ref [3,Ns]; dt: float seconds or [T] float32 CUDA tensor;
@@ -147,6 +149,9 @@ def replay(streams: torch.Tensor, acc_ref: torch.Tensor, mag_ref: torch.Tensor, 
     (created with the reference's initial values when None).  `truth` [T,Ns,4] enables the on-device
     tuning objective: `loss` [N] (created zeroed when None; pass it back in for chunked replays) is
     incremented by sum_t 1-(X_t.truth_t)^2 and is available as `state.loss`.
+    `precise_state` carries X as two floats (compensated summation) so that gains ~1e-7 (R >> Q) are
+    not lost to float32 rounding over long replays; None = automatic: on when q or r are per-filter
+    tensors (a tuning sweep) or when r/q >= 100, off otherwise (the default Q=1, R=0.1 does not need it).
     Returns (state, traj [T,N,4] or None, flips [T,N] uint8 or None)."""
     _require_cuda(streams, acc_ref, mag_ref, out_traj)
     if streams.dim() != 3 or streams.shape[1] != 9:
@@ -162,6 +167,12 @@ def replay(streams: torch.Tensor, acc_ref: torch.Tensor, mag_ref: torch.Tensor, 
     if state is None:
         state = ReplayState.initial(N, dev, r=r, with_lpf=use_lpf)
     state.r = r
+    if precise_state is None:
+        precise_state = (state.x_lo is not None or isinstance(q, torch.Tensor) or isinstance(r, torch.Tensor)
+                         or float(r) >= 100.0 * float(q))
+    if precise_state and state.x_lo is None:
+        state.x_lo = torch.zeros((4, N), dtype=torch.float32, device=dev)
+    _require_cuda(state.x_lo)
     if use_lpf and state.lpf is None:
         state.lpf = torch.zeros((6, N), dtype=torch.float32, device=dev)
     _require_cuda(state.x, state.p, state.lpf)
@@ -192,7 +203,8 @@ def replay(streams: torch.Tensor, acc_ref: torch.Tensor, mag_ref: torch.Tensor, 
             N, T, _ptr(streams), Ns, _ptr(dt_t), per_step, _ptr(acc_ref), _ptr(mag_ref), _ptr(q_t), _ptr(r_t),
             -1.0 if lpf_alpha_acc is None else float(lpf_alpha_acc),
             -1.0 if lpf_alpha_mag is None else float(lpf_alpha_mag),
-            _ptr(state.x), _ptr(state.p), _ptr(state.lpf), _ptr(out_traj), _ptr(flips), _ptr(truth),
+            _ptr(state.x), _ptr(state.x_lo if precise_state else None), _ptr(state.p), _ptr(state.lpf), _ptr(out_traj),
+            _ptr(flips), _ptr(truth),
             _ptr(loss if truth is not None else None), _lib.WAHBA[wahba], _lib.STAGING[staging], _stream())
     _lib.check(rc, "posekf_replay_f32")
     return state, out_traj, flips

@@ -157,6 +157,35 @@ template <typename F> PKF_HD Quat<F> rk4_step(const Quat<F>& q, const Vec3<F>& h
   return z;
 }
 
+// Fused-step form of the same RK4 step: returns only the INCREMENT  (c0 - 1) x + c1 (A x), so that
+// z = x + inc, WITHOUT the normalisation.  RK4 preserves the norm to O(a^6) (~1e-15 at 100 Hz), so
+// dividing by |z| only re-rounds the state; the caller renormalises lazily (see ekf_step) and, in
+// the compensated variant, folds the increment into a two-float state.
+template <typename F> PKF_HD Quat<F> rk4_increment(const Quat<F>& q, const Vec3<F>& hw, F h) {
+  Quat<F> u;   // u = A q
+  u.w = fma_(-hw.z, q.z, fma_(-hw.y, q.y, -(hw.x * q.x)));
+  u.x = fma_(-hw.y, q.z, fma_(hw.z, q.y, hw.x * q.w));
+  u.y = fma_(hw.x, q.z, fma_(-hw.z, q.x, hw.y * q.w));
+  u.z = fma_(-hw.x, q.y, fma_(hw.y, q.x, hw.z * q.w));
+  F a2 = (h * h) * dot3(hw, hw);
+  F cm = a2 * fma_(a2, F(1.0 / 24.0), F(-0.5));            // c0 - 1
+  F c1 = h * fma_(a2, F(-1.0 / 6.0), F(1));
+  Quat<F> inc;
+  inc.w = fma_(c1, u.w, cm * q.w);
+  inc.x = fma_(c1, u.x, cm * q.x);
+  inc.y = fma_(c1, u.y, cm * q.y);
+  inc.z = fma_(c1, u.z, cm * q.z);
+  return inc;
+}
+
+// Knuth two-sum: hi + lo == a + b exactly (no magnitude ordering assumed).
+template <typename F> PKF_HD void two_sum(F a, F b, F& hi, F& lo) {
+  F s = a + b;
+  F bb = s - a;
+  lo = (a - (s - bb)) + (b - bb);
+  hi = s;
+}
+
 // ------------------------------------------------------------------------------------------
 // Covariance propagation  P <- A P A^T + B(x) (q I3) B(x)^T,  A = 0.5*Omega(w)  (hw = 0.5 w),
 // x = state BEFORE the RK4 step.        (PKF/ExtendedKalmanFilter.py:59-61)
@@ -501,14 +530,22 @@ template <typename F> struct FilterConst {
   F g;                    // Q/(4R): process noise in units of r
 };
 
-template <typename F, int ALGO, bool WANT_FLIP>
-PKF_HD void ekf_step(Quat<F>& x, Sym4<F>& P, const FilterConst<F>& fc, const Vec3<F>& gyro, const Vec3<F>& acc,
-                     const Vec3<F>& mag, F h, bool& flip) {
+// COMP selects the compensated state: X is carried as x + xlo (two floats per component).  With a
+// single float, increments below half an ulp of the state (K e ~ 2e-8 per step when R >> Q) are
+// absorbed by the addition and the filter silently stops following its measurement -- the float64
+// reference does not (2.4e-5 rad apart after 5000 steps at Q=1e-3, R=1e3).  The compensated form
+// sums the step's three small terms (RK4 increment, K e, norm correction) first and folds them into
+// the state with one exact two-sum per component.
+template <typename F, int ALGO, bool WANT_FLIP, bool COMP>
+PKF_HD void ekf_step(Quat<F>& x, Quat<F>& xlo, Sym4<F>& P, const FilterConst<F>& fc, const Vec3<F>& gyro,
+                     const Vec3<F>& acc, const Vec3<F>& mag, F h, bool& flip) {
   Vec3<F> hw;
   hw.x = F(0.5) * gyro.x; hw.y = F(0.5) * gyro.y; hw.z = F(0.5) * gyro.z;
   // ---- Prediction (PKF/ExtendedKalmanFilter.py:58-68) ----
   Sym4<F> Pp = propagate_cov(P, hw, x, fc.g);                                 // :59-61 (in units of r)
-  Quat<F> z = rk4_step(x, hw, h);                                             // :62
+  Quat<F> inc = rk4_increment(x, hw, h);                                      // :62
+  Quat<F> z;                                                                  // |z| = 1 to rounding
+  z.w = x.w + inc.w; z.x = x.x + inc.x; z.y = x.y + inc.y; z.z = x.z + inc.z;
   Sym4<F> K = kalman_gain_unit(Pp);                                           // :63-66
   // ---- Correction (PKF/ExtendedKalmanFilter.py:70-80) ----
   F ka = abs_(acc.z), km = F(1) - ka;                                         // :71
@@ -531,13 +568,27 @@ PKF_HD void ekf_step(Quat<F>& x, Sym4<F>& P, const FilterConst<F>& fc, const Vec
   flip = WANT_FLIP ? reference_flip(Rm, y) : false;
   // X = z + K (y - z)                                                        :76-77
   F e0 = y.w - z.w, e1 = y.x - z.x, e2 = y.y - z.y, e3 = y.z - z.z;
-  Quat<F> xn;
-  xn.w = fma_(K.a03, e3, fma_(K.a02, e2, fma_(K.a01, e1, fma_(K.a00, e0, z.w))));
-  xn.x = fma_(K.a13, e3, fma_(K.a12, e2, fma_(K.a11, e1, fma_(K.a01, e0, z.x))));
-  xn.y = fma_(K.a23, e3, fma_(K.a22, e2, fma_(K.a12, e1, fma_(K.a02, e0, z.y))));
-  xn.z = fma_(K.a33, e3, fma_(K.a23, e2, fma_(K.a13, e1, fma_(K.a03, e0, z.z))));
-  F inv = rsqrt_(dot4(xn, xn));                                               // :79
-  x.w = xn.w * inv; x.x = xn.x * inv; x.y = xn.y * inv; x.z = xn.z * inv;
+  Quat<F> ke;
+  ke.w = fma_(K.a03, e3, fma_(K.a02, e2, fma_(K.a01, e1, K.a00 * e0)));
+  ke.x = fma_(K.a13, e3, fma_(K.a12, e2, fma_(K.a11, e1, K.a01 * e0)));
+  ke.y = fma_(K.a23, e3, fma_(K.a22, e2, fma_(K.a12, e1, K.a02 * e0)));
+  ke.z = fma_(K.a33, e3, fma_(K.a23, e2, fma_(K.a13, e1, K.a03 * e0)));
+  // X / |X| is applied as X + X (1/|X| - 1): when the norm is already 1 to rounding the correction
+  // is below half an ulp, so normalising every step does not re-round the state              :79
+  if (!COMP) {
+    Quat<F> xn;
+    xn.w = z.w + ke.w; xn.x = z.x + ke.x; xn.y = z.y + ke.y; xn.z = z.z + ke.z;
+    F d = rsqrt_(dot4(xn, xn)) - F(1);
+    x.w = fma_(xn.w, d, xn.w); x.x = fma_(xn.x, d, xn.x); x.y = fma_(xn.y, d, xn.y); x.z = fma_(xn.z, d, xn.z);
+  } else {
+    Quat<F> dl, xn;     // all small terms first, then one exact fold into (x, xlo)
+    dl.w = (inc.w + xlo.w) + ke.w; dl.x = (inc.x + xlo.x) + ke.x; dl.y = (inc.y + xlo.y) + ke.y; dl.z = (inc.z + xlo.z) + ke.z;
+    xn.w = x.w + dl.w; xn.x = x.x + dl.x; xn.y = x.y + dl.y; xn.z = x.z + dl.z;
+    F d = rsqrt_(dot4(xn, xn)) - F(1);
+    dl.w = fma_(xn.w, d, dl.w); dl.x = fma_(xn.x, d, dl.x); dl.y = fma_(xn.y, d, dl.y); dl.z = fma_(xn.z, d, dl.z);
+    two_sum(x.w, dl.w, x.w, xlo.w); two_sum(x.x, dl.x, x.x, xlo.x);
+    two_sum(x.y, dl.y, x.y, xlo.y); two_sum(x.z, dl.z, x.z, xlo.z);
+  }
   // P = P - K P = r K  (R = r I): in units of r the new covariance IS the gain     :78
   P = K;
 }

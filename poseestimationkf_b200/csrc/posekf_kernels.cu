@@ -109,6 +109,7 @@ struct ReplayParams {
   const float* r_scale;
   float alpha_acc, alpha_mag;
   float* state_x;
+  float* state_x_lo;    // [4][N] low-order part of the two-float state (compensated variant), or null
   float* state_p;
   float* state_lpf;
   float* out_traj;
@@ -119,17 +120,21 @@ struct ReplayParams {
 
 struct FilterRegs {
   Quat<float> x;
+  Quat<float> xlo;      // used by the compensated variant only
   Sym4<float> P;
   FilterConst<float> fc;
   Vec3<float> la, lm;   // low-pass state
 };
 
-template <bool LPF> __device__ __forceinline__ void load_filter(const ReplayParams& p, int64_t n, int64_t col, FilterRegs& f) {
+template <bool LPF, bool COMP>
+__device__ __forceinline__ void load_filter(const ReplayParams& p, int64_t n, int64_t col, FilterRegs& f) {
   const int64_t N = p.N, Ns = p.Ns;
   Vec3<float> ra = {p.acc_ref[col], p.acc_ref[Ns + col], p.acc_ref[2 * Ns + col]};
   Vec3<float> rm = {p.mag_ref[col], p.mag_ref[Ns + col], p.mag_ref[2 * Ns + col]};
   f.fc = make_filter_const<float>(ra, rm, p.q_scale[n], p.r_scale[n]);
   f.x = {p.state_x[n], p.state_x[N + n], p.state_x[2 * N + n], p.state_x[3 * N + n]};
+  f.xlo = {0.f, 0.f, 0.f, 0.f};
+  if (COMP) f.xlo = {p.state_x_lo[n], p.state_x_lo[N + n], p.state_x_lo[2 * N + n], p.state_x_lo[3 * N + n]};
   const float* sp = p.state_p + n;   // P/r: the step works in units of r (see ekf_step), so does the state buffer
   f.P = {sp[0], sp[N], sp[2 * N], sp[3 * N], sp[4 * N], sp[5 * N], sp[6 * N], sp[7 * N], sp[8 * N], sp[9 * N]};
   if (LPF) {
@@ -139,9 +144,13 @@ template <bool LPF> __device__ __forceinline__ void load_filter(const ReplayPara
   }
 }
 
-template <bool LPF> __device__ __forceinline__ void store_filter(const ReplayParams& p, int64_t n, const FilterRegs& f) {
+template <bool LPF, bool COMP>
+__device__ __forceinline__ void store_filter(const ReplayParams& p, int64_t n, const FilterRegs& f) {
   const int64_t N = p.N;
   p.state_x[n] = f.x.w; p.state_x[N + n] = f.x.x; p.state_x[2 * N + n] = f.x.y; p.state_x[3 * N + n] = f.x.z;
+  if (COMP) {
+    p.state_x_lo[n] = f.xlo.w; p.state_x_lo[N + n] = f.xlo.x; p.state_x_lo[2 * N + n] = f.xlo.y; p.state_x_lo[3 * N + n] = f.xlo.z;
+  }
   float* sp = p.state_p + n;
   sp[0] = f.P.a00; sp[N] = f.P.a01; sp[2 * N] = f.P.a02; sp[3 * N] = f.P.a03; sp[4 * N] = f.P.a11;
   sp[5 * N] = f.P.a12; sp[6 * N] = f.P.a13; sp[7 * N] = f.P.a22; sp[8 * N] = f.P.a23; sp[9 * N] = f.P.a33;
@@ -169,7 +178,7 @@ template <bool AUX> __device__ __forceinline__ AuxPtrs make_aux(const ReplayPara
   return a;
 }
 
-template <int ALGO, bool LPF, bool AUX>
+template <int ALGO, bool LPF, bool AUX, bool COMP>
 __device__ __forceinline__ void filter_step(const ReplayParams& p, FilterRegs& f, const float (&s)[kChannels], float h,
                                             AuxPtrs& aux) {
   Vec3<float> w = {s[0], s[1], s[2]}, a = {s[3], s[4], s[5]}, m = {s[6], s[7], s[8]};
@@ -178,7 +187,7 @@ __device__ __forceinline__ void filter_step(const ReplayParams& p, FilterRegs& f
     if (p.alpha_mag >= 0.f) { lowpass<float>(f.lm, m, p.alpha_mag, 1.f - p.alpha_mag); m = f.lm; }
   }
   bool flip;
-  ekf_step<float, ALGO, AUX>(f.x, f.P, f.fc, w, a, m, h, flip);
+  ekf_step<float, ALGO, AUX, COMP>(f.x, f.xlo, f.P, f.fc, w, a, m, h, flip);
   if (AUX) {
     if (aux.traj) {   // [T][N][4]: one 16-byte store per filter-step, consecutive filters consecutive
       asm volatile("st.global.cs.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(aux.traj), "f"(f.x.w), "f"(f.x.x), "f"(f.x.y),
@@ -190,8 +199,13 @@ __device__ __forceinline__ void filter_step(const ReplayParams& p, FilterRegs& f
     if (aux.truth) {  // tuning objective: sin^2 of the angle between the estimate and the reference track
       const float4 qt = __ldg(aux.truth);
       aux.truth += p.Ns;
-      const float d = fmaf(f.x.z, qt.w, fmaf(f.x.y, qt.z, fmaf(f.x.x, qt.y, f.x.w * qt.x)));
-      aux.loss += fmaf(-d, d, 1.f);
+      // sin^2 of the angle as the squared 4-D wedge product |X ^ q_ref|^2 = |X|^2 |q_ref|^2 - (X.q_ref)^2
+      // (Lagrange identity): the six 2x2 minors are small numbers computed without the 1 - d^2
+      // cancellation and without sensitivity to the 1e-7 norm error of either quaternion.
+      const float xw = f.x.w, xx = f.x.x, xy = f.x.y, xz = f.x.z, qw = qt.x, qx = qt.y, qy = qt.z, qz = qt.w;
+      const float m01 = fmaf(xw, qx, -(xx * qw)), m02 = fmaf(xw, qy, -(xy * qw)), m03 = fmaf(xw, qz, -(xz * qw));
+      const float m12 = fmaf(xx, qy, -(xy * qx)), m13 = fmaf(xx, qz, -(xz * qx)), m23 = fmaf(xy, qz, -(xz * qy));
+      aux.loss += fmaf(m23, m23, fmaf(m13, m13, fmaf(m12, m12, fmaf(m03, m03, fmaf(m02, m02, m01 * m01)))));
     }
   }
 }
@@ -200,14 +214,15 @@ __device__ __forceinline__ void filter_step(const ReplayParams& p, FilterRegs& f
 // Replay, LDG staging: coalesced loads straight to registers, next step prefetched while the
 // current one is computed.
 // ---------------------------------------------------------------------------------------------
-template <int ALGO, bool LPF, bool AUX>
-__global__ void __launch_bounds__(kThreads, ALGO == WAHBA_JACOBI ? 4 : kMinCtasPerSm) replay_ldg_kernel(const ReplayParams p) {
+template <int ALGO, bool LPF, bool AUX, bool COMP>
+__global__ void __launch_bounds__(kThreads, ALGO == WAHBA_JACOBI ? 4 : ((COMP || LPF) ? (kMinCtasPerSm > 5 ? 5 : kMinCtasPerSm) : kMinCtasPerSm))
+    replay_ldg_kernel(const ReplayParams p) {
   const int64_t n = (int64_t)blockIdx.x * kThreads + threadIdx.x;
   if (n >= p.N) return;
   const int64_t Ns = p.Ns;
   const int64_t col = (Ns == p.N) ? n : (n % Ns);
   FilterRegs f;
-  load_filter<LPF>(p, n, col, f);
+  load_filter<LPF, COMP>(p, n, col, f);
   AuxPtrs aux = make_aux<AUX>(p, n, col, true);
   const float* s = p.streams + col;
   const int64_t step_stride = kChannels * Ns;
@@ -221,11 +236,11 @@ __global__ void __launch_bounds__(kThreads, ALGO == WAHBA_JACOBI ? 4 : kMinCtasP
 #pragma unroll
     for (int c = 0; c < kChannels; ++c) nxt[c] = ldg_stream(s + c * Ns);
     const float h = p.dt_per_step ? __ldg(p.dt + t) : dt0;
-    filter_step<ALGO, LPF, AUX>(p, f, cur, h, aux);
+    filter_step<ALGO, LPF, AUX, COMP>(p, f, cur, h, aux);
 #pragma unroll
     for (int c = 0; c < kChannels; ++c) cur[c] = nxt[c];
   }
-  store_filter<LPF>(p, n, f);
+  store_filter<LPF, COMP>(p, n, f);
   if (AUX && aux.truth) p.loss_acc[n] = aux.loss;
 }
 
@@ -242,7 +257,7 @@ struct __align__(128) TmaSmem {
 };
 constexpr uint32_t kTileBytes = kTmaSteps * kChannels * kThreads * sizeof(float);
 
-template <int ALGO, bool LPF, bool AUX>
+template <int ALGO, bool LPF, bool AUX, bool COMP>
 __global__ void __launch_bounds__(kThreads, kMinCtasPerSm)
     replay_tma_kernel(const ReplayParams p, const __grid_constant__ CUtensorMap tmap) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -273,7 +288,7 @@ __global__ void __launch_bounds__(kThreads, kMinCtasPerSm)
   }
 
   FilterRegs f;
-  if (valid) load_filter<LPF>(p, n, (int64_t)col0 + tid, f);
+  if (valid) load_filter<LPF, COMP>(p, n, (int64_t)col0 + tid, f);
   AuxPtrs aux = make_aux<AUX>(p, n, (int64_t)col0 + tid, valid);
   const float dt0 = p.dt[0];
 
@@ -298,7 +313,7 @@ __global__ void __launch_bounds__(kThreads, kMinCtasPerSm)
 #pragma unroll
           for (int c = 0; c < kChannels; ++c) s[c] = sm.tile[stage][tt][c][tid];
           const float h = p.dt_per_step ? __ldg(p.dt + k * kTmaSteps + tt) : dt0;
-          filter_step<ALGO, LPF, AUX>(p, f, s, h, aux);
+          filter_step<ALGO, LPF, AUX, COMP>(p, f, s, h, aux);
         }
       }
     }
@@ -306,7 +321,7 @@ __global__ void __launch_bounds__(kThreads, kMinCtasPerSm)
     if ((tid & 31) == 0) mbar_arrive(&sm.empty[stage]);
     if (++stage == kTmaStages) { stage = 0; parity ^= 1; }
   }
-  if (valid) store_filter<LPF>(p, n, f);
+  if (valid) store_filter<LPF, COMP>(p, n, f);
   if (AUX && valid && aux.truth) p.loss_acc[n] = aux.loss;
 }
 
@@ -766,10 +781,10 @@ bool tma_eligible(const ReplayParams& p) {
   return true;
 }
 
-template <int ALGO, bool LPF, bool AUX> int launch_replay(const ReplayParams& p, bool use_tma, cudaStream_t st) {
+template <int ALGO, bool LPF, bool AUX, bool COMP> int launch_replay(const ReplayParams& p, bool use_tma, cudaStream_t st) {
   const unsigned grid = (unsigned)((p.N + kThreads - 1) / kThreads);
   if (!use_tma) {
-    replay_ldg_kernel<ALGO, LPF, AUX><<<grid, kThreads, 0, st>>>(p);
+    replay_ldg_kernel<ALGO, LPF, AUX, COMP><<<grid, kThreads, 0, st>>>(p);
     return launch_status();
   }
   EncodeTiledFn enc = get_encode_fn();
@@ -783,7 +798,7 @@ template <int ALGO, bool LPF, bool AUX> int launch_replay(const ReplayParams& p,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return POSEKF_EALIGN;
-  auto kern = replay_tma_kernel<ALGO, LPF, AUX>;
+  auto kern = replay_tma_kernel<ALGO, LPF, AUX, COMP>;
   // idempotent; set on every launch (cheap) so that it holds on every device of a multi-GPU process
   PKF_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TmaSmem)));
   kern<<<grid, kThreads, sizeof(TmaSmem), st>>>(p, tmap);
@@ -792,7 +807,9 @@ template <int ALGO, bool LPF, bool AUX> int launch_replay(const ReplayParams& p,
 
 template <int ALGO, bool LPF> int launch_replay_aux(const ReplayParams& p, bool use_tma, cudaStream_t st) {
   const bool aux = p.out_traj != nullptr || p.out_flip != nullptr || p.truth != nullptr;
-  return aux ? launch_replay<ALGO, LPF, true>(p, use_tma, st) : launch_replay<ALGO, LPF, false>(p, use_tma, st);
+  const bool comp = p.state_x_lo != nullptr;
+  if (comp) return aux ? launch_replay<ALGO, LPF, true, true>(p, use_tma, st) : launch_replay<ALGO, LPF, false, true>(p, use_tma, st);
+  return aux ? launch_replay<ALGO, LPF, true, false>(p, use_tma, st) : launch_replay<ALGO, LPF, false, false>(p, use_tma, st);
 }
 
 int replay_dispatch(const ReplayParams& p, int algo, int staging, cudaStream_t st) {
@@ -820,8 +837,8 @@ const char* posekf_version(void) { return "posekf_b200 0.1 sm_100a"; }
 
 int posekf_replay_f32(int64_t n_filters, int64_t n_steps, const float* streams, int64_t n_streams, const float* dt,
                       int dt_per_step, const float* acc_ref, const float* mag_ref, const float* q_scale,
-                      const float* r_scale, float lpf_alpha_acc, float lpf_alpha_mag, float* state_x, float* state_p,
-                      float* state_lpf, float* out_traj, uint8_t* out_flip, const float* truth, float* loss_acc,
+                      const float* r_scale, float lpf_alpha_acc, float lpf_alpha_mag, float* state_x, float* state_x_lo,
+                      float* state_p, float* state_lpf, float* out_traj, uint8_t* out_flip, const float* truth, float* loss_acc,
                       int wahba_algo, int staging, void* stream) {
   if (n_filters < 0 || n_steps < 0 || n_streams <= 0 && n_filters > 0) return POSEKF_EINVAL;
   if (n_filters == 0 || n_steps == 0) return 0;
@@ -836,7 +853,7 @@ int posekf_replay_f32(int64_t n_filters, int64_t n_steps, const float* streams, 
   p.N = n_filters; p.T = n_steps; p.Ns = n_streams; p.streams = streams; p.dt = dt; p.dt_per_step = dt_per_step;
   p.acc_ref = acc_ref; p.mag_ref = mag_ref; p.q_scale = q_scale; p.r_scale = r_scale;
   p.alpha_acc = lpf_alpha_acc; p.alpha_mag = lpf_alpha_mag;
-  p.state_x = state_x; p.state_p = state_p; p.state_lpf = state_lpf; p.out_traj = out_traj; p.out_flip = out_flip;
+  p.state_x = state_x; p.state_x_lo = state_x_lo; p.state_p = state_p; p.state_lpf = state_lpf; p.out_traj = out_traj; p.out_flip = out_flip;
   p.truth = truth; p.loss_acc = loss_acc;
   return replay_dispatch(p, wahba_algo, staging, (cudaStream_t)stream);
 }
@@ -943,7 +960,7 @@ int posekf_replay_host_f32(int64_t N, int64_t T, const float* streams_host, floa
     TRY(cudaStreamWaitEvent(s_comp, ev_in[b], 0));
     if (traj && c >= 2) TRY(cudaStreamWaitEvent(s_comp, ev_tfree[b], 0));  // D2H of chunk c-2 done with d_traj[b]
     rc = posekf_replay_f32(N, tc, d_in[b], N, d_dt, 0, d_ref, d_ref + 3 * N, d_qr, d_qr + N, lpf_alpha_acc,
-                           lpf_alpha_mag, d_x, d_p, d_lpf, traj ? d_traj[b] : nullptr, nullptr, nullptr, nullptr,
+                           lpf_alpha_mag, d_x, nullptr, d_p, d_lpf, traj ? d_traj[b] : nullptr, nullptr, nullptr, nullptr,
                            wahba_algo, POSEKF_STAGE_AUTO, s_comp);
     if (rc != 0) { cleanup(); return rc; }
     TRY(cudaEventRecord(ev_free[b], s_comp));

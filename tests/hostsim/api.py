@@ -19,7 +19,8 @@ def _p(a, t):
     return a.ctypes.data_as(C.POINTER(t)) if a is not None else None
 
 
-def replay(streams, dt, acc_ref, mag_ref, q, r, *, precision="f32", algo="qr2", lpf_acc=-1.0, lpf_mag=-1.0):
+def replay(streams, dt, acc_ref, mag_ref, q, r, *, precision="f32", algo="qr2", lpf_acc=-1.0, lpf_mag=-1.0,
+           compensated=False):
     """streams [T,9,N] f32, acc_ref/mag_ref [3,N] f32, q/r [N] f32, dt scalar or [T] f32 (seconds).
     Returns traj [T,4,N] f64, flips [T,N] bool, P [10,N] f64."""
     streams = np.ascontiguousarray(streams, dtype=np.float32)
@@ -33,7 +34,7 @@ def replay(streams, dt, acc_ref, mag_ref, q, r, *, precision="f32", algo="qr2", 
     flips = np.empty((T, N), dtype=np.uint8)
     P = np.empty((10, N))
     rc = lib().hostsim_replay(C.c_int(0 if precision == "f32" else 1), C.c_int(0 if algo == "qr2" else 1),
-                              C.c_int64(N), C.c_int64(T), _p(streams, C.c_float), _p(dt, C.c_double),
+                              C.c_int(int(compensated)), C.c_int64(N), C.c_int64(T), _p(streams, C.c_float), _p(dt, C.c_double),
                               C.c_int(int(dt.size > 1)), _p(acc_ref, C.c_float), _p(mag_ref, C.c_float),
                               _p(q, C.c_float), _p(r, C.c_float), C.c_float(lpf_acc), C.c_float(lpf_mag),
                               _p(traj, C.c_double), _p(flips, C.c_uint8), _p(P, C.c_double))

@@ -10,7 +10,7 @@
 
 using namespace pkf;
 
-template <typename F, int ALGO>
+template <typename F, int ALGO, bool COMP>
 static void replay_t(int64_t N, int64_t T, const float* streams, const double* dt, int dt_per_step,
                      const float* acc_ref, const float* mag_ref, const float* q, const float* r,
                      float lpf_acc, float lpf_mag, double* out_traj, uint8_t* out_flip, double* out_P) {
@@ -18,7 +18,7 @@ static void replay_t(int64_t N, int64_t T, const float* streams, const double* d
     Vec3<F> ra = {(F)acc_ref[0 * N + n], (F)acc_ref[1 * N + n], (F)acc_ref[2 * N + n]};
     Vec3<F> rm = {(F)mag_ref[0 * N + n], (F)mag_ref[1 * N + n], (F)mag_ref[2 * N + n]};
     FilterConst<F> fc = make_filter_const<F>(ra, rm, (F)q[n], (F)r[n]);
-    Quat<F> x = {F(1), F(0), F(0), F(0)};
+    Quat<F> x = {F(1), F(0), F(0), F(0)}, xlo = {F(0), F(0), F(0), F(0)};
     const F ir = F(1) / (F)r[n];   // the step carries P/r
     Sym4<F> P = {ir, F(0), F(0), F(0), ir, F(0), F(0), ir, F(0), ir};
     Vec3<F> la = {F(0), F(0), F(0)}, lm = {F(0), F(0), F(0)};
@@ -31,7 +31,7 @@ static void replay_t(int64_t N, int64_t T, const float* streams, const double* d
       if (lpf_mag >= 0.f) { lowpass<F>(lm, m, (F)lpf_mag, F(1) - (F)lpf_mag); m = lm; }
       F h = (F)(dt_per_step ? dt[t] : dt[0]);
       bool flip;
-      ekf_step<F, ALGO, true>(x, P, fc, w, a, m, h, flip);
+      ekf_step<F, ALGO, true, COMP>(x, xlo, P, fc, w, a, m, h, flip);
       if (out_traj) {
         double* o = out_traj + (size_t)t * 4 * N + n;
         o[0 * N] = x.w; o[1 * N] = x.x; o[2 * N] = x.y; o[3 * N] = x.z;
@@ -48,10 +48,10 @@ static void replay_t(int64_t N, int64_t T, const float* streams, const double* d
 extern "C" {
 
 // precision: 0 = float32, 1 = float64 ; algo: 0 = QR2, 1 = Jacobi
-int hostsim_replay(int precision, int algo, int64_t N, int64_t T, const float* streams, const double* dt,
+int hostsim_replay(int precision, int algo, int comp, int64_t N, int64_t T, const float* streams, const double* dt,
                    int dt_per_step, const float* acc_ref, const float* mag_ref, const float* q, const float* r,
                    float lpf_acc, float lpf_mag, double* out_traj, uint8_t* out_flip, double* out_P) {
-#define GO(F, A) replay_t<F, A>(N, T, streams, dt, dt_per_step, acc_ref, mag_ref, q, r, lpf_acc, lpf_mag, out_traj, out_flip, out_P)
+#define GO(F, A) if (comp) replay_t<F, A, true>(N, T, streams, dt, dt_per_step, acc_ref, mag_ref, q, r, lpf_acc, lpf_mag, out_traj, out_flip, out_P); else replay_t<F, A, false>(N, T, streams, dt, dt_per_step, acc_ref, mag_ref, q, r, lpf_acc, lpf_mag, out_traj, out_flip, out_P)
   if (precision == 0 && algo == 0) GO(float, WAHBA_QR2);
   else if (precision == 0 && algo == 1) GO(float, WAHBA_JACOBI);
   else if (precision == 1 && algo == 0) GO(double, WAHBA_QR2);

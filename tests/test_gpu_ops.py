@@ -195,9 +195,10 @@ def test_comparison_tracks_and_tuning_objective(cuda):
     r_t = _dev(np.repeat([r for _, r in grid], Ns), cuda)
     st, traj, _ = B.replay(imu.streams, imu.acc_ref, imu.mag_ref, dt=imu.dt, q=q_t, r=r_t, n_filters=G * Ns, truth=truth,
                            store_trajectory=True)
-    d = (traj.reshape(T, G, Ns, 4).double() * truth.double()[:, None]).sum(-1)
-    want = (1 - d * d).sum(0).reshape(-1)
-    torch.testing.assert_close(st.loss.double(), want, rtol=2e-3, atol=1e-7)
+    xt, qt = traj.reshape(T, G, Ns, 4).double(), truth.double()[:, None]
+    d = (xt * qt).sum(-1)
+    want = ((xt * xt).sum(-1) * (qt * qt).sum(-1) - d * d).sum(0).reshape(-1)     # |X|^2|q|^2 - (X.q)^2 = sin^2
+    torch.testing.assert_close(st.loss.double(), want, rtol=1e-3, atol=1e-9)
     # same loss without storing the trajectory, accumulated over two time chunks
     st2 = B.ReplayState.initial(G * Ns, cuda, r=r_t)
     loss = None

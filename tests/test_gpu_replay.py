@@ -242,3 +242,39 @@ def test_full_length_parity_against_c_oracle(cuda):
         inside = (az >= 0.02) & (az <= 0.98)
         print(f"sigma={sigma}: max {ang.max():.2e} rad, inside 0.02<=|a_z|<=0.98: {ang[inside].max():.2e}, "
               f"outside ({1 - inside.mean():.3f} of steps): {ang[~inside].max():.2e}, flip mismatches {mism.sum()}")
+
+
+def test_compensated_state_long_replay_extreme_tunings(cuda):
+    """BASELINE config 3 corner: Q=1e-3, R=1e3 over 5000 steps.  The gain is ~2.5e-7, so K(y-z) is below
+    half an ulp of a float32 state; the compensated (two-float) state keeps parity, the plain one drifts."""
+    from oracle import c_oracle as CO
+    Ns, T = 256, 5000
+    imu = make_imu(Ns, T, seed=13, sigma=0.01, device=cuda)
+    grid = [(1e-3, 1e3), (1e-3, 10.0), (1.0, 0.1), (1e3, 1e-3)]
+    G = len(grid)
+    q_t = _dev(np.repeat([q for q, _ in grid], Ns), cuda)
+    r_t = _dev(np.repeat([r for _, r in grid], Ns), cuda)
+    S = imu.streams.cpu().numpy()
+    refs = [CO.replay(S, imu.dt * 1e9, imu.acc_ref.cpu().numpy(), imu.mag_ref.cpu().numpy(), float(np.float32(q)),
+                      float(np.float32(r))) for q, r in grid]
+    worst = {}
+    for precise in (True, False):
+        st, traj, _ = B.replay(imu.streams, imu.acc_ref, imu.mag_ref, dt=imu.dt, q=q_t, r=r_t, n_filters=G * Ns,
+                               store_trajectory=True, precise_state=precise)
+        got = traj.cpu().numpy().reshape(T, G, Ns, 4)
+        worst[precise] = [O.quat_angle(got[:, gi], refs[gi]["X"]).max() for gi in range(G)]
+        assert (st.x_lo is not None) == precise
+    assert max(worst[True]) < TOL, worst[True]                      # every tuning within 1e-5 rad
+    assert worst[True][0] < 1e-6 and worst[False][0] > TOL          # the corner needs the compensation ...
+    assert worst[False][2] < 1e-6                                   # ... the default tuning does not
+    # automatic selection: per-filter tensors (a sweep) switch it on, the default scalars do not
+    st_auto, _, _ = B.replay(imu.streams, imu.acc_ref, imu.mag_ref, dt=imu.dt, q=q_t, r=r_t, n_filters=G * Ns)
+    assert st_auto.x_lo is not None
+    st_def, _, _ = B.replay(imu.streams, imu.acc_ref, imu.mag_ref, dt=imu.dt, q=1.0, r=0.1)
+    assert st_def.x_lo is None
+    # chunked == unchunked also for the two-float state
+    st_c = B.ReplayState.initial(G * Ns, cuda, r=r_t)
+    for t0, t1 in ((0, 1777), (1777, T)):
+        B.replay(imu.streams[t0:t1].contiguous(), imu.acc_ref, imu.mag_ref, dt=imu.dt, q=q_t, r=r_t, n_filters=G * Ns,
+                 state=st_c, precise_state=True)
+    assert torch.equal(st_c.x, st_auto.x) and torch.equal(st_c.x_lo, st_auto.x_lo) and torch.equal(st_c.p, st_auto.p)
