@@ -101,14 +101,22 @@ int posekf_replay_f32(int64_t n_filters, int64_t n_steps, const float* streams, 
  *   out_x_host [4][N], out_p_host [10][N] = upper triangle of P itself, unscaled (may be NULL), out_traj_host [T][N][4] (may be NULL).
  *   x0_host / p0_host ([4][N] / [10][N] upper triangle of P, unscaled) may be NULL (X=[1,0,0,0], P=I4:
  *   PKF/main_file.py:23,26).
- *   chunk_steps  steps per chunk (0 = choose so that one chunk is about 1 GiB).
+ *   chunk_steps  steps per chunk when no workspace is given (0 = about 256 MiB per staging buffer).
  *   device      CUDA device ordinal.
+ *   workspace   from posekf_host_workspace_create (staging buffers, streams and events are reused across
+ *               calls -- allocating and freeing GiB-sized buffers per call costs tens of ms), or NULL
+ *               for a temporary one.
  * Host buffers should be page-locked (cudaHostAlloc / cudaHostRegister) for full PCIe rate. */
 int posekf_replay_host_f32(int64_t n_filters, int64_t n_steps, const float* streams_host, float dt,
                            const float* acc_ref_host, const float* mag_ref_host, const float* q_scale_host,
                            const float* r_scale_host, float lpf_alpha_acc, float lpf_alpha_mag,
                            const float* x0_host, const float* p0_host, float* out_x_host, float* out_p_host,
-                           float* out_traj_host, int64_t chunk_steps, int wahba_algo, int device);
+                           float* out_traj_host, int64_t chunk_steps, int wahba_algo, int device, void* workspace);
+
+/* Reusable workspace of posekf_replay_host_f32 for batches of n_filters on `device` (the only objects
+ * this library ever allocates).  chunk_steps <= 0 picks ~256 MiB staging buffers. */
+int posekf_host_workspace_create(int device, int64_t n_filters, int64_t chunk_steps, int with_trajectory, void** out_ws);
+int posekf_host_workspace_destroy(void* workspace);
 
 /* ---------------------------------------------------------------------------------------------
  * Wahba.getRotation / Wahba.getQuarternion for N (acc, mag) pairs.   PKF/Wahba.py:8-17,49-50

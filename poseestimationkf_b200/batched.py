@@ -210,8 +210,28 @@ def replay(streams: torch.Tensor, acc_ref: torch.Tensor, mag_ref: torch.Tensor, 
     return state, out_traj, flips
 
 
+class HostWorkspace:
+    """Reusable device staging buffers / streams of `replay_host` for batches of `n_filters`."""
+
+    def __init__(self, n_filters: int, *, chunk_steps: int = 0, with_trajectory: bool = False, device: int = 0):
+        import ctypes as C
+        self.n_filters, self.with_trajectory, self.device = int(n_filters), bool(with_trajectory), int(device)
+        h = C.c_void_p()
+        _lib.check(_lib.load().posekf_host_workspace_create(self.device, self.n_filters, int(chunk_steps),
+                                                            int(with_trajectory), C.byref(h)), "posekf_host_workspace_create")
+        self.handle = h
+
+    def close(self):
+        if getattr(self, "handle", None):
+            _lib.load().posekf_host_workspace_destroy(self.handle)
+            self.handle = None
+
+    __del__ = close
+
+
 def replay_host(streams, acc_ref, mag_ref, *, dt: float, q, r, lpf_alpha_acc=None, lpf_alpha_mag=None,
-                store_trajectory=False, chunk_steps: int = 0, wahba: str = "qr2", device: int = 0):
+                store_trajectory=False, chunk_steps: int = 0, wahba: str = "qr2", device: int = 0,
+                workspace: "HostWorkspace | None" = None):
     """End-to-end replay from HOST memory (CPU torch tensors, ideally pinned): the stream is pushed
     through the GPU in double-buffered time chunks and the final state (and optionally the
     trajectory) is copied back.  streams [T,9,N] float32 CPU; acc_ref/mag_ref [3,N]; q, r [N].
@@ -228,7 +248,8 @@ def replay_host(streams, acc_ref, mag_ref, *, dt: float, q, r, lpf_alpha_acc=Non
         N, T, _ptr(streams), float(dt), _ptr(acc_ref), _ptr(mag_ref), _ptr(q), _ptr(r),
         -1.0 if lpf_alpha_acc is None else float(lpf_alpha_acc),
         -1.0 if lpf_alpha_mag is None else float(lpf_alpha_mag),
-        None, None, _ptr(x), _ptr(p), _ptr(traj), int(chunk_steps), _lib.WAHBA[wahba], int(device))
+        None, None, _ptr(x), _ptr(p), _ptr(traj), int(chunk_steps), _lib.WAHBA[wahba], int(device),
+        None if workspace is None else workspace.handle)
     _lib.check(rc, "posekf_replay_host_f32")
     return x, p, traj
 

@@ -858,118 +858,170 @@ int posekf_replay_f32(int64_t n_filters, int64_t n_steps, const float* streams, 
   return replay_dispatch(p, wahba_algo, staging, (cudaStream_t)stream);
 }
 
-int posekf_replay_host_f32(int64_t N, int64_t T, const float* streams_host, float dt, const float* acc_ref_host,
-                           const float* mag_ref_host, const float* q_scale_host, const float* r_scale_host,
-                           float lpf_alpha_acc, float lpf_alpha_mag, const float* x0_host, const float* p0_host,
-                           float* out_x_host, float* out_p_host, float* out_traj_host, int64_t chunk_steps,
-                           int wahba_algo, int device) {
-  if (N <= 0 || T < 0 || !streams_host || !acc_ref_host || !mag_ref_host || !q_scale_host || !r_scale_host || !out_x_host)
-    return POSEKF_EINVAL;
-  PKF_CUDA_TRY(cudaSetDevice(device));
-  if (chunk_steps <= 0) {
-    const int64_t bytes_per_step = (int64_t)kChannels * N * sizeof(float);
-    chunk_steps = std::max<int64_t>(1, (int64_t)(1ll << 30) / bytes_per_step);
-  }
-  chunk_steps = std::min<int64_t>(chunk_steps, std::max<int64_t>(T, 1));
-  const size_t chunk_elems = (size_t)chunk_steps * kChannels * N;
-  const bool lpf = lpf_alpha_acc >= 0.f || lpf_alpha_mag >= 0.f;
-  const bool traj = out_traj_host != nullptr;
-
+// ---- host-buffer replay: workspace (device staging buffers, streams, events) ----------------------
+struct HostWorkspace {
+  int device = 0;
+  int64_t N = 0, chunk_steps = 0;
+  bool traj = false;
   cudaStream_t s_copy = nullptr, s_comp = nullptr, s_out = nullptr;
   cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr}, ev_traj[2] = {nullptr, nullptr},
               ev_tfree[2] = {nullptr, nullptr};
   float *d_in[2] = {nullptr, nullptr}, *d_traj[2] = {nullptr, nullptr};
   float *d_ref = nullptr, *d_qr = nullptr, *d_x = nullptr, *d_p = nullptr, *d_lpf = nullptr, *d_dt = nullptr;
-  int rc = 0;
-  auto cleanup = [&]() {
-    for (int i = 0; i < 2; ++i) {
-      if (d_in[i]) cudaFree(d_in[i]);
-      if (d_traj[i]) cudaFree(d_traj[i]);
-      if (ev_in[i]) cudaEventDestroy(ev_in[i]);
-      if (ev_free[i]) cudaEventDestroy(ev_free[i]);
-      if (ev_traj[i]) cudaEventDestroy(ev_traj[i]);
-      if (ev_tfree[i]) cudaEventDestroy(ev_tfree[i]);
-    }
-    if (d_ref) cudaFree(d_ref);
-    if (d_qr) cudaFree(d_qr);
-    if (d_x) cudaFree(d_x);
-    if (d_p) cudaFree(d_p);
-    if (d_lpf) cudaFree(d_lpf);
-    if (d_dt) cudaFree(d_dt);
-    if (s_copy) cudaStreamDestroy(s_copy);
-    if (s_comp) cudaStreamDestroy(s_comp);
-    if (s_out) cudaStreamDestroy(s_out);
-  };
-#define TRY(expr)                                              \
-  do {                                                         \
-    cudaError_t _e = (expr);                                   \
-    if (_e != cudaSuccess) { rc = (int)_e; cleanup(); return rc; } \
-  } while (0)
-  TRY(cudaStreamCreateWithFlags(&s_copy, cudaStreamNonBlocking));
-  TRY(cudaStreamCreateWithFlags(&s_comp, cudaStreamNonBlocking));
-  TRY(cudaStreamCreateWithFlags(&s_out, cudaStreamNonBlocking));
+  float* h_init = nullptr;   // pinned scratch [10][N]
+};
+
+static void host_ws_free(HostWorkspace* w) {
+  if (!w) return;
+  cudaSetDevice(w->device);
   for (int i = 0; i < 2; ++i) {
-    TRY(cudaEventCreateWithFlags(&ev_in[i], cudaEventDisableTiming));
-    TRY(cudaEventCreateWithFlags(&ev_free[i], cudaEventDisableTiming));
-    TRY(cudaEventCreateWithFlags(&ev_traj[i], cudaEventDisableTiming));
-    TRY(cudaEventCreateWithFlags(&ev_tfree[i], cudaEventDisableTiming));
-    TRY(cudaMalloc(&d_in[i], chunk_elems * sizeof(float)));
-    if (traj) TRY(cudaMalloc(&d_traj[i], (size_t)chunk_steps * 4 * N * sizeof(float)));
+    if (w->d_in[i]) cudaFree(w->d_in[i]);
+    if (w->d_traj[i]) cudaFree(w->d_traj[i]);
+    if (w->ev_in[i]) cudaEventDestroy(w->ev_in[i]);
+    if (w->ev_free[i]) cudaEventDestroy(w->ev_free[i]);
+    if (w->ev_traj[i]) cudaEventDestroy(w->ev_traj[i]);
+    if (w->ev_tfree[i]) cudaEventDestroy(w->ev_tfree[i]);
   }
-  TRY(cudaMalloc(&d_ref, (size_t)6 * N * sizeof(float)));
-  TRY(cudaMalloc(&d_qr, (size_t)2 * N * sizeof(float)));
-  TRY(cudaMalloc(&d_x, (size_t)4 * N * sizeof(float)));
-  TRY(cudaMalloc(&d_p, (size_t)10 * N * sizeof(float)));
-  TRY(cudaMalloc(&d_dt, sizeof(float)));
-  if (lpf) { TRY(cudaMalloc(&d_lpf, (size_t)6 * N * sizeof(float))); TRY(cudaMemsetAsync(d_lpf, 0, (size_t)6 * N * sizeof(float), s_comp)); }
+  float* ptrs[] = {w->d_ref, w->d_qr, w->d_x, w->d_p, w->d_lpf, w->d_dt};
+  for (float* q : ptrs) if (q) cudaFree(q);
+  if (w->h_init) cudaFreeHost(w->h_init);
+  if (w->s_copy) cudaStreamDestroy(w->s_copy);
+  if (w->s_comp) cudaStreamDestroy(w->s_comp);
+  if (w->s_out) cudaStreamDestroy(w->s_out);
+  delete w;
+}
+
+int posekf_host_workspace_create(int device, int64_t n_filters, int64_t chunk_steps, int with_trajectory, void** out_ws) {
+  if (!out_ws || n_filters <= 0) return POSEKF_EINVAL;
+  *out_ws = nullptr;
+  PKF_CUDA_TRY(cudaSetDevice(device));
+  const int64_t N = n_filters;
+  if (chunk_steps <= 0) {   // ~256 MiB per staging buffer: small enough that the first kernel starts after ~5 ms
+    const int64_t bytes_per_step = (int64_t)kChannels * N * sizeof(float);
+    chunk_steps = std::max<int64_t>(1, (int64_t)(256ll << 20) / bytes_per_step);
+  }
+  HostWorkspace* w = new HostWorkspace();
+  w->device = device; w->N = N; w->chunk_steps = chunk_steps; w->traj = with_trajectory != 0;
+#define WS_TRY(expr)                                                   \
+  do {                                                                 \
+    cudaError_t _e = (expr);                                           \
+    if (_e != cudaSuccess) { host_ws_free(w); return (int)_e; }        \
+  } while (0)
+  WS_TRY(cudaStreamCreateWithFlags(&w->s_copy, cudaStreamNonBlocking));
+  WS_TRY(cudaStreamCreateWithFlags(&w->s_comp, cudaStreamNonBlocking));
+  WS_TRY(cudaStreamCreateWithFlags(&w->s_out, cudaStreamNonBlocking));
+  for (int i = 0; i < 2; ++i) {
+    WS_TRY(cudaEventCreateWithFlags(&w->ev_in[i], cudaEventDisableTiming));
+    WS_TRY(cudaEventCreateWithFlags(&w->ev_free[i], cudaEventDisableTiming));
+    WS_TRY(cudaEventCreateWithFlags(&w->ev_traj[i], cudaEventDisableTiming));
+    WS_TRY(cudaEventCreateWithFlags(&w->ev_tfree[i], cudaEventDisableTiming));
+    WS_TRY(cudaMalloc(&w->d_in[i], (size_t)chunk_steps * kChannels * N * sizeof(float)));
+    if (w->traj) WS_TRY(cudaMalloc(&w->d_traj[i], (size_t)chunk_steps * 4 * N * sizeof(float)));
+  }
+  WS_TRY(cudaMalloc(&w->d_ref, (size_t)6 * N * sizeof(float)));
+  WS_TRY(cudaMalloc(&w->d_qr, (size_t)2 * N * sizeof(float)));
+  WS_TRY(cudaMalloc(&w->d_x, (size_t)4 * N * sizeof(float)));
+  WS_TRY(cudaMalloc(&w->d_p, (size_t)10 * N * sizeof(float)));
+  WS_TRY(cudaMalloc(&w->d_lpf, (size_t)6 * N * sizeof(float)));
+  WS_TRY(cudaMalloc(&w->d_dt, sizeof(float)));
+  WS_TRY(cudaHostAlloc(&w->h_init, (size_t)10 * N * sizeof(float), cudaHostAllocDefault));
+#undef WS_TRY
+  *out_ws = w;
+  return 0;
+}
+
+int posekf_host_workspace_destroy(void* ws) {
+  host_ws_free(static_cast<HostWorkspace*>(ws));
+  return 0;
+}
+
+int posekf_replay_host_f32(int64_t N, int64_t T, const float* streams_host, float dt, const float* acc_ref_host,
+                           const float* mag_ref_host, const float* q_scale_host, const float* r_scale_host,
+                           float lpf_alpha_acc, float lpf_alpha_mag, const float* x0_host, const float* p0_host,
+                           float* out_x_host, float* out_p_host, float* out_traj_host, int64_t chunk_steps,
+                           int wahba_algo, int device, void* workspace) {
+  if (N <= 0 || T < 0 || !streams_host || !acc_ref_host || !mag_ref_host || !q_scale_host || !r_scale_host || !out_x_host)
+    return POSEKF_EINVAL;
+  const bool traj = out_traj_host != nullptr;
+  HostWorkspace* w = static_cast<HostWorkspace*>(workspace);
+  bool own = false;
+  if (w) {
+    if (w->N != N || w->device != device || (traj && !w->traj)) return POSEKF_EINVAL;
+  } else {
+    void* tmp = nullptr;
+    int rc0 = posekf_host_workspace_create(device, N, chunk_steps, traj ? 1 : 0, &tmp);
+    if (rc0 != 0) return rc0;
+    w = static_cast<HostWorkspace*>(tmp);
+    own = true;
+  }
+  PKF_CUDA_TRY(cudaSetDevice(device));
+  chunk_steps = w->chunk_steps;
+  const bool lpf = lpf_alpha_acc >= 0.f || lpf_alpha_mag >= 0.f;
+  int rc = 0;
+#define TRY(expr)                                                                  \
+  do {                                                                             \
+    cudaError_t _e = (expr);                                                       \
+    if (_e != cudaSuccess) { rc = (int)_e; if (own) host_ws_free(w); return rc; }  \
+  } while (0)
+  cudaStream_t s_copy = w->s_copy, s_comp = w->s_comp, s_out = w->s_out;
+  float* d_ref = w->d_ref; float* d_qr = w->d_qr; float* d_x = w->d_x; float* d_p = w->d_p; float* d_dt = w->d_dt;
+  float* d_lpf = lpf ? w->d_lpf : nullptr;
+  if (lpf) TRY(cudaMemsetAsync(d_lpf, 0, (size_t)6 * N * sizeof(float), s_comp));
   TRY(cudaMemcpyAsync(d_ref, acc_ref_host, (size_t)3 * N * sizeof(float), cudaMemcpyHostToDevice, s_comp));
   TRY(cudaMemcpyAsync(d_ref + 3 * N, mag_ref_host, (size_t)3 * N * sizeof(float), cudaMemcpyHostToDevice, s_comp));
   TRY(cudaMemcpyAsync(d_qr, q_scale_host, (size_t)N * sizeof(float), cudaMemcpyHostToDevice, s_comp));
   TRY(cudaMemcpyAsync(d_qr + N, r_scale_host, (size_t)N * sizeof(float), cudaMemcpyHostToDevice, s_comp));
   TRY(cudaMemcpyAsync(d_dt, &dt, sizeof(float), cudaMemcpyHostToDevice, s_comp));
+  // the first stream chunk is independent of the state set-up: start it right away
+  const int64_t n_chunks = (T + chunk_steps - 1) / chunk_steps;
+  auto issue_copy = [&](int64_t c) -> cudaError_t {
+    const int b = (int)(c & 1);
+    const int64_t t0 = c * chunk_steps, tc = std::min<int64_t>(chunk_steps, T - t0);
+    cudaError_t e;
+    if (c >= 2 && (e = cudaStreamWaitEvent(s_copy, w->ev_free[b], 0)) != cudaSuccess) return e;   // kernel of chunk c-2 done
+    if ((e = cudaMemcpyAsync(w->d_in[b], streams_host + (size_t)t0 * kChannels * N, (size_t)tc * kChannels * N * sizeof(float),
+                             cudaMemcpyHostToDevice, s_copy)) != cudaSuccess) return e;
+    return cudaEventRecord(w->ev_in[b], s_copy);
+  };
+  if (n_chunks > 0) TRY(issue_copy(0));
   {
-    // initial state: X = [1,0,0,0], P = I4 (PKF/main_file.py:23,26) unless given
-    std::vector<float> init;
+    // initial state: X = [1,0,0,0], P = I4 (PKF/main_file.py:23,26) unless given; the device state holds P/r
+    float* init = w->h_init;
     if (!x0_host) {
-      init.assign((size_t)4 * N, 0.f);
-      std::fill(init.begin(), init.begin() + N, 1.f);
-      TRY(cudaMemcpy(d_x, init.data(), (size_t)4 * N * sizeof(float), cudaMemcpyHostToDevice));
+      std::fill(init, init + N, 1.f);
+      std::fill(init + N, init + (size_t)4 * N, 0.f);
+      TRY(cudaMemcpyAsync(d_x, init, (size_t)4 * N * sizeof(float), cudaMemcpyHostToDevice, s_comp));
+      TRY(cudaStreamSynchronize(s_comp));      // init is reused below
     } else {
       TRY(cudaMemcpyAsync(d_x, x0_host, (size_t)4 * N * sizeof(float), cudaMemcpyHostToDevice, s_comp));
     }
-    // the device state holds P/r
-    init.assign((size_t)10 * N, 0.f);
     const int diag[4] = {0, 4, 7, 9};
     for (int k = 0; k < 10; ++k) {
       const bool on_diag = (k == diag[0] || k == diag[1] || k == diag[2] || k == diag[3]);
-      for (int64_t i = 0; i < N; ++i) {
-        const float p0 = p0_host ? p0_host[(size_t)k * N + i] : (on_diag ? 1.f : 0.f);
-        init[(size_t)k * N + i] = p0 / r_scale_host[i];
-      }
+      float* row = init + (size_t)k * N;
+      if (p0_host) { for (int64_t i = 0; i < N; ++i) row[i] = p0_host[(size_t)k * N + i] / r_scale_host[i]; }
+      else if (on_diag) { for (int64_t i = 0; i < N; ++i) row[i] = 1.f / r_scale_host[i]; }
+      else std::fill(row, row + N, 0.f);
     }
-    TRY(cudaMemcpy(d_p, init.data(), (size_t)10 * N * sizeof(float), cudaMemcpyHostToDevice));
+    TRY(cudaMemcpyAsync(d_p, init, (size_t)10 * N * sizeof(float), cudaMemcpyHostToDevice, s_comp));
   }
-  const int64_t n_chunks = (T + chunk_steps - 1) / chunk_steps;
   for (int64_t c = 0; c < n_chunks; ++c) {
     const int b = (int)(c & 1);
     const int64_t t0 = c * chunk_steps, tc = std::min<int64_t>(chunk_steps, T - t0);
-    if (c >= 2) TRY(cudaStreamWaitEvent(s_copy, ev_free[b], 0));          // kernel of chunk c-2 done with d_in[b]
-    TRY(cudaMemcpyAsync(d_in[b], streams_host + (size_t)t0 * kChannels * N, (size_t)tc * kChannels * N * sizeof(float),
-                        cudaMemcpyHostToDevice, s_copy));
-    TRY(cudaEventRecord(ev_in[b], s_copy));
-    TRY(cudaStreamWaitEvent(s_comp, ev_in[b], 0));
-    if (traj && c >= 2) TRY(cudaStreamWaitEvent(s_comp, ev_tfree[b], 0));  // D2H of chunk c-2 done with d_traj[b]
-    rc = posekf_replay_f32(N, tc, d_in[b], N, d_dt, 0, d_ref, d_ref + 3 * N, d_qr, d_qr + N, lpf_alpha_acc,
-                           lpf_alpha_mag, d_x, nullptr, d_p, d_lpf, traj ? d_traj[b] : nullptr, nullptr, nullptr, nullptr,
+    if (c + 1 < n_chunks) TRY(issue_copy(c + 1));                             // keep the copy engine one chunk ahead
+    TRY(cudaStreamWaitEvent(s_comp, w->ev_in[b], 0));
+    if (traj && c >= 2) TRY(cudaStreamWaitEvent(s_comp, w->ev_tfree[b], 0));  // D2H of chunk c-2 done with d_traj[b]
+    rc = posekf_replay_f32(N, tc, w->d_in[b], N, d_dt, 0, d_ref, d_ref + 3 * N, d_qr, d_qr + N, lpf_alpha_acc,
+                           lpf_alpha_mag, d_x, nullptr, d_p, d_lpf, traj ? w->d_traj[b] : nullptr, nullptr, nullptr, nullptr,
                            wahba_algo, POSEKF_STAGE_AUTO, s_comp);
-    if (rc != 0) { cleanup(); return rc; }
-    TRY(cudaEventRecord(ev_free[b], s_comp));
+    if (rc != 0) { if (own) host_ws_free(w); return rc; }
+    TRY(cudaEventRecord(w->ev_free[b], s_comp));
     if (traj) {
-      TRY(cudaEventRecord(ev_traj[b], s_comp));
-      TRY(cudaStreamWaitEvent(s_out, ev_traj[b], 0));
-      TRY(cudaMemcpyAsync(out_traj_host + (size_t)t0 * 4 * N, d_traj[b], (size_t)tc * 4 * N * sizeof(float),
+      TRY(cudaEventRecord(w->ev_traj[b], s_comp));
+      TRY(cudaStreamWaitEvent(s_out, w->ev_traj[b], 0));
+      TRY(cudaMemcpyAsync(out_traj_host + (size_t)t0 * 4 * N, w->d_traj[b], (size_t)tc * 4 * N * sizeof(float),
                           cudaMemcpyDeviceToHost, s_out));
-      TRY(cudaEventRecord(ev_tfree[b], s_out));
+      TRY(cudaEventRecord(w->ev_tfree[b], s_out));
     }
   }
   TRY(cudaMemcpyAsync(out_x_host, d_x, (size_t)4 * N * sizeof(float), cudaMemcpyDeviceToHost, s_comp));
@@ -981,7 +1033,7 @@ int posekf_replay_host_f32(int64_t N, int64_t T, const float* streams_host, floa
     for (int k = 0; k < 10; ++k)
       for (int64_t i = 0; i < N; ++i) out_p_host[(size_t)k * N + i] *= r_scale_host[i];
 #undef TRY
-  cleanup();
+  if (own) host_ws_free(w);
   return 0;
 }
 

@@ -177,6 +177,16 @@ def test_replay_from_host_buffers(cuda):
         assert torch.equal(x, dev_state.x.cpu())
         torch.testing.assert_close(p, dev_state.p.cpu() * 0.1, rtol=1e-6, atol=0)
         assert torch.equal(traj, dev_traj.cpu())
+    # reusable workspace: same results on repeated calls, with and without the trajectory
+    ws = B.HostWorkspace(N, chunk_steps=37, with_trajectory=True)
+    for want_traj in (True, False, True):
+        x, p, traj = B.replay_host(host, imu.acc_ref.cpu(), imu.mag_ref.cpu(), dt=imu.dt, q=q, r=r,
+                                   store_trajectory=want_traj, workspace=ws)
+        assert torch.equal(x, dev_state.x.cpu()) and (traj is None or torch.equal(traj, dev_traj.cpu()))
+    ws.close()
+    with pytest.raises(_lib.PosekfError):          # a workspace for another batch size is rejected
+        ws2 = B.HostWorkspace(N // 2)
+        B.replay_host(host, imu.acc_ref.cpu(), imu.mag_ref.cpu(), dt=imu.dt, q=q, r=r, workspace=ws2)
 
 
 def test_full_size_properties(cuda):
