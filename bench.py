@@ -33,7 +33,8 @@ BYTES_PER_STEP = 36            # 9 float32 inputs (final-state-only replay)
 # flops of the algorithm the kernel EXECUTES (FMA = 2, mul/add/rcp/rsqrt = 1; compares and selects
 # not counted), stage by stage in DESIGN.md "Roofline"; the SASS FFMA/FMUL/FADD/MUFU census of the
 # loop body gives the same number.  (SURVEY.md's 1570 is the un-restructured reference algorithm.)
-FLOPS = {"qr2": 516, "jacobi": 1294}
+FLOPS = {"qr2": 514, "jacobi": 1292}
+FLOPS_COMPENSATED_EXTRA = 32      # two-sum folding of the state (ncu: 536 + 10 MUFU flops per filter-step)
 
 
 def parse():
@@ -50,6 +51,8 @@ def parse():
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target wall time of the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--precise-state", action="store_true",
+                    help="compensated two-float state (needed for R >> Q sweeps, not for the Q=1, R=0.1 headline config)")
     return ap.parse_args()
 
 
@@ -227,7 +230,8 @@ def run_ours(args):
     torch.cuda.synchronize()
 
     def one_pass(state):
-        B.replay(streams, acc_ref, mag_ref, dt=0.01, q=q, r=r, state=state, wahba=args.wahba, staging=args.staging)
+        B.replay(streams, acc_ref, mag_ref, dt=0.01, q=q, r=r, state=state, wahba=args.wahba, staging=args.staging,
+                 precise_state=args.precise_state)
 
     def barrier():
         if world > 1:
@@ -318,7 +322,7 @@ def run_ours(args):
         pass
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
     hbm_src = "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
-    flops = FLOPS[args.wahba]
+    flops = FLOPS[args.wahba] + (FLOPS_COMPENSATED_EXTRA if args.precise_state else 0)
     ach_tf = steps_per_s_kernel * flops / 1e12
     ach_gbs = steps_per_s_kernel * BYTES_PER_STEP / 1e9
     # the binding roof is the slower of FP32 issue and HBM streaming (north_star); report both
@@ -342,10 +346,14 @@ def run_ours(args):
         "roofline_steps_per_s_per_gpu": 1.0 / max(t_fp32, t_hbm),
         "frac_of_roofline": steps_per_s_kernel * max(t_fp32, t_hbm),
     }
-    # ncu traffic, if a summary from the profiling pass is committed
+    # ncu traffic: dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of this kernel
+    # (profiles/r01_replay_tma*_ncu_full.json, taken at 200 timesteps), scaled per launch to this run's timesteps
     try:
-        prof = json.load(open(os.path.join(ROOT, "profiles", "r01_replay_ncu_summary.json")))
-        roofline["traffic"] = prof.get("dram_bytes_per_launch_scaled_to_bench")
+        name = "r01_replay_tma_compensated_ncu_full.json" if args.precise_state else "r01_replay_tma_ncu_full.json"
+        prof = json.load(open(os.path.join(ROOT, "profiles", name)))
+        per_step = prof["dram_bytes_per_launch"] / prof["workload"]["filter_steps"]
+        roofline["traffic"] = per_step * N * T
+        roofline["traffic_source"] = f"profiles/{name}: {per_step:.2f} B per filter-step measured vs {BYTES_PER_STEP} algorithmic"
     except Exception:
         pass
 
@@ -356,7 +364,8 @@ def run_ours(args):
         "config": {"workload": f"batched EKF replay: {N} independent filters x {T} steps per GPU, Q=1, R=0.1, dt=0.01 "
                                "(BASELINE.json configs[1])",
                    "filters_per_gpu": N, "timesteps": T, "wahba": args.wahba, "staging": args.staging,
-                   "store_trajectory": False, "parallelism": f"filter-sharded x{world}, no collective",
+                   "store_trajectory": False, "state": "two-float compensated" if args.precise_state else "float32",
+                   "parallelism": f"filter-sharded x{world}, no collective",
                    "l2_policy": f"input stream is {N * T * 36 / 1e9:.1f} GB per pass (>> 126 MB L2), streamed once"},
         "roofline": roofline,
         "e2e": e2e,

@@ -28,10 +28,10 @@ namespace {
 
 // tunables (overridable with -D for experiments; the defaults are what ships)
 #ifndef PKF_TMA_STEPS
-#define PKF_TMA_STEPS 2
+#define PKF_TMA_STEPS 4
 #endif
 #ifndef PKF_TMA_STAGES
-#define PKF_TMA_STAGES 3
+#define PKF_TMA_STAGES 2
 #endif
 #ifndef PKF_MIN_CTAS
 #define PKF_MIN_CTAS 6
