@@ -60,17 +60,33 @@ def parse():
 # CPU baseline: the oracle's scalar port (same numpy call sequence as the reference classes),
 # one independent trajectory per worker process, all host cores.
 # ------------------------------------------------------------------------------------------------
+_BARRIER = None
+
+
+def _cpu_init(barrier):
+    global _BARRIER
+    _BARRIER = barrier
+    for var in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[var] = "1"
+
+
 def _cpu_worker(args):
-    seed, n_steps = args
+    """One independent trajectory through the oracle's scalar port.  Input synthesis is untimed; all
+    workers start the timed replay together (barrier) so the rate is a genuine all-cores figure."""
+    seed, n_steps, use_barrier = args
     for var in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
         os.environ[var] = "1"
     import numpy as np
+    import torch
+    torch.set_num_threads(1)
     from oracle import ekf_oracle as O
     from poseestimationkf_b200.synth import make_imu
     imu = make_imu(1, n_steps, seed=seed, sigma=0.01)
     S = imu.streams.numpy().astype(np.float64)
     t_ns = np.arange(n_steps + 1, dtype=np.int64) * 10 ** 7
     a0, m0 = imu.acc_ref[:, 0].numpy().astype(np.float64), imu.mag_ref[:, 0].numpy().astype(np.float64)
+    if use_barrier and _BARRIER is not None:
+        _BARRIER.wait()
     t0 = time.perf_counter()
     X, _ = O.replay_scalar(t_ns, S[:, 0:3, 0], S[:, 3:6, 0], S[:, 6:9, 0], a0, m0, 1.0, 0.1)
     return time.perf_counter() - t0, float(X[-1, 0])
@@ -82,20 +98,21 @@ def cpu_baseline(target_seconds: float, cores: int | None = None):
     import multiprocessing as mp
     cores = cores or os.cpu_count() or 1
     # calibrate on one short run in this process
-    dt1, _ = _cpu_worker((0, 300))
+    dt1, _ = _cpu_worker((0, 300, False))
     per_step = dt1 / 300
     n_steps = int(max(500, min(20000, target_seconds / per_step)))
     ctx = mp.get_context("spawn")
-    with ctx.Pool(cores) as pool:
-        pool.map(_cpu_worker, [(i, 50) for i in range(cores)])          # warm the workers (imports)
-        t0 = time.perf_counter()
-        pool.map(_cpu_worker, [(100 + i, n_steps) for i in range(cores)])
-        wall = time.perf_counter() - t0
+    barrier = ctx.Barrier(cores)
+    with ctx.Pool(cores, initializer=_cpu_init, initargs=(barrier,)) as pool:
+        pool.map(_cpu_worker, [(i, 50, False) for i in range(cores)], chunksize=1)          # warm the workers (imports)
+        res = pool.map(_cpu_worker, [(100 + i, n_steps, True) for i in range(cores)], chunksize=1)
+    wall = max(r[0] for r in res)
     single = 1.0 / per_step
     return {"value": cores * n_steps / wall, "unit": UNIT, "cores": cores, "kind": "port",
             "sample": f"{cores} independent synthetic 100 Hz trajectories x {n_steps} steps, Q=1 R=0.1, float64 numpy "
-                      f"oracle port of the reference classes (one process per core); single-core rate {single:.0f} steps/s",
-            "single_core_value": single}
+                      f"oracle port of the reference classes (one process per core, started together); "
+                      f"single-core rate {single:.0f} steps/s",
+            "single_core_value": single, "seconds": wall}
 
 
 def cpu_baseline_compiled(n_filters: int = 16384, n_steps: int = 500):
@@ -129,7 +146,7 @@ def run_reference(args):
     v = sum(vals) / len(vals)
     base["value"] = v
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": 1e3 * base["seconds"], "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": "reference Python EKF replay (oracle port) on host cores, bounded sample",
                        "filters_per_gpu": args.filters, "timesteps": args.timesteps},

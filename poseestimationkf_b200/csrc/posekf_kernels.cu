@@ -5,8 +5,10 @@
 //     Q/R scalars live in registers for the whole launch -- a launch covers MANY timesteps;
 //   * IMU samples are a structure-of-arrays stream [T][9][N] (filter index fastest), so a warp's
 //     load of one channel of one step is one 128-byte line;
-//   * staging: either plain coalesced LDG with a one-step register prefetch, or a TMA
-//     (cp.async.bulk.tensor.3d) ring of [TC][9][128] tiles in shared memory driven by mbarriers;
+//   * staging: a TMA (cp.async.bulk.tensor.3d) ring of [TC][9][128] tiles in shared memory driven by
+//     mbarriers (default), or plain coalesced LDG with a one-step register prefetch (unaligned input);
+//   * template variants: Wahba solver (rank-2 QR / Jacobi), low-pass stage, auxiliary outputs
+//     (trajectory, flip mask, tuning loss), compensated two-float state;
 //   * no tensor cores (per-filter matrices are 4x4), no inter-thread communication on the step;
 //   * filters are independent: multi-GPU = shard N, no collective on this path.
 //
@@ -1064,8 +1066,6 @@ int posekf_tracks_f32(int64_t n_filters, int64_t n_steps, const float* streams, 
   if (!out_gyro && !out_wahba && !gyro_state) return POSEKF_EINVAL;
   if (out_wahba && (!acc_ref || !mag_ref)) return POSEKF_EINVAL;
   if (((reinterpret_cast<uintptr_t>(out_gyro) | reinterpret_cast<uintptr_t>(out_wahba)) & 15) != 0) return POSEKF_EALIGN;
-  static const float zero3[3] = {0.f, 0.f, 0.f};
-  (void)zero3;
   TracksParams p{n_filters, n_steps, n_streams, streams, dt, dt_per_step, acc_ref ? acc_ref : streams,
                  mag_ref ? mag_ref : streams, k_acc, k_mag, weights_from_acc, gyro_state, out_gyro, out_wahba};
   cudaStream_t st = (cudaStream_t)stream;
