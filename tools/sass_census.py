@@ -34,11 +34,12 @@ def opcode(line):
 
 out = {}
 for name, lines in funcs.items():
-    m = re.search(r"replay_(tma|ldg)_kernelILi(\d)ELb(\d)ELb(\d)E", name)
+    m = re.search(r"replay_(tma|ldg)_kernelILi(\d)ELb(\d)ELb(\d)ELb(\d)E", name)
     if not m:
         continue
-    key = f"replay_{m.group(1)}<algo={m.group(2)},lpf={m.group(3)},aux={m.group(4)}>"
+    key = f"replay_{m.group(1)}<algo={m.group(2)},lpf={m.group(3)},aux={m.group(4)},comp={m.group(5)}>"
     ops = collections.Counter(opcode(l) for l in lines)
-    fp = {k: ops[k] for k in ("FFMA", "FMUL", "FADD", "MUFU", "FSEL", "FSETP", "FMNMX")}
+    fp = {k: ops[k] for k in ("FFMA", "FMUL", "FADD", "MUFU", "FSEL", "FSETP", "UTMALDG", "SYNCS", "LDS", "LDG", "STG",
+                              "LDL", "STL", "HMMA")}
     out[key] = {"total_static": len(lines), **fp}
 print(json.dumps(out, indent=1))
