@@ -741,6 +741,28 @@ __global__ void __launch_bounds__(256) norm_kernel(int64_t N, int k, const float
   out[n] = sqrtf(acc);
 }
 
+// host-replay helpers: initial state and P <-> P/r conversion on the device
+__global__ void __launch_bounds__(256)
+    host_init_state_kernel(int64_t N, int have_x0, int have_p0, const float* __restrict__ r, float* x, float* p) {
+  const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  if (!have_x0) { x[n] = 1.f; x[N + n] = 0.f; x[2 * N + n] = 0.f; x[3 * N + n] = 0.f; }     // PKF/main_file.py:26
+  const float ir = 1.f / r[n];
+#pragma unroll
+  for (int k = 0; k < 10; ++k) {
+    const bool diag = (k == 0 || k == 4 || k == 7 || k == 9);
+    const float p0 = have_p0 ? p[k * N + n] : (diag ? 1.f : 0.f);                            // PKF/main_file.py:23
+    p[k * N + n] = p0 * ir;
+  }
+}
+__global__ void __launch_bounds__(256) host_unscale_p_kernel(int64_t N, const float* __restrict__ r, float* p) {
+  const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  const float rr = r[n];
+#pragma unroll
+  for (int k = 0; k < 10; ++k) p[k * N + n] *= rr;
+}
+
 // FP32 peak probe: 16 independent FFMA chains per thread, all SMs full.
 constexpr int kProbeIters = 8192, kProbeAcc = 16;
 __global__ void __launch_bounds__(256) fp32_probe_kernel(float* out, float b, float c) {
@@ -870,7 +892,6 @@ struct HostWorkspace {
               ev_tfree[2] = {nullptr, nullptr};
   float *d_in[2] = {nullptr, nullptr}, *d_traj[2] = {nullptr, nullptr};
   float *d_ref = nullptr, *d_qr = nullptr, *d_x = nullptr, *d_p = nullptr, *d_lpf = nullptr, *d_dt = nullptr;
-  float* h_init = nullptr;   // pinned scratch [10][N]
 };
 
 static void host_ws_free(HostWorkspace* w) {
@@ -886,7 +907,6 @@ static void host_ws_free(HostWorkspace* w) {
   }
   float* ptrs[] = {w->d_ref, w->d_qr, w->d_x, w->d_p, w->d_lpf, w->d_dt};
   for (float* q : ptrs) if (q) cudaFree(q);
-  if (w->h_init) cudaFreeHost(w->h_init);
   if (w->s_copy) cudaStreamDestroy(w->s_copy);
   if (w->s_comp) cudaStreamDestroy(w->s_comp);
   if (w->s_out) cudaStreamDestroy(w->s_out);
@@ -926,7 +946,6 @@ int posekf_host_workspace_create(int device, int64_t n_filters, int64_t chunk_st
   WS_TRY(cudaMalloc(&w->d_p, (size_t)10 * N * sizeof(float)));
   WS_TRY(cudaMalloc(&w->d_lpf, (size_t)6 * N * sizeof(float)));
   WS_TRY(cudaMalloc(&w->d_dt, sizeof(float)));
-  WS_TRY(cudaHostAlloc(&w->h_init, (size_t)10 * N * sizeof(float), cudaHostAllocDefault));
 #undef WS_TRY
   *out_ws = w;
   return 0;
@@ -986,27 +1005,11 @@ int posekf_replay_host_f32(int64_t N, int64_t T, const float* streams_host, floa
     return cudaEventRecord(w->ev_in[b], s_copy);
   };
   if (n_chunks > 0) TRY(issue_copy(0));
-  {
-    // initial state: X = [1,0,0,0], P = I4 (PKF/main_file.py:23,26) unless given; the device state holds P/r
-    float* init = w->h_init;
-    if (!x0_host) {
-      std::fill(init, init + N, 1.f);
-      std::fill(init + N, init + (size_t)4 * N, 0.f);
-      TRY(cudaMemcpyAsync(d_x, init, (size_t)4 * N * sizeof(float), cudaMemcpyHostToDevice, s_comp));
-      TRY(cudaStreamSynchronize(s_comp));      // init is reused below
-    } else {
-      TRY(cudaMemcpyAsync(d_x, x0_host, (size_t)4 * N * sizeof(float), cudaMemcpyHostToDevice, s_comp));
-    }
-    const int diag[4] = {0, 4, 7, 9};
-    for (int k = 0; k < 10; ++k) {
-      const bool on_diag = (k == diag[0] || k == diag[1] || k == diag[2] || k == diag[3]);
-      float* row = init + (size_t)k * N;
-      if (p0_host) { for (int64_t i = 0; i < N; ++i) row[i] = p0_host[(size_t)k * N + i] / r_scale_host[i]; }
-      else if (on_diag) { for (int64_t i = 0; i < N; ++i) row[i] = 1.f / r_scale_host[i]; }
-      else std::fill(row, row + N, 0.f);
-    }
-    TRY(cudaMemcpyAsync(d_p, init, (size_t)10 * N * sizeof(float), cudaMemcpyHostToDevice, s_comp));
-  }
+  // initial state: X = [1,0,0,0], P = I4 (PKF/main_file.py:23,26) unless given; the device state holds P/r
+  if (x0_host) TRY(cudaMemcpyAsync(d_x, x0_host, (size_t)4 * N * sizeof(float), cudaMemcpyHostToDevice, s_comp));
+  if (p0_host) TRY(cudaMemcpyAsync(d_p, p0_host, (size_t)10 * N * sizeof(float), cudaMemcpyHostToDevice, s_comp));
+  host_init_state_kernel<<<blocks_for(N, 256), 256, 0, s_comp>>>(N, x0_host != nullptr, p0_host != nullptr, d_qr + N, d_x, d_p);
+  TRY(cudaPeekAtLastError());
   for (int64_t c = 0; c < n_chunks; ++c) {
     const int b = (int)(c & 1);
     const int64_t t0 = c * chunk_steps, tc = std::min<int64_t>(chunk_steps, T - t0);
@@ -1027,13 +1030,14 @@ int posekf_replay_host_f32(int64_t N, int64_t T, const float* streams_host, floa
     }
   }
   TRY(cudaMemcpyAsync(out_x_host, d_x, (size_t)4 * N * sizeof(float), cudaMemcpyDeviceToHost, s_comp));
-  if (out_p_host) TRY(cudaMemcpyAsync(out_p_host, d_p, (size_t)10 * N * sizeof(float), cudaMemcpyDeviceToHost, s_comp));
+  if (out_p_host) {
+    host_unscale_p_kernel<<<blocks_for(N, 256), 256, 0, s_comp>>>(N, d_qr + N, d_p);     // P/r -> P
+    TRY(cudaPeekAtLastError());
+    TRY(cudaMemcpyAsync(out_p_host, d_p, (size_t)10 * N * sizeof(float), cudaMemcpyDeviceToHost, s_comp));
+  }
   TRY(cudaStreamSynchronize(s_comp));
   TRY(cudaStreamSynchronize(s_out));
   TRY(cudaStreamSynchronize(s_copy));
-  if (out_p_host)
-    for (int k = 0; k < 10; ++k)
-      for (int64_t i = 0; i < N; ++i) out_p_host[(size_t)k * N + i] *= r_scale_host[i];
 #undef TRY
   if (own) host_ws_free(w);
   return 0;

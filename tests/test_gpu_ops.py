@@ -243,3 +243,25 @@ def test_preprocess_and_log_replay(cuda):
     logged = np.asarray(d.quart_xk[1:])
     assert np.abs(traj[:, 0].cpu().numpy() - logged).max() < 2e-5        # log precision is 1e-6 per component;
     # inputs were themselves rounded to 6 decimals by the writer, hence the looser bound
+
+
+def test_wahba_negative_weights_on_device(cuda):
+    rng = np.random.default_rng(5)
+    M = 1000
+
+    def unit(v):
+        return v / np.linalg.norm(v, axis=-1, keepdims=True)
+    arrs = [unit(rng.normal(size=(M, 3))).astype(np.float32) for _ in range(4)]
+    ka = (rng.uniform(0.1, 2.0, M) * rng.choice([-1.0, 1.0], M)).astype(np.float32)
+    km = (rng.uniform(0.1, 2.0, M) * rng.choice([-1.0, 1.0], M)).astype(np.float32)
+    a64 = [a.astype(np.float64) for a in arrs]
+    Rref = O.wahba_rotation_batched(*a64, ka.astype(np.float64), km.astype(np.float64))
+    Bm = (ka.astype(np.float64)[:, None, None] * a64[0][:, :, None] * a64[2][:, None, :]
+          + km.astype(np.float64)[:, None, None] * a64[1][:, :, None] * a64[3][:, None, :])
+    sv = np.linalg.svd(Bm, compute_uv=False)
+    ok = sv[:, 1] > 0.05 * sv[:, 0]
+    for algo in ("qr2", "jacobi"):
+        R, _ = B.wahba(*[_dev(a.T, cuda) for a in arrs], k_acc=_dev(ka, cuda), k_mag=_dev(km, cuda), want_rotation=True,
+                       want_quaternion=False, algo=algo)
+        err = np.abs(R.cpu().numpy().T.reshape(-1, 3, 3) - Rref).max(axis=(1, 2))
+        assert err[ok].max() < 2e-5, (algo, err[ok].max())
