@@ -288,3 +288,36 @@ def test_compensated_state_long_replay_extreme_tunings(cuda):
         B.replay(imu.streams[t0:t1].contiguous(), imu.acc_ref, imu.mag_ref, dt=imu.dt, q=q_t, r=r_t, n_filters=G * Ns,
                  state=st_c, precise_state=True)
     assert torch.equal(st_c.x, st_auto.x) and torch.equal(st_c.x_lo, st_auto.x_lo) and torch.equal(st_c.p, st_auto.p)
+
+
+def test_no_out_of_bounds_writes(cuda):
+    """compute-sanitizer is not available on the pool, so output bounds are checked with canaries:
+    every output lives inside a larger poisoned allocation whose guard bands must stay untouched."""
+    GUARD, POISON = 4096, -12345.0
+
+    def guarded(shape, dtype=torch.float32):
+        n = int(np.prod(shape))
+        buf = torch.full((n + 2 * GUARD,), POISON if dtype == torch.float32 else 77, dtype=dtype, device=cuda)
+        return buf, buf[GUARD:GUARD + n].view(shape)
+
+    def intact(buf, n):
+        val = POISON if buf.dtype == torch.float32 else 77
+        return bool((buf[:GUARD] == val).all() and (buf[GUARD + n:] == val).all())
+
+    for N, T, staging in ((1000, 37, "tma"), (1000, 37, "ldg"), (130, 9, "auto"), (516, 5, "tma"), (3, 2, "ldg")):
+        imu = make_imu(N, T, seed=N + T, sigma=0.01, device=cuda, keep_truth=True)
+        truth = imu.q_true.permute(0, 2, 1).to(torch.float32).contiguous()
+        for precise in (False, True):
+            bx, x = guarded((4, N)); bl, xlo = guarded((4, N)); bp, p = guarded((10, N)); bf, lpf = guarded((6, N))
+            bt, traj = guarded((T, N, 4)); bloss, loss = guarded((N,))
+            x.zero_(); x[0] = 1.0; xlo.zero_(); p.zero_(); p[[0, 4, 7, 9]] = 10.0; lpf.zero_(); loss.zero_()
+            st = B.ReplayState(x, p, 0.1, lpf, None, xlo if precise else None)
+            _, _, flips = B.replay(imu.streams, imu.acc_ref, imu.mag_ref, dt=imu.dt, state=st, out_traj=traj, store_flips=True,
+                                   truth=truth, loss=loss, lpf_alpha_acc=0.2, lpf_alpha_mag=0.2, precise_state=precise,
+                                   staging=staging)
+            torch.cuda.synchronize()
+            assert intact(bx, 4 * N) and intact(bp, 10 * N) and intact(bf, 6 * N) and intact(bt, T * N * 4) and intact(bloss, N)
+            assert intact(bl, 4 * N)
+            assert torch.isfinite(traj).all() and (traj != POISON).all() and (loss >= 0).all()
+            if not precise:
+                assert (xlo == 0).all()          # untouched when the compensated variant is off
