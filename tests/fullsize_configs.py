@@ -1,5 +1,7 @@
 """Runs the other BASELINE.json configs at full size on one GPU and prints one JSON line each
-(supplementary evidence for profiles/; bench.py is the contract benchmark).
+(supplementary evidence for profiles/; bench.py is the contract benchmark).  Lives under tests/ because it
+checks every result against the float64 oracle (only tests/, smoke() and bench.py's CPU arm may use oracle/).
+    python tests/fullsize_configs.py [c3] [c4] [c5]
 
   C3  Q/R tuning sweep: 64x64 log-spaced (Q,R) grid x 256 trajectories x 5000 steps (1 Mi filters,
       shared 46 MB stream, on-device loss surface, compensated state)
@@ -15,7 +17,7 @@ import time
 import numpy as np
 import torch
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))   # repo root
 from oracle import c_oracle as CO
 from oracle import ekf_oracle as O
 from poseestimationkf_b200 import batched as B
