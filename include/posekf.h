@@ -212,6 +212,12 @@ int posekf_quat2rpy_f32(int64_t n, const float* q, float* out_rpy_deg, void* str
 /* UtilityFunctions.norm for N vectors of length k: v [k][N] -> out [N].  PKF/UtilityFunctions.py:16-21 */
 int posekf_norm_f32(int64_t n, int k, const float* v, float* out, void* stream);
 
+/* Plumbing for hosts that bind this library without a CUDA runtime binding of their own (the
+ * reference-named Python modules use them for their per-call staging): an asynchronous copy between a
+ * (preferably page-locked) host buffer and device memory on `stream`, and a stream synchronise. */
+int posekf_copy_async(void* dst, const void* src, int64_t bytes, int to_device, void* stream);
+int posekf_stream_sync(void* stream);
+
 /* Measurement helper (not in the reference): runs a register-resident FFMA loop on every SM and
  * returns the achieved FP32 rate in TFLOP/s (2 flop per FFMA) -- the denominator of the FP32
  * roofline, measured in the same process and at the same clocks as the filter kernel. */

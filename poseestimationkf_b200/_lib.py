@@ -35,6 +35,8 @@ _SIGNATURES = {
     "posekf_lowpass_f32": [_i64, _i64, _vp, _f32, _vp, _vp, _vp],
     "posekf_quat2rpy_f32": [_i64, _vp, _vp, _vp],
     "posekf_norm_f32": [_i64, _int, _vp, _vp, _vp],
+    "posekf_copy_async": [_vp, _vp, _i64, _int, _vp],
+    "posekf_stream_sync": [_vp],
     "posekf_fp32_peak_tflops": [_int, C.POINTER(C.c_double), C.POINTER(C.c_double)],
 }
 EXPORTS = ["posekf_version"] + list(_SIGNATURES)

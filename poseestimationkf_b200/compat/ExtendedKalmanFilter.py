@@ -7,11 +7,15 @@ use `poseestimationkf_b200.batched.replay`, which runs the loop of main_file.py:
 from __future__ import annotations
 
 import numpy as np
-import torch
 
-from poseestimationkf_b200 import batched as _b
+from poseestimationkf_b200 import _lib
 from Wahba import Wahba
-from _bridge import device, to_dev, to_host
+from _bridge import as_rows, call, from_rows
+
+
+def _dt_rows(dt_seconds, n):
+    dt = np.asarray(dt_seconds, dtype=np.float64)
+    return np.broadcast_to(dt.astype(np.float32).reshape(-1), (n,)).reshape(1, n).copy()
 
 
 class KalmanFilter:
@@ -29,48 +33,58 @@ class KalmanFilter:
         self.R *= r
 
     def Comparator(self, q1, q2):                          # :16-23
-        a, batched = to_dev(q1, (4,))
-        b, _ = to_dev(q2, (4,))
-        return to_host(_b.comparator(a, b), (4,), batched)
+        a, batched = as_rows(q1, (4,))
+        b, _ = as_rows(q2, (4,))
+        lib = _lib.load()
+        out, = call([a, b], [4], lambda i, o, n, s: lib.posekf_comparator_f32(n, i[0], i[1], o[0], s))
+        return from_rows(out, (4,), batched)
 
     @staticmethod
     def RungeKutta4(q_0, T, w):                            # :25-41 ; T is a time step in NANOSECONDS
-        q, batched = to_dev(q_0, (4,))
-        wd, _ = to_dev(w, (3,))
-        dt = np.asarray(T, dtype=np.float64) * (10 ** -9)
-        if dt.ndim == 0:
-            out = _b.rk4(q, float(dt), wd)
-        else:
-            out = _b.rk4(q, torch.from_numpy(dt.astype(np.float32)).to(device()), wd)
-        return to_host(out, (4,), batched)
+        q, batched = as_rows(q_0, (4,))
+        wd, _ = as_rows(w, (3,))
+        dt = _dt_rows(np.asarray(T, dtype=np.float64) * (10 ** -9), q.shape[1])
+        lib = _lib.load()
+        out, = call([q, dt, wd], [4], lambda i, o, n, s: lib.posekf_rk4_f32(n, i[0], i[1], 0, i[2], o[0], s))
+        return from_rows(out, (4,), batched)
 
     def GetJacobian_A(self, w):                            # :43-48
-        wd, batched = to_dev(w, (3,))
-        return to_host(_b.jacobian_a(wd), (4, 4), batched)
+        wd, batched = as_rows(w, (3,))
+        lib = _lib.load()
+        out, = call([wd], [16], lambda i, o, n, s: lib.posekf_jacobians_f32(n, i[0], o[0], None, None, s))
+        return from_rows(out, (4, 4), batched)
 
     def GetJacobian_B(self, q):                            # :51-56
-        qd, batched = to_dev(q, (4,))
-        return to_host(_b.jacobian_b(qd), (4, 3), batched)
+        qd, batched = as_rows(q, (4,))
+        lib = _lib.load()
+        out, = call([qd], [12], lambda i, o, n, s: lib.posekf_jacobians_f32(n, None, None, i[0], o[0], s))
+        return from_rows(out, (4, 3), batched)
 
     def Prediction(self, Gyro, T, X_k, P_k):               # :58-68
-        g, batched = to_dev(Gyro, (3,))
-        x, _ = to_dev(X_k, (4,))
-        p, _ = to_dev(P_k, (4, 4))
-        dt = (np.asarray(T, dtype=np.float64) - np.asarray(self.previousT, dtype=np.float64)) * (10 ** -9)
-        dt_arg = float(dt) if dt.ndim == 0 else torch.from_numpy(dt.astype(np.float32)).to(device())
-        dev = device()
-        qm = torch.from_numpy(np.ascontiguousarray(self.Q, dtype=np.float32).reshape(-1)).to(dev)
-        rm = torch.from_numpy(np.ascontiguousarray(self.R, dtype=np.float32).reshape(-1)).to(dev)
-        z, pn, k = _b.predict(g, dt_arg, x, p, qm, rm)
+        g, batched = as_rows(Gyro, (3,))
+        x, _ = as_rows(X_k, (4,))
+        p, _ = as_rows(P_k, (4, 4))
+        n = g.shape[1]
+        dt = _dt_rows((np.asarray(T, dtype=np.float64) - np.asarray(self.previousT, dtype=np.float64)) * (10 ** -9), n)
+        qm = np.ascontiguousarray(self.Q, dtype=np.float32).reshape(-1)
+        rm = np.ascontiguousarray(self.R, dtype=np.float32).reshape(-1)
+        lib = _lib.load()
+        z, pn, k = call([g, dt, x, p, qm, rm], [4, 16, 16],
+                        lambda i, o, n_, s: lib.posekf_predict_f32(n_, i[0], i[1], 0, i[2], i[3], i[4], i[5], None, None,
+                                                                   o[0], o[1], o[2], s))
         self.previousT = T                                 # :67
-        return to_host(z, (4,), batched), to_host(pn, (4, 4), batched), to_host(k, (4, 4), batched)
+        return from_rows(z, (4,), batched), from_rows(pn, (4, 4), batched), from_rows(k, (4, 4), batched)
 
     def Correction(self, Mag, Acc, z_k, P_k, K_k):         # :70-80 (NB: Mag before Acc)
-        m, batched = to_dev(Mag, (3,))
-        a, _ = to_dev(Acc, (3,))
-        z, _ = to_dev(z_k, (4,))
-        p, _ = to_dev(P_k, (4, 4))
-        k, _ = to_dev(K_k, (4, 4))
-        ra, rm = self.wahba._refs(a.shape[1])
-        x, pn, _, _ = _b.correct(m, a, ra, rm, z, p, k)
-        return to_host(x, (4,), batched), to_host(pn, (4, 4), batched)
+        m, batched = as_rows(Mag, (3,))
+        a, _ = as_rows(Acc, (3,))
+        z, _ = as_rows(z_k, (4,))
+        p, _ = as_rows(P_k, (4, 4))
+        k, _ = as_rows(K_k, (4, 4))
+        ra, rm, shared = self.wahba._ref_rows(a.shape[1])
+        lib = _lib.load()
+        algo = _lib.WAHBA[self.wahba.algo]
+        x, pn = call([m, a, ra, rm, z, p, k], [4, 16],
+                     lambda i, o, n, s: lib.posekf_correct_f32(n, i[0], i[1], i[2], i[3], shared, i[4], i[5], i[6], o[0], o[1],
+                                                               None, None, algo, s))
+        return from_rows(x, (4,), batched), from_rows(pn, (4, 4), batched)

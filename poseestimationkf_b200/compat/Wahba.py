@@ -4,10 +4,9 @@ for any weights in float32; "jacobi": B formed as the reference forms it + one-s
 from __future__ import annotations
 
 import numpy as np
-import torch
 
-from poseestimationkf_b200 import batched as _b
-from _bridge import to_dev, to_host
+from poseestimationkf_b200 import _lib
+from _bridge import as_rows, call, from_rows
 
 
 class Wahba:
@@ -17,35 +16,47 @@ class Wahba:
         self.w_initial_acc = acc
         self.w_initial_mag = mag
 
-    def _refs(self, n):
-        ra, ba = to_dev(self.w_initial_acc, (3,))
-        rm, _ = to_dev(self.w_initial_mag, (3,))
-        if not ba and n > 1:
-            ra, rm = ra.expand(3, n).contiguous(), rm.expand(3, n).contiguous()
-        return ra, rm
+    def _ref_rows(self, n):
+        """reference vectors as rows; one shared pair ([3] each) or one per filter ([3, n])"""
+        ra, ba = as_rows(self.w_initial_acc, (3,))
+        rm, _ = as_rows(self.w_initial_mag, (3,))
+        if ba:
+            if ra.shape[1] != n:
+                raise ValueError("batched reference vectors must match the batch size")
+            return ra, rm, 0
+        return ra.reshape(3), rm.reshape(3), 1
 
-    def _weights(self, k, n, dev):
+    @staticmethod
+    def _weights(k, n):
         k = np.asarray(k, dtype=np.float64)
-        if k.ndim == 0:
-            return torch.full((n,), float(k), dtype=torch.float32, device=dev)
-        return torch.from_numpy(k.astype(np.float32)).to(dev)
+        return np.broadcast_to(k.astype(np.float32).reshape(-1), (n,)).reshape(1, n).copy()
 
     def _solve(self, acc, mag, k_acc, k_mag, want_rotation):
-        a, batched = to_dev(acc, (3,))
-        m, _ = to_dev(mag, (3,))
+        a, batched = as_rows(acc, (3,))
+        m, _ = as_rows(mag, (3,))
         n = a.shape[1]
-        ra, rm = self._refs(n)
-        R, q = _b.wahba(ra, rm, a, m, k_acc=self._weights(k_acc, n, a.device), k_mag=self._weights(k_mag, n, a.device),
-                        want_rotation=want_rotation, want_quaternion=not want_rotation, algo=self.algo)
-        return (to_host(R, (3, 3), batched) if want_rotation else to_host(q, (4,), batched))
+        ra, rm, shared = self._ref_rows(n)
+        lib = _lib.load()
+        algo = _lib.WAHBA[self.algo]
+        if want_rotation:
+            out, = call([ra, rm, a, m, self._weights(k_acc, n), self._weights(k_mag, n)], [9],
+                        lambda i, o, n_, s: lib.posekf_wahba_f32(n_, i[0], i[1], shared, i[2], i[3], i[4], i[5], 0.0, 0.0, 0,
+                                                                 o[0], None, algo, 0, s))
+            return from_rows(out, (3, 3), batched)
+        out, = call([ra, rm, a, m, self._weights(k_acc, n), self._weights(k_mag, n)], [4],
+                    lambda i, o, n_, s: lib.posekf_wahba_f32(n_, i[0], i[1], shared, i[2], i[3], i[4], i[5], 0.0, 0.0, 0,
+                                                             None, o[0], algo, 0, s))
+        return from_rows(out, (4,), batched)
 
     def getRotation(self, acc, mag, k_acc, k_mag):         # :8-17
         return self._solve(acc, mag, k_acc, k_mag, True)
 
     @staticmethod
     def RotationMatrix2Quart(M):                           # :20-47
-        r, batched = to_dev(M, (3, 3))
-        return to_host(_b.rot2quat(r), (4,), batched)
+        r, batched = as_rows(M, (3, 3))
+        lib = _lib.load()
+        out, = call([r], [4], lambda i, o, n, s: lib.posekf_rot2quat_f32(n, i[0], o[0], s))
+        return from_rows(out, (4,), batched)
 
     def getQuarternion(self, acc, mag, k_acc, k_mag):      # :49-50
         return self._solve(acc, mag, k_acc, k_mag, False)

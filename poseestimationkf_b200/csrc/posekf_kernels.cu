@@ -1181,6 +1181,19 @@ int posekf_norm_f32(int64_t n, int k, const float* v, float* out, void* stream) 
   return launch_status();
 }
 
+int posekf_copy_async(void* dst, const void* src, int64_t bytes, int to_device, void* stream) {
+  if (bytes < 0 || (bytes > 0 && (!dst || !src))) return POSEKF_EINVAL;
+  if (bytes == 0) return 0;
+  PKF_CUDA_TRY(cudaMemcpyAsync(dst, src, (size_t)bytes, to_device ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost,
+                               (cudaStream_t)stream));
+  return 0;
+}
+
+int posekf_stream_sync(void* stream) {
+  PKF_CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+  return 0;
+}
+
 int posekf_fp32_peak_tflops(int device, double* out_tflops, double* out_ms) {
   if (!out_tflops) return POSEKF_EINVAL;
   PKF_CUDA_TRY(cudaSetDevice(device));
