@@ -46,7 +46,7 @@ def parse():
     ap.add_argument("--filters", type=int, default=1 << 20, help="filters per GPU")
     ap.add_argument("--timesteps", type=int, default=1000)
     ap.add_argument("--wahba", default="qr2", choices=["qr2", "jacobi"])
-    ap.add_argument("--staging", default="auto", choices=["auto", "ldg", "tma"])
+    ap.add_argument("--staging", default="auto", choices=["auto", "ldg", "tma", "tma_packed"])
     ap.add_argument("--e2e-timesteps", type=int, default=250, help="timesteps of the host-buffer (e2e) replay")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target wall time of the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -340,6 +340,7 @@ def run_ours(args):
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
     hbm_src = "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
     flops = FLOPS[args.wahba] + (FLOPS_COMPENSATED_EXTRA if args.precise_state else 0)
+    packed = args.staging in ("auto", "tma_packed") and args.wahba == "qr2" and N % 4 == 0
     ach_tf = steps_per_s_kernel * flops / 1e12
     ach_gbs = steps_per_s_kernel * BYTES_PER_STEP / 1e9
     # the binding roof is the slower of FP32 issue and HBM streaming (north_star); report both
@@ -353,7 +354,8 @@ def run_ours(args):
         "unit": "TFLOP/s" if bound == "fp32" else "GB/s",
         "frac": (ach_tf / fp32_peak) if bound == "fp32" else (ach_gbs / hbm_peak),
         "traffic": None,
-        "kernel": f"replay_{'tma' if args.staging != 'ldg' else 'ldg'}_kernel<{args.wahba}>",
+        "kernel": ("replay_tma2_kernel (packed f32x2, two filters per thread)" if packed
+                   else f"replay_{'tma' if args.staging != 'ldg' else 'ldg'}_kernel<{args.wahba}>"),
         "kernel_ms": avg_kernel_ms,
         "algorithmic_flops_per_filter_step": flops,
         "algorithmic_bytes_per_filter_step": BYTES_PER_STEP,
@@ -366,7 +368,8 @@ def run_ours(args):
     # ncu traffic: dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of this kernel
     # (profiles/r01_replay_tma*_ncu_full.json, taken at 200 timesteps), scaled per launch to this run's timesteps
     try:
-        name = "r01_replay_tma_compensated_ncu_full.json" if args.precise_state else "r01_replay_tma_ncu_full.json"
+        name = ("r01_replay_tma_compensated_ncu_full.json" if args.precise_state else
+                "r01_replay_packed_ncu_full.json" if packed else "r01_replay_tma_ncu_full.json")
         prof = json.load(open(os.path.join(ROOT, "profiles", name)))
         per_step = prof["dram_bytes_per_launch"] / prof["workload"]["filter_steps"]
         roofline["traffic"] = per_step * N * T

@@ -39,6 +39,8 @@ extern "C" {
 #define POSEKF_STAGE_AUTO 0     /* TMA when alignment allows, else LDG */
 #define POSEKF_STAGE_LDG  1     /* coalesced global loads, register prefetch one step ahead */
 #define POSEKF_STAGE_TMA  2     /* cp.async.bulk.tensor (TMA) multi-stage shared-memory ring */
+#define POSEKF_STAGE_TMA_PACKED 3 /* same ring, two filters per thread in packed f32x2 registers (FFMA2);
+                                     rank-2 Wahba, no trajectory/flip/loss outputs, N even */
 
 /* Library / build info: returns a static string such as "posekf_b200 0.1 sm_100a". */
 const char* posekf_version(void);

@@ -13,7 +13,7 @@ _i64, _int, _f32, _vp = C.c_int64, C.c_int, C.c_float, C.c_void_p
 
 EINVAL, EALIGN, ENODEV = -1, -2, -3
 WAHBA = {"qr2": 0, "jacobi": 1}
-STAGING = {"auto": 0, "ldg": 1, "tma": 2}
+STAGING = {"auto": 0, "ldg": 1, "tma": 2, "tma_packed": 3}
 
 _SIGNATURES = {
     "posekf_replay_f32": [_i64, _i64, _vp, _i64, _vp, _int, _vp, _vp, _vp, _vp, _f32, _f32, _vp, _vp, _vp, _vp, _vp,

@@ -67,6 +67,55 @@ template <> inline double rsqrt_<double>(double a) { return 1.0 / sqrt(a); }
 #endif
 
 template <typename F> PKF_HD F sel_(bool c, F a, F b) { return c ? a : b; }
+PKF_HD bool any_(bool m) { return m; }
+
+// ------------------------------------------------------------------------------------------
+// f32x2: TWO filters per thread in the lanes of a 64-bit register pair.  On sm_100 every operator maps
+// onto one packed instruction (FFMA2 / FMUL2 / FADD2, with negate modifiers, immediates and scalar
+// broadcast operands), so the hot step issues half as many FP32 instructions per filter; the FP32
+// pipe is busy for the same number of cycles, but the issue slots it frees absorb the non-FP32
+// instructions (loads, barriers, MUFU) that otherwise compete with it.  On the host the lanes are
+// plain floats (tests/hostsim).
+// ------------------------------------------------------------------------------------------
+struct mask2 { bool x, y; };
+PKF_HD bool any_(mask2 m) { return m.x || m.y; }
+
+struct f32x2 {
+  float x, y;
+  PKF_HD f32x2() {}
+  PKF_HD f32x2(float a) : x(a), y(a) {}
+  PKF_HD f32x2(double a) : x((float)a), y((float)a) {}
+  PKF_HD f32x2(int a) : x((float)a), y((float)a) {}
+  PKF_HD f32x2(float a, float b) : x(a), y(b) {}
+};
+#if defined(__CUDA_ARCH__)
+__device__ __forceinline__ float2 f2_(const f32x2& a) { return make_float2(a.x, a.y); }
+__device__ __forceinline__ f32x2 operator+(const f32x2& a, const f32x2& b) { float2 r = __fadd2_rn(f2_(a), f2_(b)); return f32x2(r.x, r.y); }
+__device__ __forceinline__ f32x2 operator-(const f32x2& a, const f32x2& b) { float2 r = __fadd2_rn(f2_(a), make_float2(-b.x, -b.y)); return f32x2(r.x, r.y); }
+__device__ __forceinline__ f32x2 operator*(const f32x2& a, const f32x2& b) { float2 r = __fmul2_rn(f2_(a), f2_(b)); return f32x2(r.x, r.y); }
+#else
+inline f32x2 operator+(const f32x2& a, const f32x2& b) { return f32x2(a.x + b.x, a.y + b.y); }
+inline f32x2 operator-(const f32x2& a, const f32x2& b) { return f32x2(a.x - b.x, a.y - b.y); }
+inline f32x2 operator*(const f32x2& a, const f32x2& b) { return f32x2(a.x * b.x, a.y * b.y); }
+#endif
+PKF_HD f32x2 operator-(const f32x2& a) { return f32x2(-a.x, -a.y); }
+PKF_HD f32x2 operator/(const f32x2& a, const f32x2& b) { return f32x2(a.x / b.x, a.y / b.y); }   // set-up code only
+PKF_HD f32x2& operator*=(f32x2& a, const f32x2& b) { a = a * b; return a; }
+PKF_HD mask2 operator<(const f32x2& a, const f32x2& b) { return mask2{a.x < b.x, a.y < b.y}; }
+PKF_HD mask2 operator>(const f32x2& a, const f32x2& b) { return mask2{a.x > b.x, a.y > b.y}; }
+PKF_HD f32x2 sel_(mask2 c, const f32x2& a, const f32x2& b) { return f32x2(c.x ? a.x : b.x, c.y ? a.y : b.y); }
+template <> PKF_HD f32x2 fma_<f32x2>(f32x2 a, f32x2 b, f32x2 c) {
+#if defined(__CUDA_ARCH__)
+  float2 r = __ffma2_rn(f2_(a), f2_(b), f2_(c));
+  return f32x2(r.x, r.y);
+#else
+  return f32x2(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y));
+#endif
+}
+template <> PKF_HD f32x2 abs_<f32x2>(f32x2 a) { return f32x2(abs_<float>(a.x), abs_<float>(a.y)); }
+template <> PKF_HD f32x2 rcp_<f32x2>(f32x2 a) { return f32x2(rcp_<float>(a.x), rcp_<float>(a.y)); }
+template <> PKF_HD f32x2 rsqrt_<f32x2>(f32x2 a) { return f32x2(rsqrt_<float>(a.x), rsqrt_<float>(a.y)); }
+template <> PKF_HD f32x2 sqrt_<f32x2>(f32x2 a) { return f32x2(sqrt_<float>(a.x), sqrt_<float>(a.y)); }
 
 // ------------------------------------------------------------------------------------------
 // types
@@ -310,8 +359,8 @@ PKF_HD Mat3<F> wahba_qr2(const RefFrame<F>& E, const Vec3<F>& a, const Vec3<F>& 
   F c11 = E.s22 * hh;
   // sg = sign(ka km) is +1 whenever both weights are positive (always for normalised accelerometer
   // input: ka = |a_z| <= 1); the reflected case is a rarely taken branch.
-  const bool neg = (ka * km) < F(0);
-  if (neg) { c11 = -c11; c01 = -c01; }
+  const auto neg = (ka * km) < F(0);
+  if (any_(neg)) { c11 = sel_(neg, -c11, c11); c01 = sel_(neg, -c01, c01); }
   F p = c00 + c11;
   F r = c10 - c01;
   F inv = rsqrt_(fma_(p, p, r * r));
@@ -320,7 +369,10 @@ PKF_HD Mat3<F> wahba_qr2(const RefFrame<F>& E, const Vec3<F>& a, const Vec3<F>& 
   Vec3<F> w1, w2, w3 = E.e3;
   w1.x = fma_(sn, E.e2.x, cs * E.e1.x); w1.y = fma_(sn, E.e2.y, cs * E.e1.y); w1.z = fma_(sn, E.e2.z, cs * E.e1.z);
   w2.x = fma_(cs, E.e2.x, -(sn * E.e1.x)); w2.y = fma_(cs, E.e2.y, -(sn * E.e1.y)); w2.z = fma_(cs, E.e2.z, -(sn * E.e1.z));
-  if (neg) { w2.x = -w2.x; w2.y = -w2.y; w2.z = -w2.z; w3.x = -w3.x; w3.y = -w3.y; w3.z = -w3.z; }
+  if (any_(neg)) {
+    w2.x = sel_(neg, -w2.x, w2.x); w2.y = sel_(neg, -w2.y, w2.y); w2.z = sel_(neg, -w2.z, w2.z);
+    w3.x = sel_(neg, -w3.x, w3.x); w3.y = sel_(neg, -w3.y, w3.y); w3.z = sel_(neg, -w3.z, w3.z);
+  }
   Mat3<F> R;
   const Vec3<F>&f1 = Fb.e1, &f2 = Fb.e2, &f3 = Fb.e3;
   R.m[0][0] = fma_(w3.x, f3.x, fma_(w2.x, f2.x, w1.x * f1.x));
@@ -530,6 +582,31 @@ template <typename F> struct FilterConst {
   F g;                    // Q/(4R): process noise in units of r
 };
 
+PKF_HD void quat_fallback_unaligned(const Mat3<float>& Rm, const Quat<float>& z, bool, Quat<float>& y) {
+  y = rotation_to_quat_ref(Rm);
+  float sg = dot4(y, z) < 0.f ? -1.f : 1.f;
+  y.w *= sg; y.x *= sg; y.y *= sg; y.z *= sg;
+}
+PKF_HD void quat_fallback_unaligned(const Mat3<double>& Rm, const Quat<double>& z, bool, Quat<double>& y) {
+  y = rotation_to_quat_ref(Rm);
+  double sg = dot4(y, z) < 0.0 ? -1.0 : 1.0;
+  y.w *= sg; y.x *= sg; y.y *= sg; y.z *= sg;
+}
+PKF_HD void quat_fallback_unaligned(const Mat3<f32x2>& Rm, const Quat<f32x2>& z, mask2 which, Quat<f32x2>& y) {
+  // rare path: redo the affected lane(s) with the scalar code
+  for (int lane = 0; lane < 2; ++lane) {
+    if (!(lane ? which.y : which.x)) continue;
+    Mat3<float> R1;
+    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) R1.m[i][j] = lane ? Rm.m[i][j].y : Rm.m[i][j].x;
+    Quat<float> z1 = {lane ? z.w.y : z.w.x, lane ? z.x.y : z.x.x, lane ? z.y.y : z.y.x, lane ? z.z.y : z.z.x}, y1;
+    quat_fallback_unaligned(R1, z1, true, y1);
+    if (lane) { y.w.y = y1.w; y.x.y = y1.x; y.y.y = y1.y; y.z.y = y1.z; }
+    else { y.w.x = y1.w; y.x.x = y1.x; y.y.x = y1.y; y.z.x = y1.z; }
+  }
+}
+template <typename F> PKF_HD bool reference_flip_of(const Mat3<F>& Rm, const Quat<F>& y) { return reference_flip(Rm, y); }
+template <> PKF_HD bool reference_flip_of<f32x2>(const Mat3<f32x2>&, const Quat<f32x2>&) { return false; }   // packed path has no flip output
+
 // COMP selects the compensated state: X is carried as x + xlo (two floats per component).  With a
 // single float, increments below half an ulp of the state (K e ~ 2e-8 per step when R >> Q) are
 // absorbed by the addition and the filter silently stops following its measurement -- the float64
@@ -549,23 +626,24 @@ PKF_HD void ekf_step(Quat<F>& x, Quat<F>& xlo, Sym4<F>& P, const FilterConst<F>&
   Sym4<F> K = kalman_gain_unit(Pp);                                           // :63-66
   // ---- Correction (PKF/ExtendedKalmanFilter.py:70-80) ----
   F ka = abs_(acc.z), km = F(1) - ka;                                         // :71
-  Mat3<F> Rm = (ALGO == WAHBA_QR2) ? wahba_qr2(fc.E, acc, mag, ka, km)
-                                   : wahba_jacobi(fc.ra, fc.rm, acc, mag, ka, km, kJacobiSweepsFused);
+  Mat3<F> Rm;
+  if constexpr (ALGO == WAHBA_QR2) Rm = wahba_qr2(fc.E, acc, mag, ka, km);
+  else Rm = wahba_jacobi(fc.ra, fc.rm, acc, mag, ka, km, kJacobiSweepsFused);
   // measurement quaternion with the comparator's sign already applied            :73-75
   F n2;
   Quat<F> y = rotation_to_quat_aligned(Rm, z, n2);
-  if (n2 < F(0.16)) {
-    // |y.z| < 0.1: prediction and measurement are unrelated (never in a tracking filter; can happen
-    // on the first sample of a badly initialised one).  Use the selection-based conversion.
-    y = rotation_to_quat_ref(Rm);
-    F d = dot4(y, z);
-    F sg = sel_(d < F(0), F(-1), F(1));
-    y.w *= sg; y.x *= sg; y.y *= sg; y.z *= sg;
-  } else {
+  {
     F inv = rsqrt_(n2);
     y.w *= inv; y.x *= inv; y.y *= inv; y.z *= inv;
   }
-  flip = WANT_FLIP ? reference_flip(Rm, y) : false;
+  const auto unrelated = n2 < F(0.16);
+  if (any_(unrelated)) {
+    // |y.z| < 0.1: prediction and measurement are unrelated (never in a tracking filter; can happen
+    // on the first sample of a badly initialised one).  Use the selection-based conversion.
+    quat_fallback_unaligned(Rm, z, unrelated, y);
+  }
+  flip = false;
+  if (WANT_FLIP) flip = reference_flip_of(Rm, y);
   // X = z + K (y - z)                                                        :76-77
   F e0 = y.w - z.w, e1 = y.x - z.x, e2 = y.y - z.y, e3 = y.z - z.z;
   Quat<F> ke;

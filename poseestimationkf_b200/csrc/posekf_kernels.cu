@@ -43,6 +43,23 @@ constexpr int kMinCtasPerSm = PKF_MIN_CTAS;    // 6 CTAs/SM (24 warps) <=> <=80 
 constexpr int kTmaSteps = PKF_TMA_STEPS;       // TC: timesteps per TMA tile
 constexpr int kTmaStages = PKF_TMA_STAGES;     // ring depth
 constexpr int kChannels = 9;
+// packed (two filters per thread) variant
+#ifndef PKF_TMA2_STEPS
+#define PKF_TMA2_STEPS 4
+#endif
+#ifndef PKF_TMA2_STAGES
+#define PKF_TMA2_STAGES 2
+#endif
+#ifndef PKF_MIN_CTAS2
+#define PKF_MIN_CTAS2 6
+#endif
+constexpr int kThreads2 = 64;                  // threads per CTA of the packed kernel (still 128 filters per CTA)
+constexpr int kTma2Steps = PKF_TMA2_STEPS;
+constexpr int kTma2Stages = PKF_TMA2_STAGES;
+#ifndef PKF_AUTO_PACKED
+#define PKF_AUTO_PACKED 1
+#endif
+constexpr bool kAutoPrefersPacked = PKF_AUTO_PACKED != 0;   // whether POSEKF_STAGE_AUTO picks the packed kernel
 
 #define PKF_CUDA_TRY(expr)                           \
   do {                                               \
@@ -325,6 +342,133 @@ __global__ void __launch_bounds__(kThreads, kMinCtasPerSm)
   }
   if (valid) store_filter<LPF, COMP>(p, n, f);
   if (AUX && valid && aux.truth) p.loss_acc[n] = aux.loss;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Replay, TMA staging, PACKED: each thread advances TWO filters in the lanes of f32x2 values, so
+// every FP32 operation of the step is one FFMA2 / FMUL2 / FADD2.  Same tiles, same barriers and
+// the same arithmetic per filter as replay_tma_kernel (results are bit-identical); half the
+// threads.  Rank-2 Wahba, no auxiliary outputs (those launches use the scalar kernel).
+// ---------------------------------------------------------------------------------------------
+struct __align__(128) Tma2Smem {
+  float tile[kTma2Stages][kTma2Steps][kChannels][kThreads];
+  uint64_t full[kTma2Stages];
+  uint64_t empty[kTma2Stages];
+};
+constexpr uint32_t kTile2Bytes = kTma2Steps * kChannels * kThreads * sizeof(float);
+
+struct FilterRegs2 {
+  Quat<f32x2> x, xlo;
+  Sym4<f32x2> P;
+  FilterConst<f32x2> fc;
+  Vec3<f32x2> la, lm;
+};
+
+__device__ __forceinline__ f32x2 ld2(const float* p) {
+  const float2 v = *reinterpret_cast<const float2*>(p);
+  return f32x2(v.x, v.y);
+}
+__device__ __forceinline__ void st2(float* p, const f32x2& v) { *reinterpret_cast<float2*>(p) = make_float2(v.x, v.y); }
+
+template <bool LPF, bool COMP>
+__global__ void __launch_bounds__(kThreads2, (LPF && COMP) ? (PKF_MIN_CTAS2 > 6 ? 6 : PKF_MIN_CTAS2) : PKF_MIN_CTAS2)
+    replay_tma2_kernel(const ReplayParams p, const __grid_constant__ CUtensorMap tmap) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  Tma2Smem& sm = *reinterpret_cast<Tma2Smem*>(smem_raw);
+  const int tid = threadIdx.x;
+  const int64_t n0 = (int64_t)blockIdx.x * kThreads;
+  const int64_t n = n0 + 2 * tid;                  // this thread owns filters n and n + 1 (N is even)
+  const bool valid = n < p.N;
+  const int col0 = (int)((p.Ns == p.N) ? n0 : (n0 % p.Ns));
+  const int T = (int)p.T;
+  const int n_chunks = (T + kTma2Steps - 1) / kTma2Steps;
+  const int64_t N = p.N, Ns = p.Ns;
+
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < kTma2Stages; ++s) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], kThreads2 / 32); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (tid == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
+#pragma unroll
+    for (int s = 0; s < kTma2Stages; ++s) {
+      if (s < n_chunks) {
+        mbar_expect_tx(&sm.full[s], kTile2Bytes);
+        tma_load_3d(&sm.tile[s][0][0][0], &tmap, &sm.full[s], col0, 0, s * kTma2Steps);
+      }
+    }
+  }
+
+  FilterRegs2 f;
+  if (valid) {
+    const int64_t col = (int64_t)col0 + 2 * tid;
+    Vec3<f32x2> ra = {ld2(p.acc_ref + col), ld2(p.acc_ref + Ns + col), ld2(p.acc_ref + 2 * Ns + col)};
+    Vec3<f32x2> rm = {ld2(p.mag_ref + col), ld2(p.mag_ref + Ns + col), ld2(p.mag_ref + 2 * Ns + col)};
+    f.fc = make_filter_const<f32x2>(ra, rm, ld2(p.q_scale + n), ld2(p.r_scale + n));
+    f.x = {ld2(p.state_x + n), ld2(p.state_x + N + n), ld2(p.state_x + 2 * N + n), ld2(p.state_x + 3 * N + n)};
+    f.xlo = {f32x2(0.f), f32x2(0.f), f32x2(0.f), f32x2(0.f)};
+    if (COMP) f.xlo = {ld2(p.state_x_lo + n), ld2(p.state_x_lo + N + n), ld2(p.state_x_lo + 2 * N + n), ld2(p.state_x_lo + 3 * N + n)};
+    const float* sp = p.state_p + n;
+    f.P = {ld2(sp), ld2(sp + N), ld2(sp + 2 * N), ld2(sp + 3 * N), ld2(sp + 4 * N), ld2(sp + 5 * N), ld2(sp + 6 * N),
+           ld2(sp + 7 * N), ld2(sp + 8 * N), ld2(sp + 9 * N)};
+    if (LPF) {
+      const float* sl = p.state_lpf + n;
+      f.la = {ld2(sl), ld2(sl + N), ld2(sl + 2 * N)};
+      f.lm = {ld2(sl + 3 * N), ld2(sl + 4 * N), ld2(sl + 5 * N)};
+    }
+  }
+  const float dt0 = p.dt[0];
+
+  int stage = 0;
+  uint32_t parity = 0;
+  for (int k = 0; k < n_chunks; ++k) {
+    if (tid == 0 && k >= 1 && (k - 1 + kTma2Stages) < n_chunks) {
+      const int ps = (stage == 0) ? kTma2Stages - 1 : stage - 1;
+      const uint32_t pp = (stage == 0) ? (parity ^ 1u) : parity;
+      mbar_wait(&sm.empty[ps], pp);
+      mbar_expect_tx(&sm.full[ps], kTile2Bytes);
+      tma_load_3d(&sm.tile[ps][0][0][0], &tmap, &sm.full[ps], col0, 0, (k - 1 + kTma2Stages) * kTma2Steps);
+    }
+    mbar_wait(&sm.full[stage], parity);
+    if (valid) {
+      const int steps = min(kTma2Steps, T - k * kTma2Steps);
+#pragma unroll
+      for (int tt = 0; tt < kTma2Steps; ++tt) {
+        if (tt < steps) {
+          f32x2 s[kChannels];
+#pragma unroll
+          for (int c = 0; c < kChannels; ++c) s[c] = ld2(&sm.tile[stage][tt][c][2 * tid]);
+          const float h = p.dt_per_step ? __ldg(p.dt + k * kTma2Steps + tt) : dt0;
+          Vec3<f32x2> w = {s[0], s[1], s[2]}, a = {s[3], s[4], s[5]}, m = {s[6], s[7], s[8]};
+          if (LPF) {
+            if (p.alpha_acc >= 0.f) { lowpass<f32x2>(f.la, a, f32x2(p.alpha_acc), f32x2(1.f - p.alpha_acc)); a = f.la; }
+            if (p.alpha_mag >= 0.f) { lowpass<f32x2>(f.lm, m, f32x2(p.alpha_mag), f32x2(1.f - p.alpha_mag)); m = f.lm; }
+          }
+          bool flip;
+          ekf_step<f32x2, WAHBA_QR2, false, COMP>(f.x, f.xlo, f.P, f.fc, w, a, m, f32x2(h), flip);
+        }
+      }
+    }
+    __syncwarp();
+    if ((tid & 31) == 0) mbar_arrive(&sm.empty[stage]);
+    if (++stage == kTma2Stages) { stage = 0; parity ^= 1; }
+  }
+  if (valid) {
+    st2(p.state_x + n, f.x.w); st2(p.state_x + N + n, f.x.x); st2(p.state_x + 2 * N + n, f.x.y); st2(p.state_x + 3 * N + n, f.x.z);
+    if (COMP) {
+      st2(p.state_x_lo + n, f.xlo.w); st2(p.state_x_lo + N + n, f.xlo.x); st2(p.state_x_lo + 2 * N + n, f.xlo.y);
+      st2(p.state_x_lo + 3 * N + n, f.xlo.z);
+    }
+    float* sp = p.state_p + n;
+    st2(sp, f.P.a00); st2(sp + N, f.P.a01); st2(sp + 2 * N, f.P.a02); st2(sp + 3 * N, f.P.a03); st2(sp + 4 * N, f.P.a11);
+    st2(sp + 5 * N, f.P.a12); st2(sp + 6 * N, f.P.a13); st2(sp + 7 * N, f.P.a22); st2(sp + 8 * N, f.P.a23); st2(sp + 9 * N, f.P.a33);
+    if (LPF) {
+      float* sl = p.state_lpf + n;
+      st2(sl, f.la.x); st2(sl + N, f.la.y); st2(sl + 2 * N, f.la.z); st2(sl + 3 * N, f.lm.x); st2(sl + 4 * N, f.lm.y); st2(sl + 5 * N, f.lm.z);
+    }
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -829,6 +973,33 @@ template <int ALGO, bool LPF, bool AUX, bool COMP> int launch_replay(const Repla
   return launch_status();
 }
 
+bool packed_eligible(const ReplayParams& p) {
+  // float2 accesses to the [k][N] state / constant arrays need N even and 8-byte aligned bases
+  if ((p.N & 1) != 0) return false;
+  const void* ptrs[] = {p.acc_ref, p.mag_ref, p.q_scale, p.r_scale, p.state_x, p.state_x_lo, p.state_p, p.state_lpf};
+  for (const void* q : ptrs) if ((reinterpret_cast<uintptr_t>(q) & 7) != 0) return false;
+  return p.out_traj == nullptr && p.out_flip == nullptr && p.truth == nullptr;
+}
+
+template <bool LPF, bool COMP> int launch_replay_packed(const ReplayParams& p, cudaStream_t st) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) return POSEKF_ENODEV;
+  CUtensorMap tmap;
+  const cuuint64_t dims[3] = {(cuuint64_t)p.Ns, (cuuint64_t)kChannels, (cuuint64_t)p.T};
+  const cuuint64_t strides[2] = {(cuuint64_t)p.Ns * sizeof(float), (cuuint64_t)p.Ns * kChannels * sizeof(float)};
+  const cuuint32_t box[3] = {(cuuint32_t)kThreads, (cuuint32_t)kChannels, (cuuint32_t)kTma2Steps};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(p.streams), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return POSEKF_EALIGN;
+  auto kern = replay_tma2_kernel<LPF, COMP>;
+  PKF_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Tma2Smem)));
+  const unsigned grid = (unsigned)((p.N + kThreads - 1) / kThreads);
+  kern<<<grid, kThreads2, sizeof(Tma2Smem), st>>>(p, tmap);
+  return launch_status();
+}
+
 template <int ALGO, bool LPF> int launch_replay_aux(const ReplayParams& p, bool use_tma, cudaStream_t st) {
   const bool aux = p.out_traj != nullptr || p.out_flip != nullptr || p.truth != nullptr;
   const bool comp = p.state_x_lo != nullptr;
@@ -838,11 +1009,21 @@ template <int ALGO, bool LPF> int launch_replay_aux(const ReplayParams& p, bool 
 
 int replay_dispatch(const ReplayParams& p, int algo, int staging, cudaStream_t st) {
   const bool lpf = (p.alpha_acc >= 0.f) || (p.alpha_mag >= 0.f);
-  bool use_tma;
+  bool use_tma, packed = false;
   if (staging == POSEKF_STAGE_LDG) use_tma = false;
   else if (staging == POSEKF_STAGE_TMA) { if (!tma_eligible(p)) return POSEKF_EALIGN; use_tma = true; }
-  else if (staging == POSEKF_STAGE_AUTO) use_tma = tma_eligible(p);
-  else return POSEKF_EINVAL;
+  else if (staging == POSEKF_STAGE_TMA_PACKED) {
+    if (!tma_eligible(p) || !packed_eligible(p) || algo != POSEKF_WAHBA_QR2) return POSEKF_EALIGN;
+    use_tma = packed = true;
+  } else if (staging == POSEKF_STAGE_AUTO) {
+    use_tma = tma_eligible(p);
+    packed = use_tma && kAutoPrefersPacked && algo == POSEKF_WAHBA_QR2 && packed_eligible(p);
+  } else return POSEKF_EINVAL;
+  if (packed) {
+    const bool comp = p.state_x_lo != nullptr;
+    if (lpf) return comp ? launch_replay_packed<true, true>(p, st) : launch_replay_packed<true, false>(p, st);
+    return comp ? launch_replay_packed<false, true>(p, st) : launch_replay_packed<false, false>(p, st);
+  }
   if (algo == POSEKF_WAHBA_QR2) return lpf ? launch_replay_aux<WAHBA_QR2, true>(p, use_tma, st) : launch_replay_aux<WAHBA_QR2, false>(p, use_tma, st);
   if (algo == POSEKF_WAHBA_JACOBI) return lpf ? launch_replay_aux<WAHBA_JACOBI, true>(p, use_tma, st) : launch_replay_aux<WAHBA_JACOBI, false>(p, use_tma, st);
   return POSEKF_EINVAL;

@@ -55,3 +55,23 @@ def wahba(acc_ref, mag_ref, acc, mag, ka, km, *, precision="f32", algo="qr2", sw
                              _p(ka, C.c_float), _p(km, C.c_float), _p(q, C.c_double), _p(R, C.c_double))
     assert rc == 0
     return (q, R) if want_R else q
+
+
+def replay_packed(streams, dt, acc_ref, mag_ref, q, r, *, lpf_acc=-1.0, lpf_mag=-1.0, compensated=False):
+    """The packed (two filters per thread, f32x2) form of the float32 replay.  Same arguments / results as
+    `replay` (without the flip mask); N must be even."""
+    streams = np.ascontiguousarray(streams, dtype=np.float32)
+    T, _, N = streams.shape
+    dt = np.atleast_1d(np.asarray(dt, dtype=np.float64))
+    acc_ref = np.ascontiguousarray(acc_ref, dtype=np.float32)
+    mag_ref = np.ascontiguousarray(mag_ref, dtype=np.float32)
+    q = np.ascontiguousarray(np.broadcast_to(np.asarray(q, dtype=np.float32), (N,)))
+    r = np.ascontiguousarray(np.broadcast_to(np.asarray(r, dtype=np.float32), (N,)))
+    traj = np.empty((T, 4, N))
+    P = np.empty((10, N))
+    rc = lib().hostsim_replay_packed(C.c_int(int(compensated)), C.c_int64(N), C.c_int64(T), _p(streams, C.c_float),
+                                     _p(dt, C.c_double), C.c_int(int(dt.size > 1)), _p(acc_ref, C.c_float),
+                                     _p(mag_ref, C.c_float), _p(q, C.c_float), _p(r, C.c_float), C.c_float(lpf_acc),
+                                     C.c_float(lpf_mag), _p(traj, C.c_double), _p(P, C.c_double))
+    assert rc == 0
+    return traj, P

@@ -45,7 +45,54 @@ static void replay_t(int64_t N, int64_t T, const float* streams, const double* d
   }
 }
 
+// Packed (two filters per "thread", F = f32x2) form of the same replay: exercises the lane logic of the
+// packed device kernel on the CPU.  N must be even.
+template <bool COMP>
+static void replay_packed_t(int64_t N, int64_t T, const float* streams, const double* dt, int dt_per_step,
+                            const float* acc_ref, const float* mag_ref, const float* q, const float* r, float lpf_acc,
+                            float lpf_mag, double* out_traj, double* out_P) {
+  typedef f32x2 F;
+  for (int64_t n = 0; n < N; n += 2) {
+    Vec3<F> ra = {F(acc_ref[n], acc_ref[n + 1]), F(acc_ref[N + n], acc_ref[N + n + 1]), F(acc_ref[2 * N + n], acc_ref[2 * N + n + 1])};
+    Vec3<F> rm = {F(mag_ref[n], mag_ref[n + 1]), F(mag_ref[N + n], mag_ref[N + n + 1]), F(mag_ref[2 * N + n], mag_ref[2 * N + n + 1])};
+    FilterConst<F> fc = make_filter_const<F>(ra, rm, F(q[n], q[n + 1]), F(r[n], r[n + 1]));
+    Quat<F> x = {F(1.f), F(0.f), F(0.f), F(0.f)}, xlo = {F(0.f), F(0.f), F(0.f), F(0.f)};
+    const F ir = F(1.f / r[n], 1.f / r[n + 1]);
+    Sym4<F> P = {ir, F(0.f), F(0.f), F(0.f), ir, F(0.f), F(0.f), ir, F(0.f), ir};
+    Vec3<F> la = {F(0.f), F(0.f), F(0.f)}, lm = {F(0.f), F(0.f), F(0.f)};
+    for (int64_t t = 0; t < T; ++t) {
+      const float* s = streams + (size_t)t * 9 * N + n;
+      Vec3<F> w = {F(s[0], s[1]), F(s[N], s[N + 1]), F(s[2 * N], s[2 * N + 1])};
+      Vec3<F> a = {F(s[3 * N], s[3 * N + 1]), F(s[4 * N], s[4 * N + 1]), F(s[5 * N], s[5 * N + 1])};
+      Vec3<F> m = {F(s[6 * N], s[6 * N + 1]), F(s[7 * N], s[7 * N + 1]), F(s[8 * N], s[8 * N + 1])};
+      if (lpf_acc >= 0.f) { lowpass<F>(la, a, F(lpf_acc), F(1.f - lpf_acc)); a = la; }
+      if (lpf_mag >= 0.f) { lowpass<F>(lm, m, F(lpf_mag), F(1.f - lpf_mag)); m = lm; }
+      F h = F((float)(dt_per_step ? dt[t] : dt[0]));
+      bool flip;
+      ekf_step<F, WAHBA_QR2, false, COMP>(x, xlo, P, fc, w, a, m, h, flip);
+      if (out_traj) {
+        double* o = out_traj + (size_t)t * 4 * N + n;
+        o[0] = x.w.x; o[1] = x.w.y; o[N] = x.x.x; o[N + 1] = x.x.y; o[2 * N] = x.y.x; o[2 * N + 1] = x.y.y;
+        o[3 * N] = x.z.x; o[3 * N + 1] = x.z.y;
+      }
+    }
+    if (out_P) {
+      const F p[10] = {P.a00, P.a01, P.a02, P.a03, P.a11, P.a12, P.a13, P.a22, P.a23, P.a33};
+      for (int k = 0; k < 10; ++k) { out_P[(size_t)k * N + n] = r[n] * p[k].x; out_P[(size_t)k * N + n + 1] = r[n + 1] * p[k].y; }
+    }
+  }
+}
+
 extern "C" {
+
+int hostsim_replay_packed(int comp, int64_t N, int64_t T, const float* streams, const double* dt, int dt_per_step,
+                          const float* acc_ref, const float* mag_ref, const float* q, const float* r, float lpf_acc,
+                          float lpf_mag, double* out_traj, double* out_P) {
+  if (N % 2) return 1;
+  if (comp) replay_packed_t<true>(N, T, streams, dt, dt_per_step, acc_ref, mag_ref, q, r, lpf_acc, lpf_mag, out_traj, out_P);
+  else replay_packed_t<false>(N, T, streams, dt, dt_per_step, acc_ref, mag_ref, q, r, lpf_acc, lpf_mag, out_traj, out_P);
+  return 0;
+}
 
 // precision: 0 = float32, 1 = float64 ; algo: 0 = QR2, 1 = Jacobi
 int hostsim_replay(int precision, int algo, int comp, int64_t N, int64_t T, const float* streams, const double* dt,

@@ -41,7 +41,8 @@ def test_zero_spills_reported_by_ptxas():
     spills = re.findall(r"(\d+) bytes spill stores, (\d+) bytes spill loads", log)
     assert spills and all(a == "0" and b == "0" for a, b in spills)
     regs = [int(r) for r in re.findall(r"Used (\d+) registers", log)]
-    assert max(regs) <= 128          # 4 CTAs of 128 threads per SM
+    # scalar kernels: 128 threads x >= 4 CTAs/SM (<= 128 regs); packed kernels: 64 threads x 6 CTAs/SM (<= 168 regs)
+    assert max(regs) <= 168
 
 
 def test_argument_validation_without_gpu():

@@ -321,3 +321,35 @@ def test_no_out_of_bounds_writes(cuda):
             assert torch.isfinite(traj).all() and (traj != POISON).all() and (loss >= 0).all()
             if not precise:
                 assert (xlo == 0).all()          # untouched when the compensated variant is off
+
+
+def test_packed_kernel_bitwise_equals_scalar(cuda):
+    """POSEKF_STAGE_TMA_PACKED (two filters per thread, FFMA2) must reproduce the scalar kernels bit for bit:
+    same per-filter operations in the same order."""
+    for N, T in ((4096, 101), (1000, 37), (130, 9)):
+        imu = make_imu(N, T, seed=N, sigma=0.01, device=cuda)
+        q = torch.logspace(-2, 2, N, device=cuda); r = torch.logspace(1, -2, N, device=cuda)
+        for kw in (dict(), dict(lpf_alpha_acc=0.2, lpf_alpha_mag=0.1)):
+            for precise in (False, True):
+                if N % 4:          # TMA needs N % 4 == 0: the packed request must fail loudly
+                    with pytest.raises(_lib.PosekfError):
+                        B.replay(imu.streams, imu.acc_ref, imu.mag_ref, dt=imu.dt, q=q, r=r, staging="tma_packed", **kw)
+                    continue
+                a, _, _ = B.replay(imu.streams, imu.acc_ref, imu.mag_ref, dt=imu.dt, q=q, r=r, precise_state=precise,
+                                   staging="tma", **kw)
+                b, _, _ = B.replay(imu.streams, imu.acc_ref, imu.mag_ref, dt=imu.dt, q=q, r=r, precise_state=precise,
+                                   staging="tma_packed", **kw)
+                assert torch.equal(a.x, b.x) and torch.equal(a.p, b.p)
+                if precise:
+                    assert torch.equal(a.x_lo, b.x_lo)
+                if kw:
+                    assert torch.equal(a.lpf, b.lpf)
+    # auxiliary outputs are not available in the packed kernel
+    imu = make_imu(256, 8, seed=1, device=cuda)
+    with pytest.raises(_lib.PosekfError):
+        B.replay(imu.streams, imu.acc_ref, imu.mag_ref, dt=imu.dt, store_trajectory=True, staging="tma_packed")
+    # sweep layout (shared trajectories) through the packed kernel
+    qs = torch.logspace(-3, 3, 1024, device=cuda); rs = torch.full((1024,), 0.1, device=cuda)
+    a, _, _ = B.replay(imu.streams, imu.acc_ref, imu.mag_ref, dt=imu.dt, q=qs, r=rs, n_filters=1024, staging="tma")
+    b, _, _ = B.replay(imu.streams, imu.acc_ref, imu.mag_ref, dt=imu.dt, q=qs, r=rs, n_filters=1024, staging="tma_packed")
+    assert torch.equal(a.x, b.x) and torch.equal(a.x_lo, b.x_lo)
