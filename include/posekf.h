@@ -40,7 +40,7 @@ extern "C" {
 #define POSEKF_STAGE_LDG  1     /* coalesced global loads, register prefetch one step ahead */
 #define POSEKF_STAGE_TMA  2     /* cp.async.bulk.tensor (TMA) multi-stage shared-memory ring */
 #define POSEKF_STAGE_TMA_PACKED 3 /* same ring, two filters per thread in packed f32x2 registers (FFMA2);
-                                     rank-2 Wahba, no trajectory/flip/loss outputs, N even */
+                                     rank-2 Wahba, N even; what AUTO picks when eligible */
 
 /* Library / build info: returns a static string such as "posekf_b200 0.1 sm_100a". */
 const char* posekf_version(void);
@@ -68,11 +68,12 @@ const char* posekf_version(void);
  *               r must be > 0 (the kernel carries the covariance in units of r), q >= 0
  *   lpf_alpha_acc/mag  low-pass coefficient, < 0 disables the stage
  *   state_x     [4][N]  in: X before the first step, out: X after the last step
- *   state_x_lo  [4][N] in/out or NULL.  Non-NULL selects the COMPENSATED state: X is carried as two floats
- *               (state_x + state_x_lo) so that corrections below half an ulp of the state are not lost.
- *               Needed for R >> Q tunings over thousands of steps (gain ~1e-7: a single-float state
- *               stops following its measurement; 2.4e-5 rad from the reference after 5000 steps at
- *               Q=1e-3, R=1e3, 2e-7 with this variant); costs ~7 % more instructions.  Start at 0.
+ *   state_x_lo  [4][N] in/out or NULL.  Non-NULL selects the PRECISE variant for extreme Q/R ratios: X is
+ *               carried as two floats (state_x + state_x_lo) so that corrections below half an ulp of the
+ *               state are not lost (R >> Q: 2.4e-5 rad from the reference after 5000 steps at Q=1e-3,
+ *               R=1e3 otherwise), and the gain is formed by Sherman-Morrison with the process noise kept
+ *               apart from A K A^T (Q >> R: 1.3e-5 rad spikes at Q=1e3, R=1e-3 otherwise).  <= 3e-7 rad over
+ *               the whole 1e-3..1e3 grid; costs ~17 % more time.  Start at 0.
  *   state_p     [10][N] in/out: upper triangle of P / r  (the covariance IN UNITS OF THE FILTER'S r; after
  *               an update this equals the Kalman gain) in the order 00 01 02 03 11 12 13 22 23 33.
  *               The kernel works in this scaled form, so storing it unscaled would make a chunked

@@ -79,6 +79,8 @@ PKF_HD bool any_(bool m) { return m; }
 // ------------------------------------------------------------------------------------------
 struct mask2 { bool x, y; };
 PKF_HD bool any_(mask2 m) { return m.x || m.y; }
+PKF_HD mask2 operator&&(mask2 a, mask2 b) { return mask2{a.x && b.x, a.y && b.y}; }
+PKF_HD mask2 operator!(mask2 a) { return mask2{!a.x, !a.y}; }
 
 struct f32x2 {
   float x, y;
@@ -240,7 +242,7 @@ template <typename F> PKF_HD void two_sum(F a, F b, F& hi, F& lo) {
 // x = state BEFORE the RK4 step.        (PKF/ExtendedKalmanFilter.py:59-61)
 //   B B^T = 0.25 (|x|^2 I - x x^T)  =>  second term = qq (|x|^2 I - x x^T), qq = q/4.
 // ------------------------------------------------------------------------------------------
-template <typename F>
+template <typename F, bool NOISE = true>
 PKF_HD Sym4<F> propagate_cov(const Sym4<F>& P, const Vec3<F>& hw, const Quat<F>& x, F qq) {
   const F X = hw.x, Y = hw.y, Z = hw.z;
   // M = A P (full 4x4; P symmetric so P[k][j] is read from the upper triangle)
@@ -263,23 +265,37 @@ PKF_HD Sym4<F> propagate_cov(const Sym4<F>& P, const Vec3<F>& hw, const Quat<F>&
   F m31 = fma_(-X, p12, fma_(Y, p11, Z * p01));
   F m32 = fma_(-X, p22, fma_(Y, p12, Z * p02));
   F m33 = fma_(-X, p23, fma_(Y, p13, Z * p03));
-  // process-noise term, used as the start value of the N = M A^T accumulation chains
-  F yw = qq * x.w, yx = qq * x.x, yy = qq * x.y, yz = qq * x.z;
-  F s = fma_(yz, x.z, fma_(yy, x.y, fma_(yx, x.x, yw * x.w)));   // qq |x|^2
   Sym4<F> N;
   // N[i][j] = sum_k M[i][k] A[j][k]
   //  j=0: -X M[i][1] - Y M[i][2] - Z M[i][3]     j=1:  X M[i][0] + Z M[i][2] - Y M[i][3]
   //  j=2:  Y M[i][0] - Z M[i][1] + X M[i][3]     j=3:  Z M[i][0] + Y M[i][1] - X M[i][2]
-  N.a00 = fma_(-Z, m03, fma_(-Y, m02, fma_(-X, m01, fma_(-yw, x.w, s))));
-  N.a01 = fma_(-Y, m03, fma_(Z, m02, fma_(X, m00, -(yw * x.x))));
-  N.a02 = fma_(X, m03, fma_(-Z, m01, fma_(Y, m00, -(yw * x.y))));
-  N.a03 = fma_(-X, m02, fma_(Y, m01, fma_(Z, m00, -(yw * x.z))));
-  N.a11 = fma_(-Y, m13, fma_(Z, m12, fma_(X, m10, fma_(-yx, x.x, s))));
-  N.a12 = fma_(X, m13, fma_(-Z, m11, fma_(Y, m10, -(yx * x.y))));
-  N.a13 = fma_(-X, m12, fma_(Y, m11, fma_(Z, m10, -(yx * x.z))));
-  N.a22 = fma_(X, m23, fma_(-Z, m21, fma_(Y, m20, fma_(-yy, x.y, s))));
-  N.a23 = fma_(-X, m22, fma_(Y, m21, fma_(Z, m20, -(yy * x.z))));
-  N.a33 = fma_(-X, m32, fma_(Y, m31, fma_(Z, m30, fma_(-yz, x.z, s))));
+  if constexpr (NOISE) {
+    // process-noise term, used as the start value of the accumulation chains
+    F yw = qq * x.w, yx = qq * x.x, yy = qq * x.y, yz = qq * x.z;
+    F s = fma_(yz, x.z, fma_(yy, x.y, fma_(yx, x.x, yw * x.w)));   // qq |x|^2
+    N.a00 = fma_(-Z, m03, fma_(-Y, m02, fma_(-X, m01, fma_(-yw, x.w, s))));
+    N.a01 = fma_(-Y, m03, fma_(Z, m02, fma_(X, m00, -(yw * x.x))));
+    N.a02 = fma_(X, m03, fma_(-Z, m01, fma_(Y, m00, -(yw * x.y))));
+    N.a03 = fma_(-X, m02, fma_(Y, m01, fma_(Z, m00, -(yw * x.z))));
+    N.a11 = fma_(-Y, m13, fma_(Z, m12, fma_(X, m10, fma_(-yx, x.x, s))));
+    N.a12 = fma_(X, m13, fma_(-Z, m11, fma_(Y, m10, -(yx * x.y))));
+    N.a13 = fma_(-X, m12, fma_(Y, m11, fma_(Z, m10, -(yx * x.z))));
+    N.a22 = fma_(X, m23, fma_(-Z, m21, fma_(Y, m20, fma_(-yy, x.y, s))));
+    N.a23 = fma_(-X, m22, fma_(Y, m21, fma_(Z, m20, -(yy * x.z))));
+    N.a33 = fma_(-X, m32, fma_(Y, m31, fma_(Z, m30, fma_(-yz, x.z, s))));
+  } else {
+    // A P A^T alone (the caller handles the process noise separately, see kalman_gain_sm)
+    N.a00 = fma_(-Z, m03, fma_(-Y, m02, -(X * m01)));
+    N.a01 = fma_(-Y, m03, fma_(Z, m02, X * m00));
+    N.a02 = fma_(X, m03, fma_(-Z, m01, Y * m00));
+    N.a03 = fma_(-X, m02, fma_(Y, m01, Z * m00));
+    N.a11 = fma_(-Y, m13, fma_(Z, m12, X * m10));
+    N.a12 = fma_(X, m13, fma_(-Z, m11, Y * m10));
+    N.a13 = fma_(-X, m12, fma_(Y, m11, Z * m10));
+    N.a22 = fma_(X, m23, fma_(-Z, m21, Y * m20));
+    N.a23 = fma_(-X, m22, fma_(Y, m21, Z * m20));
+    N.a33 = fma_(-X, m32, fma_(Y, m31, Z * m30));
+  }
   return N;
 }
 
@@ -297,43 +313,96 @@ PKF_HD Sym4<F> propagate_cov(const Sym4<F>& P, const Vec3<F>& hw, const Quat<F>&
 // gain accurate to ~1e-7 relative when r >> P (K ~ P/r would otherwise cancel against I), i.e. for
 // every (Q,R) tuning of the 1e-3..1e3 sweep (tests/test_gpu_replay.py::test_qr_sweep...).
 // ------------------------------------------------------------------------------------------
-template <typename F> PKF_HD Sym4<F> kalman_gain_unit(const Sym4<F>& P) {
+template <typename F> struct Ldl4 {          // S = P + I = L D L^T;  N = L^-1 - I;  i_k = 1/d_k;  e_k = d_k - 1
+  F n10, n20, n21, n30, n31, n32, i0, i1, i2, i3, e0, e1, e2, e3;
+};
+
+template <typename F> PKF_HD Ldl4<F> ldl_unit(const Sym4<F>& P) {
   // P is the predicted covariance IN UNITS OF r (P/r), so S = P + I and rho_k = 1/d_k.
   const F p01 = P.a01, p02 = P.a02, p03 = P.a03, p12 = P.a12, p13 = P.a13, p23 = P.a23;
-  F e0 = P.a00;                                   // delta_0
-  F i0 = rcp_(e0 + F(1));
-  F l10 = p01 * i0, l20 = p02 * i0, l30 = p03 * i0;
-  F e1 = fma_(-l10, p01, P.a11);
-  F i1 = rcp_(e1 + F(1));
+  Ldl4<F> f;
+  f.e0 = P.a00;                                   // delta_0
+  f.i0 = rcp_(f.e0 + F(1));
+  F l10 = p01 * f.i0, l20 = p02 * f.i0, l30 = p03 * f.i0;
+  f.e1 = fma_(-l10, p01, P.a11);
+  f.i1 = rcp_(f.e1 + F(1));
   F t21 = fma_(-l10, p02, p12);
   F t31 = fma_(-l10, p03, p13);
-  F l21 = t21 * i1, l31 = t31 * i1;
-  F e2 = fma_(-l21, t21, fma_(-l20, p02, P.a22));
-  F i2 = rcp_(e2 + F(1));
+  F l21 = t21 * f.i1, l31 = t31 * f.i1;
+  f.e2 = fma_(-l21, t21, fma_(-l20, p02, P.a22));
+  f.i2 = rcp_(f.e2 + F(1));
   F t32 = fma_(-l21, t31, fma_(-l20, p03, p23));
-  F l32 = t32 * i2;
-  F e3 = fma_(-l32, t32, fma_(-l31, t31, fma_(-l30, p03, P.a33)));
-  F i3 = rcp_(e3 + F(1));
+  F l32 = t32 * f.i2;
+  f.e3 = fma_(-l32, t32, fma_(-l31, t31, fma_(-l30, p03, P.a33)));
+  f.i3 = rcp_(f.e3 + F(1));
   // N = L^-1 - I
-  F n10 = -l10, n21 = -l21, n32 = -l32;
-  F n20 = fma_(-l21, n10, -l20);
-  F n31 = fma_(-l32, n21, -l31);
-  F n30 = fma_(-l32, n20, fma_(-l31, n10, -l30));
+  f.n10 = -l10; f.n21 = -l21; f.n32 = -l32;
+  f.n20 = fma_(-l21, f.n10, -l20);
+  f.n31 = fma_(-l32, f.n21, -l31);
+  f.n30 = fma_(-l32, f.n20, fma_(-l31, f.n10, -l30));
+  return f;
+}
+
+template <typename F> PKF_HD Sym4<F> gain_from_ldl(const Ldl4<F>& f) {
   // v_kj = -rho_k n_kj
-  F v30 = -(i3 * n30), v31 = -(i3 * n31), v32 = -(i3 * n32);
-  F v20 = -(i2 * n20), v21 = -(i2 * n21);
-  F v10 = -(i1 * n10);
+  F v30 = -(f.i3 * f.n30), v31 = -(f.i3 * f.n31), v32 = -(f.i3 * f.n32);
+  F v20 = -(f.i2 * f.n20), v21 = -(f.i2 * f.n21);
+  F v10 = -(f.i1 * f.n10);
   Sym4<F> K;
-  K.a00 = fma_(n30, v30, fma_(n20, v20, fma_(n10, v10, e0 * i0)));
-  K.a01 = fma_(n30, v31, fma_(n20, v21, v10));
-  K.a02 = fma_(n30, v32, v20);
+  K.a00 = fma_(f.n30, v30, fma_(f.n20, v20, fma_(f.n10, v10, f.e0 * f.i0)));
+  K.a01 = fma_(f.n30, v31, fma_(f.n20, v21, v10));
+  K.a02 = fma_(f.n30, v32, v20);
   K.a03 = v30;
-  K.a11 = fma_(n31, v31, fma_(n21, v21, e1 * i1));
-  K.a12 = fma_(n31, v32, v21);
+  K.a11 = fma_(f.n31, v31, fma_(f.n21, v21, f.e1 * f.i1));
+  K.a12 = fma_(f.n31, v32, v21);
   K.a13 = v31;
-  K.a22 = fma_(n32, v32, e2 * i2);
+  K.a22 = fma_(f.n32, v32, f.e2 * f.i2);
   K.a23 = v32;
-  K.a33 = e3 * i3;
+  K.a33 = f.e3 * f.i3;
+  return K;
+}
+
+template <typename F> PKF_HD Sym4<F> kalman_gain_unit(const Sym4<F>& P) { return gain_from_ldl(ldl_unit(P)); }
+
+// Gain for Q >> R (used by the compensated variant).  The predicted covariance in units of r is
+//   P = M + g (|x|^2 I - x x^T),   M = A K A^T = O(1),   g = q/4r up to ~1e6,
+// whose x-direction carries only M: forming P in float32 rounds M (and the "+ I" of S) away at
+// eps*g, i.e. a 2 % error in the gain along x at g = 2.5e5.  Keep the two parts apart instead:
+//   S = P + I = H - g x x^T,  H = I + M + g|x|^2 I  (condition number ~1),
+//   Sherman-Morrison:  S^-1 = H^-1 + (g/den) w w^T,  w = H^-1 x,
+//   den = 1 - g x^T w = x^T (I + M) w / |x|^2   (from (I + M) w + g|x|^2 w = x; no cancellation;
+//         w itself comes from the LDL^T factors of H, not from x - K_H x),
+//   K = I - S^-1 = K_H - beta w w^T,  K_H = I - H^-1 (split-pivot form above),  beta = g|x|^2 / x^T(I+M)w.
+template <typename F> PKF_HD Sym4<F> kalman_gain_sm(const Sym4<F>& M, const Quat<F>& x, F g) {
+  const F x2 = dot4(x, x);
+  const F c = g * x2;
+  Sym4<F> PH = M;
+  PH.a00 = M.a00 + c; PH.a11 = M.a11 + c; PH.a22 = M.a22 + c; PH.a33 = M.a33 + c;
+  const Ldl4<F> f = ldl_unit(PH);
+  const Sym4<F> KH = gain_from_ldl(f);
+  // w = H^-1 x = W^T D^-1 W x, W = I + N (solved through the factors: x - K_H x would cancel when g >> 1)
+  F t0 = x.w;
+  F t1 = fma_(f.n10, x.w, x.x);
+  F t2 = fma_(f.n21, x.x, fma_(f.n20, x.w, x.y));
+  F t3 = fma_(f.n32, x.y, fma_(f.n31, x.x, fma_(f.n30, x.w, x.z)));
+  F u0 = f.i0 * t0, u1 = f.i1 * t1, u2 = f.i2 * t2, u3 = f.i3 * t3;
+  F w3 = u3;
+  F w2 = fma_(f.n32, u3, u2);
+  F w1 = fma_(f.n31, u3, fma_(f.n21, u2, u1));
+  F w0 = fma_(f.n30, u3, fma_(f.n20, u2, fma_(f.n10, u1, u0)));
+  // (I + M) w
+  F g0 = fma_(M.a03, w3, fma_(M.a02, w2, fma_(M.a01, w1, fma_(M.a00, w0, w0))));
+  F g1 = fma_(M.a13, w3, fma_(M.a12, w2, fma_(M.a11, w1, fma_(M.a01, w0, w1))));
+  F g2 = fma_(M.a23, w3, fma_(M.a22, w2, fma_(M.a12, w1, fma_(M.a02, w0, w2))));
+  F g3 = fma_(M.a33, w3, fma_(M.a23, w2, fma_(M.a13, w1, fma_(M.a03, w0, w3))));
+  F num = fma_(x.z, g3, fma_(x.y, g2, fma_(x.x, g1, x.w * g0)));
+  F nb = -(c * rcp_(num));                     // -beta
+  F b0 = nb * w0, b1 = nb * w1, b2 = nb * w2, b3 = nb * w3;
+  Sym4<F> K;
+  K.a00 = fma_(b0, w0, KH.a00); K.a01 = fma_(b0, w1, KH.a01); K.a02 = fma_(b0, w2, KH.a02); K.a03 = fma_(b0, w3, KH.a03);
+  K.a11 = fma_(b1, w1, KH.a11); K.a12 = fma_(b1, w2, KH.a12); K.a13 = fma_(b1, w3, KH.a13);
+  K.a22 = fma_(b2, w2, KH.a22); K.a23 = fma_(b2, w3, KH.a23);
+  K.a33 = fma_(b3, w3, KH.a33);
   return K;
 }
 
@@ -558,11 +627,11 @@ template <typename F> PKF_HD Quat<F> rotation_to_quat_aligned(const Mat3<F>& M, 
 
 // The reference's q/-q decision for a measurement whose aligned form is y (y.z >= 0): the
 // reference's raw quaternion has component i >= 0 (i = its branch), so it negated iff y_i < 0.
-template <typename F> PKF_HD bool reference_flip(const Mat3<F>& M, const Quat<F>& y) {
+template <typename F> PKF_HD auto reference_flip(const Mat3<F>& M, const Quat<F>& y) -> decltype(y.w < y.w) {
   const F r00 = M.m[0][0], r11 = M.m[1][1], r22 = M.m[2][2];
   F tr1 = F(1) + r00 - r11 - r22, tr2 = F(1) - r00 + r11 - r22, tr3 = F(1) - r00 - r11 + r22;
-  bool b1 = (tr1 > tr2) && (tr1 > tr3);
-  bool b2 = !b1 && (tr2 > tr1) && (tr2 > tr3);
+  auto b1 = (tr1 > tr2) && (tr1 > tr3);
+  auto b2 = !b1 && ((tr2 > tr1) && (tr2 > tr3));
   return sel_(b1, y.x, sel_(b2, y.y, y.z)) < F(0);
 }
 
@@ -604,26 +673,31 @@ PKF_HD void quat_fallback_unaligned(const Mat3<f32x2>& Rm, const Quat<f32x2>& z,
     else { y.w.x = y1.w; y.x.x = y1.x; y.y.x = y1.y; y.z.x = y1.z; }
   }
 }
-template <typename F> PKF_HD bool reference_flip_of(const Mat3<F>& Rm, const Quat<F>& y) { return reference_flip(Rm, y); }
-template <> PKF_HD bool reference_flip_of<f32x2>(const Mat3<f32x2>&, const Quat<f32x2>&) { return false; }   // packed path has no flip output
-
-// COMP selects the compensated state: X is carried as x + xlo (two floats per component).  With a
+// COMP selects the "precise" variant: (i) the Sherman-Morrison gain (kalman_gain_sm) that keeps the
+// process noise apart from A K A^T, for Q >> R; (ii) the compensated state for R >> Q:
+// X is carried as x + xlo (two floats per component).  With a
 // single float, increments below half an ulp of the state (K e ~ 2e-8 per step when R >> Q) are
 // absorbed by the addition and the filter silently stops following its measurement -- the float64
 // reference does not (2.4e-5 rad apart after 5000 steps at Q=1e-3, R=1e3).  The compensated form
 // sums the step's three small terms (RK4 increment, K e, norm correction) first and folds them into
 // the state with one exact two-sum per component.
-template <typename F, int ALGO, bool WANT_FLIP, bool COMP>
+template <typename F, int ALGO, bool WANT_FLIP, bool COMP, typename FlagT>
 PKF_HD void ekf_step(Quat<F>& x, Quat<F>& xlo, Sym4<F>& P, const FilterConst<F>& fc, const Vec3<F>& gyro,
-                     const Vec3<F>& acc, const Vec3<F>& mag, F h, bool& flip) {
+                     const Vec3<F>& acc, const Vec3<F>& mag, F h, FlagT& flip) {
   Vec3<F> hw;
   hw.x = F(0.5) * gyro.x; hw.y = F(0.5) * gyro.y; hw.z = F(0.5) * gyro.z;
   // ---- Prediction (PKF/ExtendedKalmanFilter.py:58-68) ----
-  Sym4<F> Pp = propagate_cov(P, hw, x, fc.g);                                 // :59-61 (in units of r)
+  Sym4<F> K;
+  if constexpr (COMP) {
+    Sym4<F> M = propagate_cov<F, false>(P, hw, x, fc.g);                      // :59-61, noise kept apart
+    K = kalman_gain_sm(M, x, fc.g);                                           // :63-66
+  } else {
+    Sym4<F> Pp = propagate_cov<F, true>(P, hw, x, fc.g);                      // :59-61 (in units of r)
+    K = kalman_gain_unit(Pp);                                                 // :63-66
+  }
   Quat<F> inc = rk4_increment(x, hw, h);                                      // :62
   Quat<F> z;                                                                  // |z| = 1 to rounding
   z.w = x.w + inc.w; z.x = x.x + inc.x; z.y = x.y + inc.y; z.z = x.z + inc.z;
-  Sym4<F> K = kalman_gain_unit(Pp);                                           // :63-66
   // ---- Correction (PKF/ExtendedKalmanFilter.py:70-80) ----
   F ka = abs_(acc.z), km = F(1) - ka;                                         // :71
   Mat3<F> Rm;
@@ -631,21 +705,23 @@ PKF_HD void ekf_step(Quat<F>& x, Quat<F>& xlo, Sym4<F>& P, const FilterConst<F>&
   else Rm = wahba_jacobi(fc.ra, fc.rm, acc, mag, ka, km, kJacobiSweepsFused);
   // measurement quaternion with the comparator's sign already applied            :73-75
   F n2;
-  Quat<F> y = rotation_to_quat_aligned(Rm, z, n2);
-  {
-    F inv = rsqrt_(n2);
-    y.w *= inv; y.x *= inv; y.y *= inv; y.z *= inv;
-  }
+  Quat<F> y = rotation_to_quat_aligned(Rm, z, n2);       // un-normalised: 4 (y.z) y
+  flip = FlagT();
+  if (WANT_FLIP) flip = reference_flip(Rm, y);           // only the signs of y matter
+  // innovation e = y/|y| - z, the normalisation folded into the subtraction       :76
+  const F inv = rsqrt_(n2);
+  F e0 = fma_(y.w, inv, -z.w), e1 = fma_(y.x, inv, -z.x), e2 = fma_(y.y, inv, -z.y), e3 = fma_(y.z, inv, -z.z);
   const auto unrelated = n2 < F(0.16);
   if (any_(unrelated)) {
     // |y.z| < 0.1: prediction and measurement are unrelated (never in a tracking filter; can happen
-    // on the first sample of a badly initialised one).  Use the selection-based conversion.
-    quat_fallback_unaligned(Rm, z, unrelated, y);
+    // on the first sample of a badly initialised one).  Use the selection-based conversion there.
+    Quat<F> yf = y;
+    quat_fallback_unaligned(Rm, z, unrelated, yf);
+    if (WANT_FLIP) flip = reference_flip(Rm, yf);
+    e0 = sel_(unrelated, yf.w - z.w, e0); e1 = sel_(unrelated, yf.x - z.x, e1);
+    e2 = sel_(unrelated, yf.y - z.y, e2); e3 = sel_(unrelated, yf.z - z.z, e3);
   }
-  flip = false;
-  if (WANT_FLIP) flip = reference_flip_of(Rm, y);
-  // X = z + K (y - z)                                                        :76-77
-  F e0 = y.w - z.w, e1 = y.x - z.x, e2 = y.y - z.y, e3 = y.z - z.z;
+  // X = z + K e                                                              :77
   Quat<F> ke;
   ke.w = fma_(K.a03, e3, fma_(K.a02, e2, fma_(K.a01, e1, K.a00 * e0)));
   ke.x = fma_(K.a13, e3, fma_(K.a12, e2, fma_(K.a11, e1, K.a01 * e0)));

@@ -277,7 +277,7 @@ struct __align__(128) TmaSmem {
 constexpr uint32_t kTileBytes = kTmaSteps * kChannels * kThreads * sizeof(float);
 
 template <int ALGO, bool LPF, bool AUX, bool COMP>
-__global__ void __launch_bounds__(kThreads, kMinCtasPerSm)
+__global__ void __launch_bounds__(kThreads, (COMP && (LPF || AUX)) ? (kMinCtasPerSm > 5 ? 5 : kMinCtasPerSm) : kMinCtasPerSm)
     replay_tma_kernel(const ReplayParams p, const __grid_constant__ CUtensorMap tmap) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   TmaSmem& sm = *reinterpret_cast<TmaSmem*>(smem_raw);
@@ -348,7 +348,7 @@ __global__ void __launch_bounds__(kThreads, kMinCtasPerSm)
 // Replay, TMA staging, PACKED: each thread advances TWO filters in the lanes of f32x2 values, so
 // every FP32 operation of the step is one FFMA2 / FMUL2 / FADD2.  Same tiles, same barriers and
 // the same arithmetic per filter as replay_tma_kernel (results are bit-identical); half the
-// threads.  Rank-2 Wahba, no auxiliary outputs (those launches use the scalar kernel).
+// threads.  Rank-2 Wahba only (the Jacobi variant uses the scalar kernel).
 // ---------------------------------------------------------------------------------------------
 struct __align__(128) Tma2Smem {
   float tile[kTma2Stages][kTma2Steps][kChannels][kThreads];
@@ -370,7 +370,7 @@ __device__ __forceinline__ f32x2 ld2(const float* p) {
 }
 __device__ __forceinline__ void st2(float* p, const f32x2& v) { *reinterpret_cast<float2*>(p) = make_float2(v.x, v.y); }
 
-template <bool LPF, bool COMP>
+template <bool LPF, bool AUX, bool COMP>
 __global__ void __launch_bounds__(kThreads2, (LPF && COMP) ? (PKF_MIN_CTAS2 > 6 ? 6 : PKF_MIN_CTAS2) : PKF_MIN_CTAS2)
     replay_tma2_kernel(const ReplayParams p, const __grid_constant__ CUtensorMap tmap) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -420,6 +420,16 @@ __global__ void __launch_bounds__(kThreads2, (LPF && COMP) ? (PKF_MIN_CTAS2 > 6 
     }
   }
   const float dt0 = p.dt[0];
+  // auxiliary outputs: this thread's pair of adjacent slots
+  float4* traj = nullptr;
+  uint8_t* flips = nullptr;
+  const float4* truth = nullptr;
+  f32x2 loss(0.f);
+  if (AUX && valid) {
+    if (p.out_traj) traj = reinterpret_cast<float4*>(p.out_traj) + n;
+    if (p.out_flip) flips = p.out_flip + n;
+    if (p.truth) { truth = reinterpret_cast<const float4*>(p.truth) + ((int64_t)col0 + 2 * tid); loss = ld2(p.loss_acc + n); }
+  }
 
   int stage = 0;
   uint32_t parity = 0;
@@ -446,8 +456,27 @@ __global__ void __launch_bounds__(kThreads2, (LPF && COMP) ? (PKF_MIN_CTAS2 > 6 
             if (p.alpha_acc >= 0.f) { lowpass<f32x2>(f.la, a, f32x2(p.alpha_acc), f32x2(1.f - p.alpha_acc)); a = f.la; }
             if (p.alpha_mag >= 0.f) { lowpass<f32x2>(f.lm, m, f32x2(p.alpha_mag), f32x2(1.f - p.alpha_mag)); m = f.lm; }
           }
-          bool flip;
-          ekf_step<f32x2, WAHBA_QR2, false, COMP>(f.x, f.xlo, f.P, f.fc, w, a, m, f32x2(h), flip);
+          mask2 flip;
+          ekf_step<f32x2, WAHBA_QR2, AUX, COMP>(f.x, f.xlo, f.P, f.fc, w, a, m, f32x2(h), flip);
+          if (AUX) {
+            if (traj) {   // [T][N][4]: two adjacent 16-byte quaternions
+              asm volatile("st.global.cs.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(traj), "f"(f.x.w.x), "f"(f.x.x.x), "f"(f.x.y.x),
+                           "f"(f.x.z.x) : "memory");
+              asm volatile("st.global.cs.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(traj + 1), "f"(f.x.w.y), "f"(f.x.x.y),
+                           "f"(f.x.y.y), "f"(f.x.z.y) : "memory");
+              traj += N;
+            }
+            if (flips) { *reinterpret_cast<uchar2*>(flips) = make_uchar2(flip.x ? 1 : 0, flip.y ? 1 : 0); flips += N; }
+            if (truth) {  // squared wedge product |X ^ q_ref|^2 per lane (see the scalar kernel)
+              const float4 t0 = __ldg(truth), t1 = __ldg(truth + 1);
+              truth += Ns;
+              const f32x2 qw(t0.x, t1.x), qx(t0.y, t1.y), qy(t0.z, t1.z), qz(t0.w, t1.w);
+              const f32x2 xw = f.x.w, xx = f.x.x, xy = f.x.y, xz = f.x.z;
+              const f32x2 m01 = fma_(xw, qx, -(xx * qw)), m02 = fma_(xw, qy, -(xy * qw)), m03 = fma_(xw, qz, -(xz * qw));
+              const f32x2 m12 = fma_(xx, qy, -(xy * qx)), m13 = fma_(xx, qz, -(xz * qx)), m23 = fma_(xy, qz, -(xz * qy));
+              loss = loss + fma_(m23, m23, fma_(m13, m13, fma_(m12, m12, fma_(m03, m03, fma_(m02, m02, m01 * m01)))));
+            }
+          }
         }
       }
     }
@@ -468,6 +497,7 @@ __global__ void __launch_bounds__(kThreads2, (LPF && COMP) ? (PKF_MIN_CTAS2 > 6 
       float* sl = p.state_lpf + n;
       st2(sl, f.la.x); st2(sl + N, f.la.y); st2(sl + 2 * N, f.la.z); st2(sl + 3 * N, f.lm.x); st2(sl + 4 * N, f.lm.y); st2(sl + 5 * N, f.lm.z);
     }
+    if (AUX && p.truth) st2(p.loss_acc + n, loss);
   }
 }
 
@@ -978,10 +1008,11 @@ bool packed_eligible(const ReplayParams& p) {
   if ((p.N & 1) != 0) return false;
   const void* ptrs[] = {p.acc_ref, p.mag_ref, p.q_scale, p.r_scale, p.state_x, p.state_x_lo, p.state_p, p.state_lpf};
   for (const void* q : ptrs) if ((reinterpret_cast<uintptr_t>(q) & 7) != 0) return false;
-  return p.out_traj == nullptr && p.out_flip == nullptr && p.truth == nullptr;
+  if ((reinterpret_cast<uintptr_t>(p.loss_acc) & 7) != 0 || (reinterpret_cast<uintptr_t>(p.out_flip) & 1) != 0) return false;
+  return true;      // out_traj / truth are already required to be 16-byte aligned
 }
 
-template <bool LPF, bool COMP> int launch_replay_packed(const ReplayParams& p, cudaStream_t st) {
+template <bool LPF, bool AUX, bool COMP> int launch_replay_packed(const ReplayParams& p, cudaStream_t st) {
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) return POSEKF_ENODEV;
   CUtensorMap tmap;
@@ -993,7 +1024,7 @@ template <bool LPF, bool COMP> int launch_replay_packed(const ReplayParams& p, c
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return POSEKF_EALIGN;
-  auto kern = replay_tma2_kernel<LPF, COMP>;
+  auto kern = replay_tma2_kernel<LPF, AUX, COMP>;
   PKF_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Tma2Smem)));
   const unsigned grid = (unsigned)((p.N + kThreads - 1) / kThreads);
   kern<<<grid, kThreads2, sizeof(Tma2Smem), st>>>(p, tmap);
@@ -1021,8 +1052,13 @@ int replay_dispatch(const ReplayParams& p, int algo, int staging, cudaStream_t s
   } else return POSEKF_EINVAL;
   if (packed) {
     const bool comp = p.state_x_lo != nullptr;
-    if (lpf) return comp ? launch_replay_packed<true, true>(p, st) : launch_replay_packed<true, false>(p, st);
-    return comp ? launch_replay_packed<false, true>(p, st) : launch_replay_packed<false, false>(p, st);
+    const bool aux = p.out_traj != nullptr || p.out_flip != nullptr || p.truth != nullptr;
+    if (lpf) {
+      if (aux) return comp ? launch_replay_packed<true, true, true>(p, st) : launch_replay_packed<true, true, false>(p, st);
+      return comp ? launch_replay_packed<true, false, true>(p, st) : launch_replay_packed<true, false, false>(p, st);
+    }
+    if (aux) return comp ? launch_replay_packed<false, true, true>(p, st) : launch_replay_packed<false, true, false>(p, st);
+    return comp ? launch_replay_packed<false, false, true>(p, st) : launch_replay_packed<false, false, false>(p, st);
   }
   if (algo == POSEKF_WAHBA_QR2) return lpf ? launch_replay_aux<WAHBA_QR2, true>(p, use_tma, st) : launch_replay_aux<WAHBA_QR2, false>(p, use_tma, st);
   if (algo == POSEKF_WAHBA_JACOBI) return lpf ? launch_replay_aux<WAHBA_JACOBI, true>(p, use_tma, st) : launch_replay_aux<WAHBA_JACOBI, false>(p, use_tma, st);

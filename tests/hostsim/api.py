@@ -69,9 +69,10 @@ def replay_packed(streams, dt, acc_ref, mag_ref, q, r, *, lpf_acc=-1.0, lpf_mag=
     r = np.ascontiguousarray(np.broadcast_to(np.asarray(r, dtype=np.float32), (N,)))
     traj = np.empty((T, 4, N))
     P = np.empty((10, N))
+    flips = np.empty((T, N), dtype=np.uint8)
     rc = lib().hostsim_replay_packed(C.c_int(int(compensated)), C.c_int64(N), C.c_int64(T), _p(streams, C.c_float),
                                      _p(dt, C.c_double), C.c_int(int(dt.size > 1)), _p(acc_ref, C.c_float),
                                      _p(mag_ref, C.c_float), _p(q, C.c_float), _p(r, C.c_float), C.c_float(lpf_acc),
-                                     C.c_float(lpf_mag), _p(traj, C.c_double), _p(P, C.c_double))
+                                     C.c_float(lpf_mag), _p(traj, C.c_double), _p(P, C.c_double), _p(flips, C.c_uint8))
     assert rc == 0
-    return traj, P
+    return traj, P, flips.astype(bool)

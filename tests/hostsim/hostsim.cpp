@@ -50,7 +50,7 @@ static void replay_t(int64_t N, int64_t T, const float* streams, const double* d
 template <bool COMP>
 static void replay_packed_t(int64_t N, int64_t T, const float* streams, const double* dt, int dt_per_step,
                             const float* acc_ref, const float* mag_ref, const float* q, const float* r, float lpf_acc,
-                            float lpf_mag, double* out_traj, double* out_P) {
+                            float lpf_mag, double* out_traj, double* out_P, uint8_t* out_flip) {
   typedef f32x2 F;
   for (int64_t n = 0; n < N; n += 2) {
     Vec3<F> ra = {F(acc_ref[n], acc_ref[n + 1]), F(acc_ref[N + n], acc_ref[N + n + 1]), F(acc_ref[2 * N + n], acc_ref[2 * N + n + 1])};
@@ -68,8 +68,9 @@ static void replay_packed_t(int64_t N, int64_t T, const float* streams, const do
       if (lpf_acc >= 0.f) { lowpass<F>(la, a, F(lpf_acc), F(1.f - lpf_acc)); a = la; }
       if (lpf_mag >= 0.f) { lowpass<F>(lm, m, F(lpf_mag), F(1.f - lpf_mag)); m = lm; }
       F h = F((float)(dt_per_step ? dt[t] : dt[0]));
-      bool flip;
-      ekf_step<F, WAHBA_QR2, false, COMP>(x, xlo, P, fc, w, a, m, h, flip);
+      mask2 flip;
+      ekf_step<F, WAHBA_QR2, true, COMP>(x, xlo, P, fc, w, a, m, h, flip);
+      if (out_flip) { out_flip[(size_t)t * N + n] = flip.x; out_flip[(size_t)t * N + n + 1] = flip.y; }
       if (out_traj) {
         double* o = out_traj + (size_t)t * 4 * N + n;
         o[0] = x.w.x; o[1] = x.w.y; o[N] = x.x.x; o[N + 1] = x.x.y; o[2 * N] = x.y.x; o[2 * N + 1] = x.y.y;
@@ -87,10 +88,10 @@ extern "C" {
 
 int hostsim_replay_packed(int comp, int64_t N, int64_t T, const float* streams, const double* dt, int dt_per_step,
                           const float* acc_ref, const float* mag_ref, const float* q, const float* r, float lpf_acc,
-                          float lpf_mag, double* out_traj, double* out_P) {
+                          float lpf_mag, double* out_traj, double* out_P, uint8_t* out_flip) {
   if (N % 2) return 1;
-  if (comp) replay_packed_t<true>(N, T, streams, dt, dt_per_step, acc_ref, mag_ref, q, r, lpf_acc, lpf_mag, out_traj, out_P);
-  else replay_packed_t<false>(N, T, streams, dt, dt_per_step, acc_ref, mag_ref, q, r, lpf_acc, lpf_mag, out_traj, out_P);
+  if (comp) replay_packed_t<true>(N, T, streams, dt, dt_per_step, acc_ref, mag_ref, q, r, lpf_acc, lpf_mag, out_traj, out_P, out_flip);
+  else replay_packed_t<false>(N, T, streams, dt, dt_per_step, acc_ref, mag_ref, q, r, lpf_acc, lpf_mag, out_traj, out_P, out_flip);
   return 0;
 }
 

@@ -149,18 +149,20 @@ def test_packed_lanes_equal_scalar(golden_traj):
     what the scalar float32 instantiation gives (same operations, same order)."""
     g = golden_traj
     for comp in (False, True):
-        a, _, Pa = H.replay(g["noisy_streams"], 0.01, g["noisy_acc_ref"], g["noisy_mag_ref"], g["noisy_q"], g["noisy_r"],
-                            precision="f32", algo="qr2", compensated=comp, lpf_acc=0.3)
-        b, Pb = H.replay_packed(g["noisy_streams"], 0.01, g["noisy_acc_ref"], g["noisy_mag_ref"], g["noisy_q"], g["noisy_r"],
-                                compensated=comp, lpf_acc=0.3)
+        a, fa, Pa = H.replay(g["noisy_streams"], 0.01, g["noisy_acc_ref"], g["noisy_mag_ref"], g["noisy_q"], g["noisy_r"],
+                             precision="f32", algo="qr2", compensated=comp, lpf_acc=0.3)
+        b, Pb, fb = H.replay_packed(g["noisy_streams"], 0.01, g["noisy_acc_ref"], g["noisy_mag_ref"], g["noisy_q"], g["noisy_r"],
+                                    compensated=comp, lpf_acc=0.3)
         np.testing.assert_array_equal(a, b)
         np.testing.assert_array_equal(Pa, Pb)
+        np.testing.assert_array_equal(fa, fb)
     # negative-weight branch in one lane only (|acc_z| > 1 for filter 0, normal for filter 1) and an
     # "unrelated measurement" start (X0 far from the first measurement) in the other lane
     S = g["clean_streams"][:50, :, :2].copy()
     S[:, 3:6, 0] *= 3.0
     ar, mr = g["clean_acc_ref"][:, :2].copy(), g["clean_mag_ref"][:, :2].copy()
     mr[:, 1] = -mr[:, 1]; ar[:, 1] = -ar[:, 1]
-    a, _, _ = H.replay(S, 0.01, ar, mr, 1.0, 0.1, precision="f32", algo="qr2")
-    b, _ = H.replay_packed(S, 0.01, ar, mr, 1.0, 0.1)
+    a, fa, _ = H.replay(S, 0.01, ar, mr, 1.0, 0.1, precision="f32", algo="qr2")
+    b, _, fb = H.replay_packed(S, 0.01, ar, mr, 1.0, 0.1)
     np.testing.assert_array_equal(a, b)
+    np.testing.assert_array_equal(fa, fb)
