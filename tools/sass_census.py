@@ -35,11 +35,15 @@ def opcode(line):
 out = {}
 for name, lines in funcs.items():
     m = re.search(r"replay_(tma|ldg)_kernelILi(\d)ELb(\d)ELb(\d)ELb(\d)E", name)
-    if not m:
+    m2 = re.search(r"replay_tma2_kernelILb(\d)ELb(\d)ELb(\d)E", name)
+    if m:
+        key = f"replay_{m.group(1)}<algo={m.group(2)},lpf={m.group(3)},aux={m.group(4)},comp={m.group(5)}>"
+    elif m2:
+        key = f"replay_tma2_packed<lpf={m2.group(1)},aux={m2.group(2)},comp={m2.group(3)}>"
+    else:
         continue
-    key = f"replay_{m.group(1)}<algo={m.group(2)},lpf={m.group(3)},aux={m.group(4)},comp={m.group(5)}>"
     ops = collections.Counter(opcode(l) for l in lines)
-    fp = {k: ops[k] for k in ("FFMA", "FMUL", "FADD", "MUFU", "FSEL", "FSETP", "UTMALDG", "SYNCS", "LDS", "LDG", "STG",
+    fp = {k: ops[k] for k in ("FFMA2", "FMUL2", "FADD2", "FFMA", "FMUL", "FADD", "MUFU", "FSEL", "FSETP", "UTMALDG", "SYNCS", "LDS", "LDG", "STG",
                               "LDL", "STL", "HMMA")}
     out[key] = {"total_static": len(lines), **fp}
 print(json.dumps(out, indent=1))
