@@ -149,9 +149,10 @@ def replay(streams: torch.Tensor, acc_ref: torch.Tensor, mag_ref: torch.Tensor, 
     (created with the reference's initial values when None).  `truth` [T,Ns,4] enables the on-device
     tuning objective: `loss` [N] (created zeroed when None; pass it back in for chunked replays) is
     incremented by sum_t 1-(X_t.truth_t)^2 and is available as `state.loss`.
-    `precise_state` carries X as two floats (compensated summation) so that gains ~1e-7 (R >> Q) are
-    not lost to float32 rounding over long replays; None = automatic: on when q or r are per-filter
-    tensors (a tuning sweep) or when r/q >= 100, off otherwise (the default Q=1, R=0.1 does not need it).
+    `precise_state` selects the precise variant for extreme Q/R ratios (two-float state so that gains
+    ~1e-7 are not lost when R >> Q; Sherman-Morrison gain when Q >> R; +17 % time); None = automatic:
+    on when q or r are per-filter tensors (a tuning sweep), when r/q >= 100 or q/r >= 1e4, off otherwise
+    (the default Q=1, R=0.1 does not need it).
     Returns (state, traj [T,N,4] or None, flips [T,N] uint8 or None)."""
     _require_cuda(streams, acc_ref, mag_ref, out_traj)
     if streams.dim() != 3 or streams.shape[1] != 9:
@@ -169,7 +170,7 @@ def replay(streams: torch.Tensor, acc_ref: torch.Tensor, mag_ref: torch.Tensor, 
     state.r = r
     if precise_state is None:
         precise_state = (state.x_lo is not None or isinstance(q, torch.Tensor) or isinstance(r, torch.Tensor)
-                         or float(r) >= 100.0 * float(q))
+                         or float(r) >= 100.0 * float(q) or float(q) >= 1.0e4 * float(r))
     if precise_state and state.x_lo is None:
         state.x_lo = torch.zeros((4, N), dtype=torch.float32, device=dev)
     _require_cuda(state.x_lo)
