@@ -13,7 +13,10 @@ LIB_PATH = os.path.join(PKG_DIR, "libposekf_b200.so")
 SOURCES = [os.path.join(CSRC, "posekf_kernels.cu")]
 DEPENDS = SOURCES + [os.path.join(CSRC, "ekf_math.cuh"), os.path.join(PKG_DIR, "..", "include", "posekf.h")]
 
-NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--shared",
+# -fmad=false: only the explicit fma_() calls of ekf_math.cuh fuse.  The scalar kernels, the packed (f32x2
+# intrinsics, never contracted) kernels and the g++ -ffp-contract=off host build then execute the same
+# roundings, which is what makes their results bit-identical.
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-fmad=false", "--shared",
               "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
 
 

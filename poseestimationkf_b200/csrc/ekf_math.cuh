@@ -105,6 +105,7 @@ PKF_HD f32x2 operator/(const f32x2& a, const f32x2& b) { return f32x2(a.x / b.x,
 PKF_HD f32x2& operator*=(f32x2& a, const f32x2& b) { a = a * b; return a; }
 PKF_HD mask2 operator<(const f32x2& a, const f32x2& b) { return mask2{a.x < b.x, a.y < b.y}; }
 PKF_HD mask2 operator>(const f32x2& a, const f32x2& b) { return mask2{a.x > b.x, a.y > b.y}; }
+PKF_HD mask2 operator==(const f32x2& a, const f32x2& b) { return mask2{a.x == b.x, a.y == b.y}; }
 PKF_HD f32x2 sel_(mask2 c, const f32x2& a, const f32x2& b) { return f32x2(c.x ? a.x : b.x, c.y ? a.y : b.y); }
 template <> PKF_HD f32x2 fma_<f32x2>(f32x2 a, f32x2 b, f32x2 c) {
 #if defined(__CUDA_ARCH__)
@@ -377,7 +378,7 @@ template <typename F> PKF_HD Sym4<F> kalman_gain_sm(const Sym4<F>& M, const Quat
   const F x2 = dot4(x, x);
   const F c = g * x2;
   Sym4<F> PH = M;
-  PH.a00 = M.a00 + c; PH.a11 = M.a11 + c; PH.a22 = M.a22 + c; PH.a33 = M.a33 + c;
+  PH.a00 = fma_(g, x2, M.a00); PH.a11 = fma_(g, x2, M.a11); PH.a22 = fma_(g, x2, M.a22); PH.a33 = fma_(g, x2, M.a33);
   const Ldl4<F> f = ldl_unit(PH);
   const Sym4<F> KH = gain_from_ldl(f);
   // w = H^-1 x = W^T D^-1 W x, W = I + N (solved through the factors: x - K_H x would cancel when g >> 1)
@@ -421,17 +422,17 @@ template <typename F> PKF_HD Sym4<F> kalman_gain_sm(const Sym4<F>& M, const Quat
 template <typename F>
 PKF_HD Mat3<F> wahba_qr2(const RefFrame<F>& E, const Vec3<F>& a, const Vec3<F>& m, F ka, F km) {
   RefFrame<F> Fb = frame_from_pair(a, m);
-  F g = km * Fb.s12, hh = km * Fb.s22;
-  F c00 = fma_(E.s12, g, (E.s11 * ka) * Fb.s11);
-  F c01 = E.s12 * hh;
-  F c10 = E.s22 * g;
-  F c11 = E.s22 * hh;
-  // sg = sign(ka km) is +1 whenever both weights are positive (always for normalised accelerometer
-  // input: ka = |a_z| <= 1); the reflected case is a rarely taken branch.
+  // (every product that feeds a sum is an explicit fma_: nothing is left to the compiler's
+  //  contraction heuristics, so the scalar, packed and host builds round identically)
   const auto neg = (ka * km) < F(0);
-  if (any_(neg)) { c11 = sel_(neg, -c11, c11); c01 = sel_(neg, -c01, c01); }
-  F p = c00 + c11;
-  F r = c10 - c01;
+  F g = km * Fb.s12, hh = km * Fb.s22;
+  // sg = sign(ka km) is +1 whenever both weights are positive (always for normalised accelerometer
+  // input: ka = |a_z| <= 1); the reflected case flips the sign of c01 and c11.
+  if (any_(neg)) hh = sel_(neg, -hh, hh);
+  F c00 = fma_(E.s12, g, (E.s11 * ka) * Fb.s11);
+  F c01 = E.s12 * hh;                      // sg c01
+  F p = fma_(E.s22, hh, c00);              // c00 + sg c11
+  F r = fma_(E.s22, g, -c01);              // c10 - sg c01
   F inv = rsqrt_(fma_(p, p, r * r));
   F cs = p * inv, sn = r * inv;
   // W = E * blockdiag([[cs, -sg sn],[sn, sg cs]], sg)
@@ -573,13 +574,14 @@ template <typename F> PKF_HD Quat<F> rotation_to_quat_ref(const Mat3<F>& M) {
   F dx = M.m[2][1] - M.m[1][2], dy = M.m[0][2] - M.m[2][0], dz = M.m[1][0] - M.m[0][1];
   F sxy = M.m[0][1] + M.m[1][0], sxz = M.m[0][2] + M.m[2][0], syz = M.m[1][2] + M.m[2][1];
   // reference branch (sign convention): 1 -> x, 2 -> y, else z
-  bool b1 = (tr1 > tr2) && (tr1 > tr3);
-  bool b2 = !b1 && (tr2 > tr1) && (tr2 > tr3);
+  auto b1 = (tr1 > tr2) && (tr1 > tr3);
+  auto b2 = !b1 && ((tr2 > tr1) && (tr2 > tr3));
   // best-conditioned candidate among (w,x,y,z): the largest of the four traces (independent of the
   // reference's tie rule, which only fixes the sign)
-  F mwx = tr0 > tr1 ? tr0 : tr1, myz = tr2 > tr3 ? tr2 : tr3;
-  bool lo = mwx > myz;                           // winner is w or x, else y or z
-  bool kw = lo && (tr0 > tr1), kx = lo && !(tr0 > tr1), ky = !lo && (tr2 > tr3);
+  auto w_gt_x = tr0 > tr1, y_gt_z = tr2 > tr3;
+  F mwx = sel_(w_gt_x, tr0, tr1), myz = sel_(y_gt_z, tr2, tr3);
+  auto lo = mwx > myz;                           // winner is w or x, else y or z
+  auto kw = lo && w_gt_x, kx = lo && !w_gt_x, ky = !lo && y_gt_z;
   Quat<F> c;
   c.w = sel_(kw, tr0, sel_(kx, dx, sel_(ky, dy, dz)));
   c.x = sel_(kw, dx, sel_(kx, tr1, sel_(ky, sxy, sxz)));
@@ -592,8 +594,8 @@ template <typename F> PKF_HD Quat<F> rotation_to_quat_ref(const Mat3<F>& M) {
   Quat<F> q;
   q.w = c.w * inv; q.x = c.x * inv; q.y = c.y * inv; q.z = c.z * inv;
   // exact identity: S = 0 in the reference's last branch -> 0/0, 0/0, 0/0, 0.25*0
-  bool ident = (tr1 == F(0)) && (tr2 == F(0)) && (tr3 == F(0)) && (dx == F(0)) && (dy == F(0)) && (dz == F(0));
-  F nanv = (F)NAN;
+  auto ident = ((tr1 == F(0)) && (tr2 == F(0))) && ((tr3 == F(0)) && (dx == F(0))) && ((dy == F(0)) && (dz == F(0)));
+  F nanv = F(NAN);
   q.w = sel_(ident, nanv, q.w); q.x = sel_(ident, nanv, q.x); q.y = sel_(ident, nanv, q.y); q.z = sel_(ident, F(0), q.z);
   return q;
 }

@@ -117,6 +117,12 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, u
       : "memory");
 }
 
+__device__ __forceinline__ f32x2 ld2(const float* p) {
+  const float2 v = *reinterpret_cast<const float2*>(p);
+  return f32x2(v.x, v.y);
+}
+__device__ __forceinline__ void st2(float* p, const f32x2& v) { *reinterpret_cast<float2*>(p) = make_float2(v.x, v.y); }
+
 struct ReplayParams {
   int64_t N, T, Ns;
   const float* streams;
@@ -363,12 +369,6 @@ struct FilterRegs2 {
   FilterConst<f32x2> fc;
   Vec3<f32x2> la, lm;
 };
-
-__device__ __forceinline__ f32x2 ld2(const float* p) {
-  const float2 v = *reinterpret_cast<const float2*>(p);
-  return f32x2(v.x, v.y);
-}
-__device__ __forceinline__ void st2(float* p, const f32x2& v) { *reinterpret_cast<float2*>(p) = make_float2(v.x, v.y); }
 
 template <bool LPF, bool AUX, bool COMP>
 __global__ void __launch_bounds__(kThreads2, (LPF && COMP) ? (PKF_MIN_CTAS2 > 6 ? 6 : PKF_MIN_CTAS2) : PKF_MIN_CTAS2)
@@ -685,6 +685,45 @@ __global__ void __launch_bounds__(256) traj2rpy_kernel(int64_t M, const float4* 
   out[3 * i] = atan2f(2.f * (w * x + y * z), 1.f - 2.f * (x * x + y * y)) * k;
   out[3 * i + 1] = asinf(2.f * (w * y - z * x)) * k;
   out[3 * i + 2] = atan2f(2.f * (w * z + x * y), 1.f - 2.f * (y * y + z * z)) * k;
+}
+
+// Packed form of the rank-2 Wahba kernel: two solves per thread in f32x2 lanes (N even, per-pair or
+// shared references).  Same arithmetic per solve as wahba_kernel<WAHBA_QR2>.
+__global__ void __launch_bounds__(256) wahba2_kernel(const WahbaParams p) {
+  const int64_t n = 2 * ((int64_t)blockIdx.x * blockDim.x + threadIdx.x);
+  if (n >= p.N) return;
+  const int64_t N = p.N;
+  Vec3<f32x2> ra, rm;
+  if (p.ref_shared) {
+    ra = {f32x2(__ldg(p.acc_ref)), f32x2(__ldg(p.acc_ref + 1)), f32x2(__ldg(p.acc_ref + 2))};
+    rm = {f32x2(__ldg(p.mag_ref)), f32x2(__ldg(p.mag_ref + 1)), f32x2(__ldg(p.mag_ref + 2))};
+  } else {
+    ra = {ld2(p.acc_ref + n), ld2(p.acc_ref + N + n), ld2(p.acc_ref + 2 * N + n)};
+    rm = {ld2(p.mag_ref + n), ld2(p.mag_ref + N + n), ld2(p.mag_ref + 2 * N + n)};
+  }
+  auto ld2s = [](const float* q) {
+    float2 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(q));
+    return f32x2(v.x, v.y);
+  };
+  Vec3<f32x2> a = {ld2s(p.acc + n), ld2s(p.acc + N + n), ld2s(p.acc + 2 * N + n)};
+  Vec3<f32x2> m = {ld2s(p.mag + n), ld2s(p.mag + N + n), ld2s(p.mag + 2 * N + n)};
+  f32x2 ka, km;
+  if (p.k_acc) { ka = ld2s(p.k_acc + n); km = ld2s(p.k_mag + n); }
+  else if (p.weights_from_acc) { ka = abs_<f32x2>(a.z); km = f32x2(1.f) - ka; }
+  else { ka = f32x2(p.k_acc_s); km = f32x2(p.k_mag_s); }
+  const Mat3<f32x2> R = wahba_qr2<f32x2>(frame_from_pair<f32x2>(ra, rm), a, m, ka, km);
+  auto st2s = [](float* q, const f32x2& v) { asm volatile("st.global.cs.v2.f32 [%0], {%1, %2};" ::"l"(q), "f"(v.x), "f"(v.y) : "memory"); };
+  if (p.out_rot) {
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int c = 0; c < 3; ++c) st2s(p.out_rot + (3 * r + c) * N + n, R.m[r][c]);
+  }
+  if (p.out_quat) {
+    const Quat<f32x2> q = rotation_to_quat_ref<f32x2>(R);
+    st2s(p.out_quat + n, q.w); st2s(p.out_quat + N + n, q.x); st2s(p.out_quat + 2 * N + n, q.y); st2s(p.out_quat + 3 * N + n, q.z);
+  }
 }
 
 __global__ void __launch_bounds__(256) rot2quat_kernel(int64_t N, const float* __restrict__ rot, float* __restrict__ out) {
@@ -1271,7 +1310,14 @@ int posekf_wahba_f32(int64_t n, const float* acc_ref, const float* mag_ref, int 
   WahbaParams p{n, acc_ref, mag_ref, ref_shared, acc, mag, k_acc, k_mag, k_acc_s, k_mag_s, weights_from_acc,
                 out_rot, out_quat, jacobi_sweeps > 0 ? jacobi_sweeps : 6};
   cudaStream_t st = (cudaStream_t)stream;
-  if (wahba_algo == POSEKF_WAHBA_QR2) wahba_kernel<WAHBA_QR2><<<blocks_for(n, 256), 256, 0, st>>>(p);
+  if (wahba_algo == POSEKF_WAHBA_QR2) {
+    // two solves per thread (packed f32x2) when every [k][N] array can be read as float2
+    bool packed = (n & 1) == 0;
+    const void* ptrs[] = {acc, mag, k_acc, k_mag, out_rot, out_quat, ref_shared ? nullptr : acc_ref, ref_shared ? nullptr : mag_ref};
+    for (const void* q : ptrs) packed = packed && (reinterpret_cast<uintptr_t>(q) & 7) == 0;
+    if (packed) wahba2_kernel<<<blocks_for(n / 2, 256), 256, 0, st>>>(p);
+    else wahba_kernel<WAHBA_QR2><<<blocks_for(n, 256), 256, 0, st>>>(p);
+  }
   else if (wahba_algo == POSEKF_WAHBA_JACOBI) wahba_kernel<WAHBA_JACOBI><<<blocks_for(n, 256), 256, 0, st>>>(p);
   else return POSEKF_EINVAL;
   return launch_status();

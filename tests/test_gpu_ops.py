@@ -265,3 +265,22 @@ def test_wahba_negative_weights_on_device(cuda):
                        want_quaternion=False, algo=algo)
         err = np.abs(R.cpu().numpy().T.reshape(-1, 3, 3) - Rref).max(axis=(1, 2))
         assert err[ok].max() < 2e-5, (algo, err[ok].max())
+
+
+def test_packed_wahba_kernel_bitwise_equals_scalar(golden_wahba, cuda):
+    """posekf_wahba_f32 runs two solves per thread (f32x2) when N is even; an odd N takes the scalar
+    kernel.  Same operations per solve, so dropping the last element must not change the others."""
+    g = golden_wahba
+    args = [_dev(g[k].T, cuda) for k in ("acc_ref", "mag_ref", "acc", "mag")]
+    ka, km = _dev(g["refw_ka"], cuda), _dev(g["refw_km"], cuda)
+    R2, q2 = B.wahba(*args, k_acc=ka, k_mag=km, want_rotation=True)                          # N = 1500: packed
+    odd = [a[:, :1499].contiguous() for a in args]
+    R1, q1 = B.wahba(*odd, k_acc=ka[:1499].contiguous(), k_mag=km[:1499].contiguous(), want_rotation=True)   # scalar
+    assert torch.equal(R2[:, :1499], R1) and torch.equal(q2[:, :1499], q1)
+    # shared reference pair + weights taken from the accelerometer, and the NaN-at-identity rule in a lane
+    ra, rm = args[0][:, 0].contiguous(), args[1][:, 0].contiguous()
+    acc = torch.stack([ra, args[2][:, 1]], dim=1).contiguous()
+    mag = torch.stack([rm, args[3][:, 1]], dim=1).contiguous()
+    _, qa = B.wahba(ra, rm, acc, mag, weights_from_acc=True)
+    _, qb = B.wahba(ra, rm, acc[:, 1:].contiguous(), mag[:, 1:].contiguous(), weights_from_acc=True)
+    assert torch.equal(qa[:, 1:], qb)
