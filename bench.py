@@ -51,6 +51,7 @@ def parse():
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target wall time of the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-variants", action="store_true", help="skip the context measurements of the other kernels")
     ap.add_argument("--precise-state", action="store_true",
                     help="compensated two-float state (needed for R >> Q sweeps, not for the Q=1, R=0.1 headline config)")
     return ap.parse_args()
@@ -291,6 +292,37 @@ def run_ours(args):
     avg_kernel_ms = sum(kernel_ms) / len(kernel_ms)
     steps_per_s_kernel = N * T / (avg_kernel_ms * 1e-3)
 
+    # --- context: the other kernels on the first 250 timesteps of the same resident workload (not the headline) ----
+    variants = {}
+    if rank == 0 and not args.no_variants:
+        Tv = min(250, T)
+        sub = streams[:Tv]
+        traj_buf = torch.empty((Tv, N, 4), dtype=torch.float32, device=dev)
+
+        def rate(**kw):
+            best = 1e30
+            for i in range(3):
+                st = B.ReplayState.initial(N, dev, r=0.1)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                B.replay(sub, acc_ref, mag_ref, dt=0.01, q=q, r=r, state=st, **kw)
+                e1.record()
+                torch.cuda.synchronize()
+                if i:
+                    best = min(best, e0.elapsed_time(e1))
+            return N * Tv / (best * 1e-3)
+
+        variants = {
+            "packed_tma (default)": rate(precise_state=False, staging="tma_packed"),
+            "scalar_tma": rate(precise_state=False, staging="tma"),
+            "scalar_ldg": rate(precise_state=False, staging="ldg"),
+            "packed_tma + precise variant (sweeps)": rate(precise_state=True, staging="tma_packed"),
+            "packed_tma + trajectory stored [T,N,4]": rate(precise_state=False, staging="tma_packed", out_traj=traj_buf),
+            "scalar_tma, Jacobi SVD Wahba (north_star literal)": rate(precise_state=False, staging="tma", wahba="jacobi"),
+        }
+        del traj_buf
+        variants = {k: round(v / 1e9, 2) for k, v in variants.items()}
+
     # --- e2e: host buffers through the C ABI (H2D + kernel + D2H inside the timed region) --------
     e2e = None
     if not args.no_e2e:
@@ -391,6 +423,7 @@ def run_ours(args):
         "e2e": e2e,
         "gpu_launches": K,
         "clocks": clocks,
+        "variants_gsteps_per_s_1gpu_250_timesteps": variants,
     }
     if not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(args.cpu_seconds)
