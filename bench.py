@@ -339,13 +339,14 @@ def run_ours(args):
         link_gbs = host.numel() * 4 / (time.perf_counter() - tl0) / 1e9
         del scratch
         ws = B.HostWorkspace(N, device=local)
-        B.replay_host(host, ar_h, mr_h, dt=0.01, q=q_h, r=r_h, wahba=args.wahba, device=local, workspace=ws)   # warm-up
+        B.replay_host(host, ar_h, mr_h, dt=0.01, q=q_h, r=r_h, wahba=args.wahba, device=local, workspace=ws,
+                      precise_state=args.precise_state)   # warm-up
         barrier()
         reps_e = 3
         t0 = time.perf_counter()
         for _ in range(reps_e):
             x_h, p_h, _ = B.replay_host(host, ar_h, mr_h, dt=0.01, q=q_h, r=r_h, wahba=args.wahba, device=local,
-                                        workspace=ws)
+                                        workspace=ws, precise_state=args.precise_state)
         barrier()
         dt_e = (time.perf_counter() - t0) / reps_e
         if world > 1:

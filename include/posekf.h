@@ -104,6 +104,7 @@ int posekf_replay_f32(int64_t n_filters, int64_t n_steps, const float* streams, 
  *   out_x_host [4][N], out_p_host [10][N] = upper triangle of P itself, unscaled (may be NULL), out_traj_host [T][N][4] (may be NULL).
  *   x0_host / p0_host ([4][N] / [10][N] upper triangle of P, unscaled) may be NULL (X=[1,0,0,0], P=I4:
  *   PKF/main_file.py:23,26).
+ *   precise     non-zero selects the precise variant (see state_x_lo of posekf_replay_f32) for extreme Q/R.
  *   chunk_steps  steps per chunk when no workspace is given (0 = about 256 MiB per staging buffer).
  *   device      CUDA device ordinal.
  *   workspace   from posekf_host_workspace_create (staging buffers, streams and events are reused across
@@ -114,7 +115,8 @@ int posekf_replay_host_f32(int64_t n_filters, int64_t n_steps, const float* stre
                            const float* acc_ref_host, const float* mag_ref_host, const float* q_scale_host,
                            const float* r_scale_host, float lpf_alpha_acc, float lpf_alpha_mag,
                            const float* x0_host, const float* p0_host, float* out_x_host, float* out_p_host,
-                           float* out_traj_host, int64_t chunk_steps, int wahba_algo, int device, void* workspace);
+                           float* out_traj_host, int64_t chunk_steps, int wahba_algo, int precise, int device,
+                           void* workspace);
 
 /* Reusable workspace of posekf_replay_host_f32 for batches of n_filters on `device` (the only objects
  * this library ever allocates).  chunk_steps <= 0 picks ~256 MiB staging buffers. */

@@ -231,11 +231,13 @@ class HostWorkspace:
 
 
 def replay_host(streams, acc_ref, mag_ref, *, dt: float, q, r, lpf_alpha_acc=None, lpf_alpha_mag=None,
-                store_trajectory=False, chunk_steps: int = 0, wahba: str = "qr2", device: int = 0,
-                workspace: "HostWorkspace | None" = None):
+                store_trajectory=False, chunk_steps: int = 0, wahba: str = "qr2", precise_state: bool = True,
+                device: int = 0, workspace: "HostWorkspace | None" = None):
     """End-to-end replay from HOST memory (CPU torch tensors, ideally pinned): the stream is pushed
     through the GPU in double-buffered time chunks and the final state (and optionally the
     trajectory) is copied back.  streams [T,9,N] float32 CPU; acc_ref/mag_ref [3,N]; q, r [N].
+    `precise_state` (default on: per-filter q/r are given as arrays here, and the link, not the kernel,
+    bounds this path) selects the precise variant for extreme Q/R ratios.
     Returns (x [4,N], p [10,N], traj [T,N,4] or None) as CPU tensors."""
     for t in (streams, acc_ref, mag_ref, q, r):
         if t.is_cuda or t.dtype != torch.float32 or not t.is_contiguous():
@@ -249,7 +251,7 @@ def replay_host(streams, acc_ref, mag_ref, *, dt: float, q, r, lpf_alpha_acc=Non
         N, T, _ptr(streams), float(dt), _ptr(acc_ref), _ptr(mag_ref), _ptr(q), _ptr(r),
         -1.0 if lpf_alpha_acc is None else float(lpf_alpha_acc),
         -1.0 if lpf_alpha_mag is None else float(lpf_alpha_mag),
-        None, None, _ptr(x), _ptr(p), _ptr(traj), int(chunk_steps), _lib.WAHBA[wahba], int(device),
+        None, None, _ptr(x), _ptr(p), _ptr(traj), int(chunk_steps), _lib.WAHBA[wahba], int(bool(precise_state)), int(device),
         None if workspace is None else workspace.handle)
     _lib.check(rc, "posekf_replay_host_f32")
     return x, p, traj

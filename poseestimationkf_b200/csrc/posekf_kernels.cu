@@ -1147,7 +1147,7 @@ struct HostWorkspace {
   cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr}, ev_traj[2] = {nullptr, nullptr},
               ev_tfree[2] = {nullptr, nullptr};
   float *d_in[2] = {nullptr, nullptr}, *d_traj[2] = {nullptr, nullptr};
-  float *d_ref = nullptr, *d_qr = nullptr, *d_x = nullptr, *d_p = nullptr, *d_lpf = nullptr, *d_dt = nullptr;
+  float *d_ref = nullptr, *d_qr = nullptr, *d_x = nullptr, *d_xlo = nullptr, *d_p = nullptr, *d_lpf = nullptr, *d_dt = nullptr;
 };
 
 static void host_ws_free(HostWorkspace* w) {
@@ -1161,7 +1161,7 @@ static void host_ws_free(HostWorkspace* w) {
     if (w->ev_traj[i]) cudaEventDestroy(w->ev_traj[i]);
     if (w->ev_tfree[i]) cudaEventDestroy(w->ev_tfree[i]);
   }
-  float* ptrs[] = {w->d_ref, w->d_qr, w->d_x, w->d_p, w->d_lpf, w->d_dt};
+  float* ptrs[] = {w->d_ref, w->d_qr, w->d_x, w->d_xlo, w->d_p, w->d_lpf, w->d_dt};
   for (float* q : ptrs) if (q) cudaFree(q);
   if (w->s_copy) cudaStreamDestroy(w->s_copy);
   if (w->s_comp) cudaStreamDestroy(w->s_comp);
@@ -1199,6 +1199,7 @@ int posekf_host_workspace_create(int device, int64_t n_filters, int64_t chunk_st
   WS_TRY(cudaMalloc(&w->d_ref, (size_t)6 * N * sizeof(float)));
   WS_TRY(cudaMalloc(&w->d_qr, (size_t)2 * N * sizeof(float)));
   WS_TRY(cudaMalloc(&w->d_x, (size_t)4 * N * sizeof(float)));
+  WS_TRY(cudaMalloc(&w->d_xlo, (size_t)4 * N * sizeof(float)));
   WS_TRY(cudaMalloc(&w->d_p, (size_t)10 * N * sizeof(float)));
   WS_TRY(cudaMalloc(&w->d_lpf, (size_t)6 * N * sizeof(float)));
   WS_TRY(cudaMalloc(&w->d_dt, sizeof(float)));
@@ -1216,7 +1217,7 @@ int posekf_replay_host_f32(int64_t N, int64_t T, const float* streams_host, floa
                            const float* mag_ref_host, const float* q_scale_host, const float* r_scale_host,
                            float lpf_alpha_acc, float lpf_alpha_mag, const float* x0_host, const float* p0_host,
                            float* out_x_host, float* out_p_host, float* out_traj_host, int64_t chunk_steps,
-                           int wahba_algo, int device, void* workspace) {
+                           int wahba_algo, int precise, int device, void* workspace) {
   if (N <= 0 || T < 0 || !streams_host || !acc_ref_host || !mag_ref_host || !q_scale_host || !r_scale_host || !out_x_host)
     return POSEKF_EINVAL;
   const bool traj = out_traj_host != nullptr;
@@ -1243,7 +1244,9 @@ int posekf_replay_host_f32(int64_t N, int64_t T, const float* streams_host, floa
   cudaStream_t s_copy = w->s_copy, s_comp = w->s_comp, s_out = w->s_out;
   float* d_ref = w->d_ref; float* d_qr = w->d_qr; float* d_x = w->d_x; float* d_p = w->d_p; float* d_dt = w->d_dt;
   float* d_lpf = lpf ? w->d_lpf : nullptr;
+  float* d_xlo = precise ? w->d_xlo : nullptr;
   if (lpf) TRY(cudaMemsetAsync(d_lpf, 0, (size_t)6 * N * sizeof(float), s_comp));
+  if (precise) TRY(cudaMemsetAsync(d_xlo, 0, (size_t)4 * N * sizeof(float), s_comp));
   TRY(cudaMemcpyAsync(d_ref, acc_ref_host, (size_t)3 * N * sizeof(float), cudaMemcpyHostToDevice, s_comp));
   TRY(cudaMemcpyAsync(d_ref + 3 * N, mag_ref_host, (size_t)3 * N * sizeof(float), cudaMemcpyHostToDevice, s_comp));
   TRY(cudaMemcpyAsync(d_qr, q_scale_host, (size_t)N * sizeof(float), cudaMemcpyHostToDevice, s_comp));
@@ -1273,7 +1276,7 @@ int posekf_replay_host_f32(int64_t N, int64_t T, const float* streams_host, floa
     TRY(cudaStreamWaitEvent(s_comp, w->ev_in[b], 0));
     if (traj && c >= 2) TRY(cudaStreamWaitEvent(s_comp, w->ev_tfree[b], 0));  // D2H of chunk c-2 done with d_traj[b]
     rc = posekf_replay_f32(N, tc, w->d_in[b], N, d_dt, 0, d_ref, d_ref + 3 * N, d_qr, d_qr + N, lpf_alpha_acc,
-                           lpf_alpha_mag, d_x, nullptr, d_p, d_lpf, traj ? w->d_traj[b] : nullptr, nullptr, nullptr, nullptr,
+                           lpf_alpha_mag, d_x, d_xlo, d_p, d_lpf, traj ? w->d_traj[b] : nullptr, nullptr, nullptr, nullptr,
                            wahba_algo, POSEKF_STAGE_AUTO, s_comp);
     if (rc != 0) { if (own) host_ws_free(w); return rc; }
     TRY(cudaEventRecord(w->ev_free[b], s_comp));

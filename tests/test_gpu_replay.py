@@ -173,7 +173,7 @@ def test_replay_from_host_buffers(cuda):
     q = torch.full((N,), 1.0); r = torch.full((N,), 0.1)
     for chunk in (0, 1, 50, 300):
         x, p, traj = B.replay_host(host, imu.acc_ref.cpu(), imu.mag_ref.cpu(), dt=imu.dt, q=q, r=r,
-                                   store_trajectory=True, chunk_steps=chunk)
+                                   store_trajectory=True, chunk_steps=chunk, precise_state=False)
         assert torch.equal(x, dev_state.x.cpu())
         torch.testing.assert_close(p, dev_state.p.cpu() * 0.1, rtol=1e-6, atol=0)
         assert torch.equal(traj, dev_traj.cpu())
@@ -181,8 +181,12 @@ def test_replay_from_host_buffers(cuda):
     ws = B.HostWorkspace(N, chunk_steps=37, with_trajectory=True)
     for want_traj in (True, False, True):
         x, p, traj = B.replay_host(host, imu.acc_ref.cpu(), imu.mag_ref.cpu(), dt=imu.dt, q=q, r=r,
-                                   store_trajectory=want_traj, workspace=ws)
+                                   store_trajectory=want_traj, workspace=ws, precise_state=False)
         assert torch.equal(x, dev_state.x.cpu()) and (traj is None or torch.equal(traj, dev_traj.cpu()))
+    # the precise variant through the host path equals the precise device path
+    prec_state, _, _ = B.replay(imu.streams, imu.acc_ref, imu.mag_ref, dt=imu.dt, precise_state=True)
+    x, _, _ = B.replay_host(host, imu.acc_ref.cpu(), imu.mag_ref.cpu(), dt=imu.dt, q=q, r=r, workspace=ws, precise_state=True)
+    assert torch.equal(x, prec_state.x.cpu())
     ws.close()
     with pytest.raises(_lib.PosekfError):          # a workspace for another batch size is rejected
         ws2 = B.HostWorkspace(N // 2)
