@@ -53,7 +53,11 @@ constexpr int kChannels = 9;
 #ifndef PKF_MIN_CTAS2
 #define PKF_MIN_CTAS2 6
 #endif
-constexpr int kThreads2 = 64;                  // threads per CTA of the packed kernel (still 128 filters per CTA)
+#ifndef PKF_THREADS2
+#define PKF_THREADS2 64
+#endif
+constexpr int kThreads2 = PKF_THREADS2;        // threads per CTA of the packed kernel
+constexpr int kTile2 = 2 * kThreads2;          // filters per CTA (two per thread); TMA box width, <= 256
 constexpr int kTma2Steps = PKF_TMA2_STEPS;
 constexpr int kTma2Stages = PKF_TMA2_STAGES;
 #ifndef PKF_AUTO_PACKED
@@ -357,11 +361,11 @@ __global__ void __launch_bounds__(kThreads, (COMP && (LPF || AUX)) ? (kMinCtasPe
 // threads.  Rank-2 Wahba only (the Jacobi variant uses the scalar kernel).
 // ---------------------------------------------------------------------------------------------
 struct __align__(128) Tma2Smem {
-  float tile[kTma2Stages][kTma2Steps][kChannels][kThreads];
+  float tile[kTma2Stages][kTma2Steps][kChannels][kTile2];
   uint64_t full[kTma2Stages];
   uint64_t empty[kTma2Stages];
 };
-constexpr uint32_t kTile2Bytes = kTma2Steps * kChannels * kThreads * sizeof(float);
+constexpr uint32_t kTile2Bytes = kTma2Steps * kChannels * kTile2 * sizeof(float);
 
 struct FilterRegs2 {
   Quat<f32x2> x, xlo;
@@ -376,7 +380,7 @@ __global__ void __launch_bounds__(kThreads2, (LPF && COMP) ? (PKF_MIN_CTAS2 > 6 
   extern __shared__ __align__(128) unsigned char smem_raw[];
   Tma2Smem& sm = *reinterpret_cast<Tma2Smem*>(smem_raw);
   const int tid = threadIdx.x;
-  const int64_t n0 = (int64_t)blockIdx.x * kThreads;
+  const int64_t n0 = (int64_t)blockIdx.x * kTile2;
   const int64_t n = n0 + 2 * tid;                  // this thread owns filters n and n + 1 (N is even)
   const bool valid = n < p.N;
   const int col0 = (int)((p.Ns == p.N) ? n0 : (n0 % p.Ns));
@@ -1045,6 +1049,7 @@ template <int ALGO, bool LPF, bool AUX, bool COMP> int launch_replay(const Repla
 bool packed_eligible(const ReplayParams& p) {
   // float2 accesses to the [k][N] state / constant arrays need N even and 8-byte aligned bases
   if ((p.N & 1) != 0) return false;
+  if (p.Ns != p.N && (p.Ns % kTile2) != 0) return false;      // a CTA's columns must not wrap
   const void* ptrs[] = {p.acc_ref, p.mag_ref, p.q_scale, p.r_scale, p.state_x, p.state_x_lo, p.state_p, p.state_lpf};
   for (const void* q : ptrs) if ((reinterpret_cast<uintptr_t>(q) & 7) != 0) return false;
   if ((reinterpret_cast<uintptr_t>(p.loss_acc) & 7) != 0 || (reinterpret_cast<uintptr_t>(p.out_flip) & 1) != 0) return false;
@@ -1057,7 +1062,7 @@ template <bool LPF, bool AUX, bool COMP> int launch_replay_packed(const ReplayPa
   CUtensorMap tmap;
   const cuuint64_t dims[3] = {(cuuint64_t)p.Ns, (cuuint64_t)kChannels, (cuuint64_t)p.T};
   const cuuint64_t strides[2] = {(cuuint64_t)p.Ns * sizeof(float), (cuuint64_t)p.Ns * kChannels * sizeof(float)};
-  const cuuint32_t box[3] = {(cuuint32_t)kThreads, (cuuint32_t)kChannels, (cuuint32_t)kTma2Steps};
+  const cuuint32_t box[3] = {(cuuint32_t)kTile2, (cuuint32_t)kChannels, (cuuint32_t)kTma2Steps};
   const cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(p.streams), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -1065,7 +1070,7 @@ template <bool LPF, bool AUX, bool COMP> int launch_replay_packed(const ReplayPa
   if (r != CUDA_SUCCESS) return POSEKF_EALIGN;
   auto kern = replay_tma2_kernel<LPF, AUX, COMP>;
   PKF_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Tma2Smem)));
-  const unsigned grid = (unsigned)((p.N + kThreads - 1) / kThreads);
+  const unsigned grid = (unsigned)((p.N + kTile2 - 1) / kTile2);
   kern<<<grid, kThreads2, sizeof(Tma2Smem), st>>>(p, tmap);
   return launch_status();
 }
