@@ -10,8 +10,9 @@ import sys
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "libposekf_b200.so")
-SOURCES = [os.path.join(CSRC, "posekf_kernels.cu")]
-DEPENDS = SOURCES + [os.path.join(CSRC, "ekf_math.cuh"), os.path.join(PKG_DIR, "..", "include", "posekf.h")]
+SOURCES = [os.path.join(CSRC, "posekf_capi.cu")]
+DEPENDS = SOURCES + [os.path.join(CSRC, f) for f in ("ekf_math.cuh", "device_util.cuh", "replay_kernels.cuh", "ops_kernels.cuh")] + [
+    os.path.join(PKG_DIR, "..", "include", "posekf.h")]
 
 # -fmad=false: only the explicit fma_() calls of ekf_math.cuh fuse.  The scalar kernels, the packed (f32x2
 # intrinsics, never contracted) kernels and the g++ -ffp-contract=off host build then execute the same

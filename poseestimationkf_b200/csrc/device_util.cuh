@@ -1,0 +1,100 @@
+// device_util.cuh -- tunables and small device helpers (streaming loads/stores, mbarrier, TMA).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "ekf_math.cuh"
+
+namespace pkf_dev {
+using namespace pkf;
+
+// tunables (overridable with -D for experiments; the defaults are what ships)
+#ifndef PKF_TMA_STEPS
+#define PKF_TMA_STEPS 4
+#endif
+#ifndef PKF_TMA_STAGES
+#define PKF_TMA_STAGES 2
+#endif
+#ifndef PKF_MIN_CTAS
+#define PKF_MIN_CTAS 6
+#endif
+constexpr int kThreads = 128;                  // filters per CTA (4 warps)
+constexpr int kMinCtasPerSm = PKF_MIN_CTAS;    // 6 CTAs/SM (24 warps) <=> <=80 registers per thread
+constexpr int kTmaSteps = PKF_TMA_STEPS;       // TC: timesteps per TMA tile
+constexpr int kTmaStages = PKF_TMA_STAGES;     // ring depth
+constexpr int kChannels = 9;
+// packed (two filters per thread) variant
+#ifndef PKF_TMA2_STEPS
+#define PKF_TMA2_STEPS 4
+#endif
+#ifndef PKF_TMA2_STAGES
+#define PKF_TMA2_STAGES 2
+#endif
+#ifndef PKF_MIN_CTAS2
+#define PKF_MIN_CTAS2 6
+#endif
+#ifndef PKF_THREADS2
+#define PKF_THREADS2 64
+#endif
+constexpr int kThreads2 = PKF_THREADS2;        // threads per CTA of the packed kernel
+constexpr int kTile2 = 2 * kThreads2;          // filters per CTA (two per thread); TMA box width, <= 256
+constexpr int kTma2Steps = PKF_TMA2_STEPS;
+constexpr int kTma2Stages = PKF_TMA2_STAGES;
+#ifndef PKF_AUTO_PACKED
+#define PKF_AUTO_PACKED 1
+#endif
+constexpr bool kAutoPrefersPacked = PKF_AUTO_PACKED != 0;   // whether POSEKF_STAGE_AUTO picks the packed kernel
+
+// ---------------------------------------------------------------------------------------------
+// small device helpers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float ldg_stream(const float* p) {
+  // streamed once: read-only path, do not keep in L1
+  float v;
+  asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ void stg_stream(float* p, float v) {
+  asm volatile("st.global.cs.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
+}
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+
+__device__ __forceinline__ f32x2 ld2(const float* p) {
+  const float2 v = *reinterpret_cast<const float2*>(p);
+  return f32x2(v.x, v.y);
+}
+__device__ __forceinline__ void st2(float* p, const f32x2& v) { *reinterpret_cast<float2*>(p) = make_float2(v.x, v.y); }
+
+}  // namespace pkf_dev

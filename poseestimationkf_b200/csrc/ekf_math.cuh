@@ -1,7 +1,7 @@
 // ekf_math.cuh -- per-filter arithmetic of the quaternion EKF step, register resident.
 //
 // Everything here is a __host__ __device__ template over the scalar type F so that the *same*
-// source is (a) instantiated with F=float inside the sm_100a kernels (posekf_kernels.cu) and
+// source is (a) instantiated with F=float inside the sm_100a kernels (replay_kernels.cuh, ops_kernels.cuh) and
 // (b) compiled by g++ with F=float / F=double in tests/hostsim (a CPU-only numerics probe used while
 // developing without a GPU; it is a test tool, never a product path).
 //

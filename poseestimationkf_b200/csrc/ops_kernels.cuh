@@ -1,0 +1,501 @@
+// ops_kernels.cuh -- stand-alone operators with the reference's per-function semantics (Wahba, rot2quat,
+// Prediction, Correction, RK4, Jacobians, Comparator, low-pass, RPY, norm), the comparison tracks,
+// the raw-sensor pre-processing, and the measurement / host-replay helper kernels.
+#pragma once
+#include "device_util.cuh"
+
+namespace pkf_dev {
+
+// ---------------------------------------------------------------------------------------------
+// Stand-alone Wahba (config "Wahba-only batched 3x3 SVD + R->quat").
+// The Jacobi variant runs sweeps until every lane of the warp has converged (warp vote), at most
+// `max_sweeps`.
+// ---------------------------------------------------------------------------------------------
+struct WahbaParams {
+  int64_t N;
+  const float *acc_ref, *mag_ref;
+  int ref_shared;
+  const float *acc, *mag, *k_acc, *k_mag;
+  float k_acc_s, k_mag_s;
+  int weights_from_acc;
+  float *out_rot, *out_quat;
+  int max_sweeps;
+};
+
+template <int ALGO> __global__ void __launch_bounds__(256) wahba_kernel(const WahbaParams p) {
+  const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool valid = n < p.N;
+  const int64_t i = valid ? n : 0;   // tail lanes recompute element 0 so the warp vote stays full
+  const int64_t N = p.N;
+  Vec3<float> ra, rm;
+  if (p.ref_shared) {
+    ra = {__ldg(p.acc_ref), __ldg(p.acc_ref + 1), __ldg(p.acc_ref + 2)};
+    rm = {__ldg(p.mag_ref), __ldg(p.mag_ref + 1), __ldg(p.mag_ref + 2)};
+  } else {
+    ra = {ldg_stream(p.acc_ref + i), ldg_stream(p.acc_ref + N + i), ldg_stream(p.acc_ref + 2 * N + i)};
+    rm = {ldg_stream(p.mag_ref + i), ldg_stream(p.mag_ref + N + i), ldg_stream(p.mag_ref + 2 * N + i)};
+  }
+  Vec3<float> a = {ldg_stream(p.acc + i), ldg_stream(p.acc + N + i), ldg_stream(p.acc + 2 * N + i)};
+  Vec3<float> m = {ldg_stream(p.mag + i), ldg_stream(p.mag + N + i), ldg_stream(p.mag + 2 * N + i)};
+  float ka, km;
+  if (p.k_acc) { ka = ldg_stream(p.k_acc + i); km = ldg_stream(p.k_mag + i); }
+  else if (p.weights_from_acc) { ka = fabsf(a.z); km = 1.f - ka; }           // PKF/ExtendedKalmanFilter.py:71
+  else { ka = p.k_acc_s; km = p.k_mag_s; }
+  Mat3<float> R;
+  if (ALGO == WAHBA_QR2) {
+    R = wahba_qr2<float>(frame_from_pair<float>(ra, rm), a, m, ka, km);
+  } else {
+    Vec3<float> g0, g1, g2;
+    wahba_form_b<float>(ra, rm, a, m, ka, km, g0, g1, g2);
+    Vec3<float> v0 = {1.f, 0.f, 0.f}, v1 = {0.f, 1.f, 0.f}, v2 = {0.f, 0.f, 1.f};
+    for (int s = 0; s < p.max_sweeps; ++s) {
+      jacobi_pair(g0, g1, v0, v1);
+      jacobi_pair(g0, g2, v0, v2);
+      jacobi_pair(g1, g2, v1, v2);
+      // converged when every pairwise column dot product is below eps * (largest column norm)^2
+      float nmax = fmaxf(dot3(g0, g0), fmaxf(dot3(g1, g1), dot3(g2, g2)));
+      bool more = jacobi_offdiag(g0, g1, g2) > 6e-8f * nmax;
+      if (!__any_sync(0xffffffffu, more)) break;
+    }
+    R = rotation_from_svd_pairs<float>(g0, g1, g2, v0, v1, v2);
+  }
+  if (!valid) return;
+  if (p.out_rot) {
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int c = 0; c < 3; ++c) stg_stream(p.out_rot + (3 * r + c) * N + n, R.m[r][c]);
+  }
+  if (p.out_quat) {
+    Quat<float> q = rotation_to_quat_ref<float>(R);
+    stg_stream(p.out_quat + n, q.w); stg_stream(p.out_quat + N + n, q.x);
+    stg_stream(p.out_quat + 2 * N + n, q.y); stg_stream(p.out_quat + 3 * N + n, q.z);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Comparison tracks of the tuning workflow (what Results/*.png overlays): the gyro-only attitude
+// (RK4 without correction: SRV/KalmanFilter.cpp:149, `Quarternion_Gyro_pure`) and the Wahba-only
+// attitude per sample (PKF/main_file.py:40: getQuarternion(acc, mag, .5, .5), raw sign convention).
+// ---------------------------------------------------------------------------------------------
+struct TracksParams {
+  int64_t N, T, Ns;
+  const float *streams, *dt;
+  int dt_per_step;
+  const float *acc_ref, *mag_ref;
+  float k_acc, k_mag;
+  int weights_from_acc;
+  float* gyro_state;   // [4][N] in/out, or null
+  float* out_gyro;     // [T][N][4] or null
+  float* out_wahba;    // [T][N][4] or null
+};
+
+template <int ALGO> __global__ void __launch_bounds__(128) tracks_kernel(const TracksParams p) {
+  const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= p.N) return;
+  const int64_t N = p.N, Ns = p.Ns, col = (Ns == N) ? n : (n % Ns);
+  Vec3<float> ra = {p.acc_ref[col], p.acc_ref[Ns + col], p.acc_ref[2 * Ns + col]};
+  Vec3<float> rm = {p.mag_ref[col], p.mag_ref[Ns + col], p.mag_ref[2 * Ns + col]};
+  const RefFrame<float> E = frame_from_pair<float>(ra, rm);
+  Quat<float> g = {1.f, 0.f, 0.f, 0.f};
+  if (p.gyro_state) g = {p.gyro_state[n], p.gyro_state[N + n], p.gyro_state[2 * N + n], p.gyro_state[3 * N + n]};
+  const float* s = p.streams + col;
+  float4* og = p.out_gyro ? reinterpret_cast<float4*>(p.out_gyro) + n : nullptr;
+  float4* ow = p.out_wahba ? reinterpret_cast<float4*>(p.out_wahba) + n : nullptr;
+  const float dt0 = p.dt[0];
+  for (int64_t t = 0; t < p.T; ++t, s += kChannels * Ns) {
+    const float h = p.dt_per_step ? __ldg(p.dt + t) : dt0;
+    if (og || p.gyro_state) {
+      Vec3<float> hw = {0.5f * ldg_stream(s), 0.5f * ldg_stream(s + Ns), 0.5f * ldg_stream(s + 2 * Ns)};
+      g = rk4_step<float>(g, hw, h);
+      if (og) { *og = make_float4(g.w, g.x, g.y, g.z); og += N; }
+    }
+    if (ow) {
+      Vec3<float> a = {ldg_stream(s + 3 * Ns), ldg_stream(s + 4 * Ns), ldg_stream(s + 5 * Ns)};
+      Vec3<float> m = {ldg_stream(s + 6 * Ns), ldg_stream(s + 7 * Ns), ldg_stream(s + 8 * Ns)};
+      float ka = p.k_acc, km = p.k_mag;
+      if (p.weights_from_acc) { ka = fabsf(a.z); km = 1.f - ka; }
+      Mat3<float> R = (ALGO == WAHBA_QR2) ? wahba_qr2<float>(E, a, m, ka, km) : wahba_jacobi<float>(ra, rm, a, m, ka, km, 6);
+      Quat<float> q = rotation_to_quat_ref<float>(R);
+      *ow = make_float4(q.w, q.x, q.y, q.z);
+      ow += N;
+    }
+  }
+  if (p.gyro_state) { p.gyro_state[n] = g.w; p.gyro_state[N + n] = g.x; p.gyro_state[2 * N + n] = g.y; p.gyro_state[3 * N + n] = g.z; }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Raw-sensor pre-processing of the online pipeline (the step in front of the filter): linear
+// interpolation of the accel / mag samples that bracket the gyro timestamp, normalisation, and the
+// optional alpha low-pass -- SRV/Parser.cpp:229-267 (ExecuteKalmanFilter, LinearInterpolationSensor),
+// :221-228 (NormalizeValues), SRV/KalmanFilter.cpp:279-303 (low-pass inside Set*Measurements).
+// Writes the [T][9][N] stream the replay kernel consumes.
+// ---------------------------------------------------------------------------------------------
+struct PreprocessParams {
+  int64_t N, T;
+  const float* gyro;        // [T][3][N]
+  const float* raw_prev;    // [T][6][N]  acc xyz, mag xyz : sample before the gyro timestamp (y1)
+  const float* raw_next;    // [T][6][N]  sample after (y2)
+  const float* tspan;       // [T][4][N]  seconds: acc (t2-t1), acc (t3-t1), mag (t2-t1), mag (t3-t1)
+  float alpha_acc, alpha_mag;
+  float* lpf_state;         // [6][N] in/out or null
+  float* out_streams;       // [T][9][N]
+};
+
+__global__ void __launch_bounds__(256) preprocess_kernel(const PreprocessParams p) {
+  const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= p.N) return;
+  const int64_t N = p.N;
+  const bool lpa = p.alpha_acc >= 0.f, lpm = p.alpha_mag >= 0.f;
+  Vec3<float> la = {0.f, 0.f, 0.f}, lm = {0.f, 0.f, 0.f};
+  if (p.lpf_state) {
+    la = {p.lpf_state[n], p.lpf_state[N + n], p.lpf_state[2 * N + n]};
+    lm = {p.lpf_state[3 * N + n], p.lpf_state[4 * N + n], p.lpf_state[5 * N + n]};
+  }
+  for (int64_t t = 0; t < p.T; ++t) {
+    const float* y1 = p.raw_prev + t * 6 * N + n;
+    const float* y2 = p.raw_next + t * 6 * N + n;
+    const float* ts = p.tspan + t * 4 * N + n;
+    float* o = p.out_streams + t * 9 * N + n;
+    const float* g = p.gyro + t * 3 * N + n;
+    o[0] = ldg_stream(g); o[N] = ldg_stream(g + N); o[2 * N] = ldg_stream(g + 2 * N);
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {                      // s = 0 accel, 1 mag
+      const float t21 = ldg_stream(ts + (2 * s) * N), t31 = ldg_stream(ts + (2 * s + 1) * N);
+      float v[3];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const float a = ldg_stream(y1 + (3 * s + c) * N), b = ldg_stream(y2 + (3 * s + c) * N);
+        v[c] = (b - a) / t21 * t31 + a;                // Parser.cpp:264, same operation order
+      }
+      const float den = sqrtf(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);     // Parser.cpp:223-227
+      Vec3<float> u = {v[0] / den, v[1] / den, v[2] / den};
+      if (s == 0 && lpa) { lowpass<float>(la, u, p.alpha_acc, 1.f - p.alpha_acc); u = la; }
+      if (s == 1 && lpm) { lowpass<float>(lm, u, p.alpha_mag, 1.f - p.alpha_mag); u = lm; }
+      o[(3 + 3 * s) * N] = u.x; o[(4 + 3 * s) * N] = u.y; o[(5 + 3 * s) * N] = u.z;
+    }
+  }
+  if (p.lpf_state) {
+    p.lpf_state[n] = la.x; p.lpf_state[N + n] = la.y; p.lpf_state[2 * N + n] = la.z;
+    p.lpf_state[3 * N + n] = lm.x; p.lpf_state[4 * N + n] = lm.y; p.lpf_state[5 * N + n] = lm.z;
+  }
+}
+
+// trajectory [M][4] -> roll/pitch/yaw degrees [M][3]   (PKF/UtilityFunctions.py:3-14 per row)
+__global__ void __launch_bounds__(256) traj2rpy_kernel(int64_t M, const float4* __restrict__ q, float* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= M) return;
+  const float4 v = q[i];
+  const float w = v.x, x = v.y, y = v.z, z = v.w, k = 57.29577951308232f;
+  out[3 * i] = atan2f(2.f * (w * x + y * z), 1.f - 2.f * (x * x + y * y)) * k;
+  out[3 * i + 1] = asinf(2.f * (w * y - z * x)) * k;
+  out[3 * i + 2] = atan2f(2.f * (w * z + x * y), 1.f - 2.f * (y * y + z * z)) * k;
+}
+
+// Packed form of the rank-2 Wahba kernel: two solves per thread in f32x2 lanes (N even, per-pair or
+// shared references).  Same arithmetic per solve as wahba_kernel<WAHBA_QR2>.
+__global__ void __launch_bounds__(256) wahba2_kernel(const WahbaParams p) {
+  const int64_t n = 2 * ((int64_t)blockIdx.x * blockDim.x + threadIdx.x);
+  if (n >= p.N) return;
+  const int64_t N = p.N;
+  Vec3<f32x2> ra, rm;
+  if (p.ref_shared) {
+    ra = {f32x2(__ldg(p.acc_ref)), f32x2(__ldg(p.acc_ref + 1)), f32x2(__ldg(p.acc_ref + 2))};
+    rm = {f32x2(__ldg(p.mag_ref)), f32x2(__ldg(p.mag_ref + 1)), f32x2(__ldg(p.mag_ref + 2))};
+  } else {
+    ra = {ld2(p.acc_ref + n), ld2(p.acc_ref + N + n), ld2(p.acc_ref + 2 * N + n)};
+    rm = {ld2(p.mag_ref + n), ld2(p.mag_ref + N + n), ld2(p.mag_ref + 2 * N + n)};
+  }
+  auto ld2s = [](const float* q) {
+    float2 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(q));
+    return f32x2(v.x, v.y);
+  };
+  Vec3<f32x2> a = {ld2s(p.acc + n), ld2s(p.acc + N + n), ld2s(p.acc + 2 * N + n)};
+  Vec3<f32x2> m = {ld2s(p.mag + n), ld2s(p.mag + N + n), ld2s(p.mag + 2 * N + n)};
+  f32x2 ka, km;
+  if (p.k_acc) { ka = ld2s(p.k_acc + n); km = ld2s(p.k_mag + n); }
+  else if (p.weights_from_acc) { ka = abs_<f32x2>(a.z); km = f32x2(1.f) - ka; }
+  else { ka = f32x2(p.k_acc_s); km = f32x2(p.k_mag_s); }
+  const Mat3<f32x2> R = wahba_qr2<f32x2>(frame_from_pair<f32x2>(ra, rm), a, m, ka, km);
+  auto st2s = [](float* q, const f32x2& v) { asm volatile("st.global.cs.v2.f32 [%0], {%1, %2};" ::"l"(q), "f"(v.x), "f"(v.y) : "memory"); };
+  if (p.out_rot) {
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int c = 0; c < 3; ++c) st2s(p.out_rot + (3 * r + c) * N + n, R.m[r][c]);
+  }
+  if (p.out_quat) {
+    const Quat<f32x2> q = rotation_to_quat_ref<f32x2>(R);
+    st2s(p.out_quat + n, q.w); st2s(p.out_quat + N + n, q.x); st2s(p.out_quat + 2 * N + n, q.y); st2s(p.out_quat + 3 * N + n, q.z);
+  }
+}
+
+__global__ void __launch_bounds__(256) rot2quat_kernel(int64_t N, const float* __restrict__ rot, float* __restrict__ out) {
+  const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  Mat3<float> R;
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+#pragma unroll
+    for (int c = 0; c < 3; ++c) R.m[r][c] = rot[(3 * r + c) * N + n];
+  Quat<float> q = rotation_to_quat_ref<float>(R);
+  out[n] = q.w; out[N + n] = q.x; out[2 * N + n] = q.y; out[3 * N + n] = q.z;
+}
+
+// ---------------------------------------------------------------------------------------------
+// General Prediction / Correction (full matrices, exactly the reference's operations).
+// ---------------------------------------------------------------------------------------------
+struct PredictParams {
+  int64_t N;
+  const float *gyro, *dt;
+  int dt_shared;
+  const float *x, *p, *q_mat, *r_mat, *q_scale, *r_scale;
+  float *out_z, *out_p, *out_k;
+};
+
+__global__ void __launch_bounds__(128) predict_kernel(const PredictParams a) {
+  const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= a.N) return;
+  const int64_t N = a.N;
+  Vec3<float> w = {a.gyro[n], a.gyro[N + n], a.gyro[2 * N + n]};
+  Quat<float> x = {a.x[n], a.x[N + n], a.x[2 * N + n], a.x[3 * N + n]};
+  Mat4<float> P, A, AP, S, Si;
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) P.m[i][j] = a.p[(4 * i + j) * N + n];
+  half_omega<float>(w, A);                                      // GetJacobian_A  :43-48
+  // GetJacobian_B(x)  :51-56
+  const float B[4][3] = {{-0.5f * x.x, -0.5f * x.y, -0.5f * x.z},
+                         {0.5f * x.w, 0.5f * x.z, -0.5f * x.y},
+                         {-0.5f * x.z, 0.5f * x.w, 0.5f * x.x},
+                         {0.5f * x.y, -0.5f * x.x, 0.5f * x.w}};
+  const float qs = a.q_scale ? a.q_scale[n] : 1.f, rs = a.r_scale ? a.r_scale[n] : 1.f;
+  float BQ[4][3];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      float acc = 0.f;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) acc = fmaf(B[i][k], qs * __ldg(a.q_mat + 3 * k + j), acc);
+      BQ[i][j] = acc;
+    }
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float acc = 0.f;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) acc = fmaf(A.m[i][k], P.m[k][j], acc);
+      AP.m[i][j] = acc;
+    }
+  Mat4<float> Pn;                                               // P = A P A^T + B Q B^T   :61
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float acc = 0.f;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) acc = fmaf(AP.m[i][k], A.m[j][k], acc);
+#pragma unroll
+      for (int k = 0; k < 3; ++k) acc = fmaf(BQ[i][k], B[j][k], acc);
+      Pn.m[i][j] = acc;
+      S.m[i][j] = acc + rs * __ldg(a.r_mat + 4 * i + j);        // S = P + R   :63
+    }
+  const float h = a.dt_shared ? a.dt[0] : a.dt[n];
+  Vec3<float> hw = {0.5f * w.x, 0.5f * w.y, 0.5f * w.z};
+  Quat<float> z = rk4_step<float>(x, hw, h);                    // :62
+  inverse4<float>(S, Si);                                       // :65
+  a.out_z[n] = z.w; a.out_z[N + n] = z.x; a.out_z[2 * N + n] = z.y; a.out_z[3 * N + n] = z.z;
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float acc = 0.f;                                          // K = P S^-1   :66
+#pragma unroll
+      for (int k = 0; k < 4; ++k) acc = fmaf(Pn.m[i][k], Si.m[k][j], acc);
+      a.out_k[(4 * i + j) * N + n] = acc;
+      a.out_p[(4 * i + j) * N + n] = Pn.m[i][j];
+    }
+}
+
+struct CorrectParams {
+  int64_t N;
+  const float *mag, *acc, *acc_ref, *mag_ref;
+  int ref_shared;
+  const float *z, *p, *k;
+  float *out_x, *out_p;
+  uint8_t* out_flip;
+  float* out_meas;
+};
+
+template <int ALGO> __global__ void __launch_bounds__(128) correct_kernel(const CorrectParams a) {
+  const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= a.N) return;
+  const int64_t N = a.N;
+  Vec3<float> ra, rm;
+  if (a.ref_shared) {
+    ra = {a.acc_ref[0], a.acc_ref[1], a.acc_ref[2]};
+    rm = {a.mag_ref[0], a.mag_ref[1], a.mag_ref[2]};
+  } else {
+    ra = {a.acc_ref[n], a.acc_ref[N + n], a.acc_ref[2 * N + n]};
+    rm = {a.mag_ref[n], a.mag_ref[N + n], a.mag_ref[2 * N + n]};
+  }
+  Vec3<float> ac = {a.acc[n], a.acc[N + n], a.acc[2 * N + n]};
+  Vec3<float> mg = {a.mag[n], a.mag[N + n], a.mag[2 * N + n]};
+  Quat<float> z = {a.z[n], a.z[N + n], a.z[2 * N + n], a.z[3 * N + n]};
+  const float ka = fabsf(ac.z), km = 1.f - ka;                                     // :71
+  Mat3<float> R = (ALGO == WAHBA_QR2) ? wahba_qr2<float>(frame_from_pair<float>(ra, rm), ac, mg, ka, km)
+                                      : wahba_jacobi<float>(ra, rm, ac, mg, ka, km, 6);
+  Quat<float> y = rotation_to_quat_ref<float>(R);
+  const bool flip = dot4(y, z) < 0.f;                                              // :73-74 (Comparator[0] == dot)
+  if (flip) { y.w = -y.w; y.x = -y.x; y.y = -y.y; y.z = -y.z; }
+  const float e[4] = {y.w - z.w, y.x - z.x, y.y - z.y, y.z - z.z};                 // :76
+  float K[4][4], P[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { K[i][j] = a.k[(4 * i + j) * N + n]; P[i][j] = a.p[(4 * i + j) * N + n]; }
+  const float zz[4] = {z.w, z.x, z.y, z.z};
+  float X[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float acc = zz[i];                                                             // X = z + K e   :77
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc = fmaf(K[i][j], e[j], acc);
+    X[i] = acc;
+  }
+  const float inv = rsqrtf(fmaf(X[3], X[3], fmaf(X[2], X[2], fmaf(X[1], X[1], X[0] * X[0]))));
+#pragma unroll
+  for (int i = 0; i < 4; ++i) a.out_x[i * N + n] = X[i] * inv;                     // :79
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float acc = P[i][j];                                                         // P = P - K P   :78
+#pragma unroll
+      for (int k = 0; k < 4; ++k) acc = fmaf(-K[i][k], P[k][j], acc);
+      a.out_p[(4 * i + j) * N + n] = acc;
+    }
+  if (a.out_flip) a.out_flip[n] = flip ? 1 : 0;
+  if (a.out_meas) { a.out_meas[n] = y.w; a.out_meas[N + n] = y.x; a.out_meas[2 * N + n] = y.y; a.out_meas[3 * N + n] = y.z; }
+}
+
+__global__ void __launch_bounds__(256)
+    rk4_kernel(int64_t N, const float* q, const float* dt, int dt_shared, const float* w, float* out) {
+  const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  Quat<float> x = {q[n], q[N + n], q[2 * N + n], q[3 * N + n]};
+  Vec3<float> hw = {0.5f * w[n], 0.5f * w[N + n], 0.5f * w[2 * N + n]};
+  Quat<float> z = rk4_step<float>(x, hw, dt_shared ? dt[0] : dt[n]);
+  out[n] = z.w; out[N + n] = z.x; out[2 * N + n] = z.y; out[3 * N + n] = z.z;
+}
+
+__global__ void __launch_bounds__(256)
+    jacobians_kernel(int64_t N, const float* w, float* out_a, const float* q, float* out_b) {
+  const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  if (w && out_a) {
+    Mat4<float> A;
+    half_omega<float>({w[n], w[N + n], w[2 * N + n]}, A);
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) out_a[(4 * i + j) * N + n] = A.m[i][j];
+  }
+  if (q && out_b) {
+    const float q0 = 0.5f * q[n], q1 = 0.5f * q[N + n], q2 = 0.5f * q[2 * N + n], q3 = 0.5f * q[3 * N + n];
+    const float B[12] = {-q1, -q2, -q3, q0, q3, -q2, -q3, q0, q1, q2, -q1, q0};
+#pragma unroll
+    for (int i = 0; i < 12; ++i) out_b[i * N + n] = B[i];
+  }
+}
+
+__global__ void __launch_bounds__(256) comparator_kernel(int64_t N, const float* q1, const float* q2, float* out) {
+  const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  // conj(q1) (x) q2, written as the reference's 4x4 mat-vec (PKF/ExtendedKalmanFilter.py:17-23)
+  const float c0 = q1[n], c1 = -q1[N + n], c2 = -q1[2 * N + n], c3 = -q1[3 * N + n];
+  const float b0 = q2[n], b1 = q2[N + n], b2 = q2[2 * N + n], b3 = q2[3 * N + n];
+  out[n] = fmaf(-c3, b3, fmaf(-c2, b2, fmaf(-c1, b1, c0 * b0)));
+  out[N + n] = fmaf(c2, b3, fmaf(-c3, b2, fmaf(c0, b1, c1 * b0)));
+  out[2 * N + n] = fmaf(-c1, b3, fmaf(c0, b2, fmaf(c3, b1, c2 * b0)));
+  out[3 * N + n] = fmaf(c0, b3, fmaf(c1, b2, fmaf(-c2, b1, c3 * b0)));
+}
+
+__global__ void __launch_bounds__(256)
+    lowpass_kernel(int64_t N, int64_t T, const float* x, float alpha, float* state, float* out) {
+  const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  Vec3<float> y = {state[n], state[N + n], state[2 * N + n]};
+  const float oma = 1.f - alpha;
+  for (int64_t t = 0; t < T; ++t) {
+    const float* xi = x + t * 3 * N + n;
+    Vec3<float> v = {ldg_stream(xi), ldg_stream(xi + N), ldg_stream(xi + 2 * N)};
+    lowpass<float>(y, v, alpha, oma);
+    float* o = out + t * 3 * N + n;
+    o[0] = y.x; o[N] = y.y; o[2 * N] = y.z;
+  }
+  state[n] = y.x; state[N + n] = y.y; state[2 * N + n] = y.z;
+}
+
+__global__ void __launch_bounds__(256) quat2rpy_kernel(int64_t N, const float* q, float* out) {
+  const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  const float w = q[n], x = q[N + n], y = q[2 * N + n], z = q[3 * N + n];
+  const float k = 57.29577951308232f;
+  out[n] = atan2f(2.f * (w * x + y * z), 1.f - 2.f * (x * x + y * y)) * k;
+  out[N + n] = asinf(2.f * (w * y - z * x)) * k;
+  out[2 * N + n] = atan2f(2.f * (w * z + x * y), 1.f - 2.f * (y * y + z * z)) * k;
+}
+
+__global__ void __launch_bounds__(256) norm_kernel(int64_t N, int k, const float* v, float* out) {
+  const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  float acc = 0.f;
+  for (int i = 0; i < k; ++i) { const float e = v[(int64_t)i * N + n]; acc = fmaf(e, e, acc); }   // left to right, :18-19
+  out[n] = sqrtf(acc);
+}
+
+// host-replay helpers: initial state and P <-> P/r conversion on the device
+__global__ void __launch_bounds__(256)
+    host_init_state_kernel(int64_t N, int have_x0, int have_p0, const float* __restrict__ r, float* x, float* p) {
+  const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  if (!have_x0) { x[n] = 1.f; x[N + n] = 0.f; x[2 * N + n] = 0.f; x[3 * N + n] = 0.f; }     // PKF/main_file.py:26
+  const float ir = 1.f / r[n];
+#pragma unroll
+  for (int k = 0; k < 10; ++k) {
+    const bool diag = (k == 0 || k == 4 || k == 7 || k == 9);
+    const float p0 = have_p0 ? p[k * N + n] : (diag ? 1.f : 0.f);                            // PKF/main_file.py:23
+    p[k * N + n] = p0 * ir;
+  }
+}
+__global__ void __launch_bounds__(256) host_unscale_p_kernel(int64_t N, const float* __restrict__ r, float* p) {
+  const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  const float rr = r[n];
+#pragma unroll
+  for (int k = 0; k < 10; ++k) p[k * N + n] *= rr;
+}
+
+// FP32 peak probe: 16 independent FFMA chains per thread, all SMs full.
+constexpr int kProbeIters = 8192, kProbeAcc = 16;
+__global__ void __launch_bounds__(256) fp32_probe_kernel(float* out, float b, float c) {
+  float a[kProbeAcc];
+#pragma unroll
+  for (int i = 0; i < kProbeAcc; ++i) a[i] = threadIdx.x * 1e-3f + i;
+  for (int it = 0; it < kProbeIters; ++it) {
+#pragma unroll
+    for (int i = 0; i < kProbeAcc; ++i) a[i] = fmaf(a[i], b, c);
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < kProbeAcc; ++i) s += a[i];
+  out[(int64_t)blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+// ---------------------------------------------------------------------------------------------
+}  // namespace pkf_dev
