@@ -486,7 +486,7 @@ template <typename F> PKF_HD void jacobi_pair(Vec3<F>& gi, Vec3<F>& gj, Vec3<F>&
   vi = ni; vj = nj;
 }
 
-template <typename F> PKF_HD void swap_if(bool c, Vec3<F>& a, Vec3<F>& b) {
+template <typename F, typename M> PKF_HD void swap_if(M c, Vec3<F>& a, Vec3<F>& b) {
   Vec3<F> t = a;
   a.x = sel_(c, b.x, a.x); a.y = sel_(c, b.y, a.y); a.z = sel_(c, b.z, a.z);
   b.x = sel_(c, t.x, b.x); b.y = sel_(c, t.y, b.y); b.z = sel_(c, t.z, b.z);
@@ -503,8 +503,8 @@ template <typename F>
 PKF_HD Mat3<F> rotation_from_svd_pairs(Vec3<F> g0, Vec3<F> g1, Vec3<F> g2, Vec3<F> v0, Vec3<F> v1, Vec3<F> v2) {
   // bring the two largest columns to slots 0,1 (order among them is irrelevant)
   F n0 = dot3(g0, g0), n1 = dot3(g1, g1), n2 = dot3(g2, g2);
-  bool s0 = (n0 < n1) && (n0 < n2);          // column 0 is the smallest -> swap with 2
-  bool s1 = !s0 && (n1 < n2);                // column 1 is the smallest -> swap with 2
+  auto s0 = (n0 < n1) && (n0 < n2);          // column 0 is the smallest -> swap with 2
+  auto s1 = !s0 && (n1 < n2);                // column 1 is the smallest -> swap with 2
   swap_if(s0, g0, g2); swap_if(s0, v0, v2);
   F t = n0; n0 = sel_(s0, n2, n0); n2 = sel_(s0, t, n2);
   swap_if(s1, g1, g2); swap_if(s1, v1, v2);
