@@ -308,7 +308,8 @@ def test_no_out_of_bounds_writes(cuda):
         val = POISON if buf.dtype == torch.float32 else 77
         return bool((buf[:GUARD] == val).all() and (buf[GUARD + n:] == val).all())
 
-    for N, T, staging in ((1000, 37, "tma"), (1000, 37, "ldg"), (130, 9, "auto"), (516, 5, "tma"), (3, 2, "ldg")):
+    for N, T, staging in ((1000, 37, "tma"), (1000, 37, "tma_packed"), (1000, 37, "ldg"), (130, 9, "auto"), (516, 5, "tma"),
+                          (516, 5, "tma_packed"), (4, 1, "tma_packed"), (3, 2, "ldg")):
         imu = make_imu(N, T, seed=N + T, sigma=0.01, device=cuda, keep_truth=True)
         truth = imu.q_true.permute(0, 2, 1).to(torch.float32).contiguous()
         for precise in (False, True):
