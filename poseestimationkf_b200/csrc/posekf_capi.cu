@@ -47,7 +47,8 @@ inline int launch_status() {
   return e == cudaSuccess ? 0 : (int)e;
 }
 
-// host side
+// ---------------------------------------------------------------------------------------------
+// launch logic
 // ---------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -64,6 +65,21 @@ EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
+// Tensor map over the stream [T][9][Ns] (float32) with a box of `columns` filters x 9 channels x `steps`
+// timesteps; out-of-range columns / steps are zero-filled by the TMA unit.
+int encode_stream_map(const ReplayParams& p, int columns, int steps, CUtensorMap* tmap) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) return POSEKF_ENODEV;
+  const cuuint64_t dims[3] = {(cuuint64_t)p.Ns, (cuuint64_t)kChannels, (cuuint64_t)p.T};
+  const cuuint64_t strides[2] = {(cuuint64_t)p.Ns * sizeof(float), (cuuint64_t)p.Ns * kChannels * sizeof(float)};
+  const cuuint32_t box[3] = {(cuuint32_t)columns, (cuuint32_t)kChannels, (cuuint32_t)steps};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(p.streams), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : POSEKF_EALIGN;
+}
+
 bool tma_eligible(const ReplayParams& p) {
   if ((reinterpret_cast<uintptr_t>(p.streams) & 15) != 0) return false;
   if (p.Ns % 4 != 0) return false;                        // global strides must be multiples of 16 bytes
@@ -78,17 +94,8 @@ template <int ALGO, bool LPF, bool AUX, bool COMP> int launch_replay(const Repla
     replay_ldg_kernel<ALGO, LPF, AUX, COMP><<<grid, kThreads, 0, st>>>(p);
     return launch_status();
   }
-  EncodeTiledFn enc = get_encode_fn();
-  if (!enc) return POSEKF_ENODEV;
   CUtensorMap tmap;
-  const cuuint64_t dims[3] = {(cuuint64_t)p.Ns, (cuuint64_t)kChannels, (cuuint64_t)p.T};
-  const cuuint64_t strides[2] = {(cuuint64_t)p.Ns * sizeof(float), (cuuint64_t)p.Ns * kChannels * sizeof(float)};
-  const cuuint32_t box[3] = {(cuuint32_t)kThreads, (cuuint32_t)kChannels, (cuuint32_t)kTmaSteps};
-  const cuuint32_t estr[3] = {1, 1, 1};
-  CUresult r = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(p.streams), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) return POSEKF_EALIGN;
+  if (int rc = encode_stream_map(p, kThreads, kTmaSteps, &tmap)) return rc;
   auto kern = replay_tma_kernel<ALGO, LPF, AUX, COMP>;
   // idempotent; set on every launch (cheap) so that it holds on every device of a multi-GPU process
   PKF_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TmaSmem)));
@@ -107,17 +114,8 @@ bool packed_eligible(const ReplayParams& p) {
 }
 
 template <bool LPF, bool AUX, bool COMP> int launch_replay_packed(const ReplayParams& p, cudaStream_t st) {
-  EncodeTiledFn enc = get_encode_fn();
-  if (!enc) return POSEKF_ENODEV;
   CUtensorMap tmap;
-  const cuuint64_t dims[3] = {(cuuint64_t)p.Ns, (cuuint64_t)kChannels, (cuuint64_t)p.T};
-  const cuuint64_t strides[2] = {(cuuint64_t)p.Ns * sizeof(float), (cuuint64_t)p.Ns * kChannels * sizeof(float)};
-  const cuuint32_t box[3] = {(cuuint32_t)kTile2, (cuuint32_t)kChannels, (cuuint32_t)kTma2Steps};
-  const cuuint32_t estr[3] = {1, 1, 1};
-  CUresult r = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(p.streams), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) return POSEKF_EALIGN;
+  if (int rc = encode_stream_map(p, kTile2, kTma2Steps, &tmap)) return rc;
   auto kern = replay_tma2_kernel<LPF, AUX, COMP>;
   PKF_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Tma2Smem)));
   const unsigned grid = (unsigned)((p.N + kTile2 - 1) / kTile2);
