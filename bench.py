@@ -40,7 +40,7 @@ FLOPS_COMPENSATED_EXTRA = 32      # two-sum folding of the state (ncu: 536 + 10 
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--filters", type=int, default=1 << 20, help="filters per GPU")
