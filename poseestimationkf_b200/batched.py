@@ -127,6 +127,14 @@ def _scalar_tensor(value: float, device) -> torch.Tensor:
     return t
 
 
+def _same_scale(a, b) -> bool:
+    if isinstance(a, torch.Tensor) or isinstance(b, torch.Tensor):
+        if isinstance(a, torch.Tensor) and isinstance(b, torch.Tensor):
+            return a is b or (a.shape == b.shape and bool(torch.equal(a, b)))
+        return False
+    return float(a) == float(b)
+
+
 def _per_filter(v, n, device):
     if isinstance(v, torch.Tensor):
         _require_cuda(v)
@@ -167,6 +175,11 @@ def replay(streams: torch.Tensor, acc_ref: torch.Tensor, mag_ref: torch.Tensor, 
         raise ValueError("r must be > 0 (the kernel carries the covariance in units of r)")
     if state is None:
         state = ReplayState.initial(N, dev, r=r, with_lpf=use_lpf)
+    elif not _same_scale(state.r, r):
+        # the covariance is stored in units of the r it was created with: re-express it in units of the new r
+        old = state.r if isinstance(state.r, torch.Tensor) else float(state.r)
+        new = r if isinstance(r, torch.Tensor) else float(r)
+        state.p.mul_(old / new)
     state.r = r
     if precise_state is None:
         precise_state = (state.x_lo is not None or isinstance(q, torch.Tensor) or isinstance(r, torch.Tensor)

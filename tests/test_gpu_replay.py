@@ -365,3 +365,13 @@ def test_packed_kernel_bitwise_equals_scalar(cuda):
     a, _, _ = B.replay(imu.streams, imu.acc_ref, imu.mag_ref, dt=imu.dt, q=qs, r=rs, n_filters=1024, staging="tma")
     b, _, _ = B.replay(imu.streams, imu.acc_ref, imu.mag_ref, dt=imu.dt, q=qs, r=rs, n_filters=1024, staging="tma_packed")
     assert torch.equal(a.x, b.x) and torch.equal(a.x_lo, b.x_lo)
+
+
+def test_state_created_with_another_r_is_rescaled(cuda):
+    # ReplayState stores P/r; a state made for one r and replayed with another must keep the same P
+    imu = make_imu(512, 30, seed=3, sigma=0.01, device=cuda)
+    a, _, _ = B.replay(imu.streams, imu.acc_ref, imu.mag_ref, dt=imu.dt, q=2.0, r=0.5, precise_state=False)
+    st = B.ReplayState.initial(512, cuda)                    # created with the default r = 0.1
+    B.replay(imu.streams, imu.acc_ref, imu.mag_ref, dt=imu.dt, q=2.0, r=0.5, state=st, precise_state=False)
+    assert torch.equal(a.x, st.x) and torch.equal(a.p, st.p)
+    torch.testing.assert_close(st.covariance(), a.covariance())
