@@ -165,6 +165,13 @@ int posekf_preprocess_f32(int64_t n_filters, int64_t n_steps, const float* gyro,
                           const float* raw_next, const float* tspan, float lpf_alpha_acc, float lpf_alpha_mag,
                           float* lpf_state, float* out_streams, void* stream);
 
+/* Initial reference vectors of the online pipeline: mean and (optionally) unbiased variance of the first K
+ * samples of a sensor for N recordings; normalize != 0 divides the mean by its norm, which is how acc_0 / mag_0
+ * are produced (SRV/InitialValues.cpp:19-66, SRV/Parser.cpp:46-49; K = 100 there, SRV/Parser.cpp:5-7).
+ *   samples [K][3][N] -> out_mean [3][N], out_var [3][N] or NULL (variance of the raw samples, K >= 2). */
+int posekf_initial_values_f32(int64_t n_filters, int64_t n_samples, const float* samples, int normalize, float* out_mean,
+                              float* out_var, void* stream);
+
 /* Quart2RPY over a stored trajectory: traj [M][4] (e.g. out_traj with M = T*N) -> degrees [M][3].
  * PKF/UtilityFunctions.py:3-14; C++ twin SRV/KalmanFilter.cpp:194-233 (which clamps asin; this does not,
  * like the Python oracle). */

@@ -25,6 +25,7 @@ _SIGNATURES = {
     "posekf_wahba_f32": [_i64, _vp, _vp, _int, _vp, _vp, _vp, _vp, _f32, _f32, _int, _vp, _vp, _int, _int, _vp],
     "posekf_tracks_f32": [_i64, _i64, _vp, _i64, _vp, _int, _vp, _vp, _f32, _f32, _int, _vp, _vp, _vp, _int, _vp],
     "posekf_traj2rpy_f32": [_i64, _vp, _vp, _vp],
+    "posekf_initial_values_f32": [_i64, _i64, _vp, _int, _vp, _vp, _vp],
     "posekf_preprocess_f32": [_i64, _i64, _vp, _vp, _vp, _vp, _f32, _f32, _vp, _vp, _vp],
     "posekf_rot2quat_f32": [_i64, _vp, _vp, _vp],
     "posekf_predict_f32": [_i64, _vp, _vp, _int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],

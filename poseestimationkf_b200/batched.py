@@ -349,6 +349,19 @@ def preprocess(gyro, raw_prev, raw_next, tspan, *, lpf_alpha_acc=None, lpf_alpha
     return out, lpf_state
 
 
+def initial_values(samples, *, normalize: bool = True, want_variance: bool = False):
+    """acc_0 / mag_0 of the online pipeline: (normalised) mean of the first K samples, samples [K,3,N] ->
+    (mean [3,N], var [3,N] or None)."""
+    _require_cuda(samples)
+    K, _, N = samples.shape
+    mean = torch.empty((3, N), dtype=torch.float32, device=samples.device)
+    var = torch.empty((3, N), dtype=torch.float32, device=samples.device) if want_variance else None
+    with torch.cuda.device(samples.device):
+        _lib.check(_lib.load().posekf_initial_values_f32(N, K, _ptr(samples), int(normalize), _ptr(mean), _ptr(var), _stream()),
+                   "posekf_initial_values_f32")
+    return mean, var
+
+
 def traj2rpy(traj):
     """Quart2RPY over a stored trajectory [..., 4] -> degrees [..., 3]."""
     _require_cuda(traj)

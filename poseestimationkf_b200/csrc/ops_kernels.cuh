@@ -181,6 +181,39 @@ __global__ void __launch_bounds__(256) preprocess_kernel(const PreprocessParams 
   }
 }
 
+// Initial reference vectors of the online pipeline: mean (and unbiased variance) of the first K samples of a
+// sensor, the mean optionally normalised -- SRV/InitialValues.cpp:19-66 (running sum, two-pass variance with
+// K-1), SRV/Parser.cpp:46-49 (acc0 / mag0 = normalised means).  samples [K][3][N] -> mean [3][N], var [3][N].
+__global__ void __launch_bounds__(256)
+    initial_values_kernel(int64_t N, int64_t K, const float* __restrict__ x, int normalize, float* __restrict__ mean,
+                          float* __restrict__ var) {
+  const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+  for (int64_t k = 0; k < K; ++k) {
+    const float* p = x + k * 3 * N + n;
+    s0 += ldg_stream(p); s1 += ldg_stream(p + N); s2 += ldg_stream(p + 2 * N);
+  }
+  const float ik = 1.f / (float)K;
+  const float m0 = s0 * ik, m1 = s1 * ik, m2 = s2 * ik;
+  if (var) {
+    float v0 = 0.f, v1 = 0.f, v2 = 0.f;
+    for (int64_t k = 0; k < K; ++k) {
+      const float* p = x + k * 3 * N + n;
+      const float d0 = __ldg(p) - m0, d1 = __ldg(p + N) - m1, d2 = __ldg(p + 2 * N) - m2;
+      v0 = fmaf(d0, d0, v0); v1 = fmaf(d1, d1, v1); v2 = fmaf(d2, d2, v2);
+    }
+    const float ik1 = 1.f / (float)(K - 1);
+    var[n] = v0 * ik1; var[N + n] = v1 * ik1; var[2 * N + n] = v2 * ik1;
+  }
+  float o0 = m0, o1 = m1, o2 = m2;
+  if (normalize) {
+    const float den = sqrtf(m0 * m0 + m1 * m1 + m2 * m2);       // Parser.cpp:223-227
+    o0 = m0 / den; o1 = m1 / den; o2 = m2 / den;
+  }
+  mean[n] = o0; mean[N + n] = o1; mean[2 * N + n] = o2;
+}
+
 // trajectory [M][4] -> roll/pitch/yaw degrees [M][3]   (PKF/UtilityFunctions.py:3-14 per row)
 __global__ void __launch_bounds__(256) traj2rpy_kernel(int64_t M, const float4* __restrict__ q, float* __restrict__ out) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;

@@ -410,6 +410,16 @@ int posekf_preprocess_f32(int64_t n_filters, int64_t n_steps, const float* gyro,
   return launch_status();
 }
 
+int posekf_initial_values_f32(int64_t n_filters, int64_t n_samples, const float* samples, int normalize, float* out_mean,
+                              float* out_var, void* stream) {
+  if (n_filters < 0 || n_samples < 1) return POSEKF_EINVAL;
+  if (n_filters == 0) return 0;
+  if (!samples || !out_mean || (out_var && n_samples < 2)) return POSEKF_EINVAL;
+  initial_values_kernel<<<blocks_for(n_filters, 256), 256, 0, (cudaStream_t)stream>>>(n_filters, n_samples, samples, normalize,
+                                                                                        out_mean, out_var);
+  return launch_status();
+}
+
 int posekf_traj2rpy_f32(int64_t m, const float* traj, float* out_rpy_deg, void* stream) {
   if (m < 0) return POSEKF_EINVAL;
   if (m == 0) return 0;

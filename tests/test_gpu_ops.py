@@ -284,3 +284,59 @@ def test_packed_wahba_kernel_bitwise_equals_scalar(golden_wahba, cuda):
     _, qa = B.wahba(ra, rm, acc, mag, weights_from_acc=True)
     _, qb = B.wahba(ra, rm, acc[:, 1:].contiguous(), mag[:, 1:].contiguous(), weights_from_acc=True)
     assert torch.equal(qa[:, 1:], qb)
+
+
+def test_initial_values(cuda):
+    # SRV/InitialValues.cpp: mean of the first 100 samples, unbiased variance; Parser.cpp:46-49 normalises the mean
+    rng = np.random.default_rng(2)
+    x = (rng.normal(size=(100, 3, 500)) * 0.05 + rng.normal(size=(1, 3, 500))).astype(np.float32)
+    mean, var = B.initial_values(_dev(x, cuda), normalize=True, want_variance=True)
+    m = x.astype(np.float64).sum(axis=0) / 100
+    v = ((x.astype(np.float64) - m) ** 2).sum(axis=0) / 99
+    np.testing.assert_allclose(mean.cpu().numpy(), m / np.sqrt((m * m).sum(axis=0, keepdims=True)), atol=2e-6)
+    np.testing.assert_allclose(var.cpu().numpy(), v, rtol=2e-4)
+    raw, none = B.initial_values(_dev(x, cuda), normalize=False)
+    np.testing.assert_allclose(raw.cpu().numpy(), m, atol=2e-6)
+    assert none is None
+
+
+def test_raw_sensor_pipeline_end_to_end(cuda):
+    """The online pipeline of the C++ server as one device chain: first-100-sample means -> acc_0/mag_0
+    (InitialValues / Parser.cpp:46-49), interpolation + normalisation + alpha=0.1 low-pass per gyro sample
+    (Parser.cpp:229-242, KalmanFilter.cpp:279-303), then the filter -- against the float64 restatements."""
+    from poseestimationkf_b200.synth import make_imu
+    N, T, K = 300, 80, 100
+    imu = make_imu(N, T + K, seed=9, sigma=0.01, device=cuda)
+    S = imu.streams                                                       # used as "raw" unit-ish samples
+    scale_a, scale_m = 9.81, 47.0                                         # raw sensors are not unit vectors
+    acc_raw, mag_raw = S[:, 3:6] * scale_a, S[:, 6:9] * scale_m
+    acc0, _ = B.initial_values(acc_raw[:K].contiguous(), normalize=True)
+    mag0, _ = B.initial_values(mag_raw[:K].contiguous(), normalize=True)
+    # bracketing samples: previous = sample t-1, next = sample t, gyro timestamp 30 % into the interval
+    prev = torch.cat([acc_raw[K - 1:-1], mag_raw[K - 1:-1]], dim=1).contiguous()
+    nxt = torch.cat([acc_raw[K:], mag_raw[K:]], dim=1).contiguous()
+    tspan = torch.empty((T, 4, N), device=cuda)
+    tspan[:, 0::2] = 0.01
+    tspan[:, 1::2] = 0.003
+    gyro = S[K:, 0:3].contiguous()
+    streams, _ = B.preprocess(gyro, prev, nxt, tspan, lpf_alpha_acc=0.1, lpf_alpha_mag=0.1)
+    _, traj, _ = B.replay(streams, acc0, mag0, dt=0.01, q=1.0, r=0.1, store_trajectory=True)
+    # float64 chain
+    a0 = acc_raw[:K].double().cpu().numpy().sum(0) / K; a0 = a0 / np.sqrt((a0 * a0).sum(0, keepdims=True))
+    m0 = mag_raw[:K].double().cpu().numpy().sum(0) / K; m0 = m0 / np.sqrt((m0 * m0).sum(0, keepdims=True))
+    np.testing.assert_allclose(acc0.cpu().numpy(), a0, atol=2e-6)
+    P, Nx = prev.double().cpu().numpy(), nxt.double().cpu().numpy()
+    ts = tspan.double().cpu().numpy()          # the float32 values the kernel saw
+    acc_i = O.interpolate_normalise(P[:, 0:3].transpose(0, 2, 1), Nx[:, 0:3].transpose(0, 2, 1), 0.0, ts[:, 0], ts[:, 1])
+    mag_i = O.interpolate_normalise(P[:, 3:6].transpose(0, 2, 1), Nx[:, 3:6].transpose(0, 2, 1), 0.0, ts[:, 2], ts[:, 3])
+    Sf = np.empty((T, 9, N))
+    Sf[:, 0:3] = gyro.double().cpu().numpy()
+    for n in range(N):
+        Sf[:, 3:6, n] = O.lowpass_scalar(acc_i[:, n], 0.1)
+        Sf[:, 6:9, n] = O.lowpass_scalar(mag_i[:, n], 0.1)
+    np.testing.assert_allclose(streams.cpu().numpy(), Sf, atol=3e-6)
+    ref = O.replay_batched(np.full(T, 1e7), Sf[:, 0:3], Sf[:, 3:6], Sf[:, 6:9], acc0.double().cpu().numpy().T,
+                           mag0.double().cpu().numpy().T, 1.0, 0.1)
+    # the oracle consumes the float64 pre-processing output, the kernel its float32 one: the comparison
+    # includes that input rounding (amplified while the low-pass state is still small)
+    assert O.quat_angle(traj.cpu().numpy(), ref["X"])[5:].max() < 2e-5
