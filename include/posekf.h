@@ -34,6 +34,8 @@ extern "C" {
 /* Wahba solver selection (see DESIGN.md "Wahba stage") */
 #define POSEKF_WAHBA_QR2    0   /* rank-2 SVD: QR of both vector pairs + closed-form 2x2 polar factor */
 #define POSEKF_WAHBA_JACOBI 1   /* B formed as in PKF/Wahba.py:11-13, one-sided Jacobi SVD in registers */
+#define POSEKF_WAHBA_PRECOMPUTED 2 /* posekf_replay_f32 only: stream rows 3-6 already hold the Wahba quaternion
+                                      (posekf_measurement_stream_f32) -- for (Q,R) sweeps over shared streams */
 
 /* Stream staging selection for posekf_replay_f32 */
 #define POSEKF_STAGE_AUTO 0     /* TMA when alignment allows, else LDG */
@@ -171,6 +173,17 @@ int posekf_preprocess_f32(int64_t n_filters, int64_t n_steps, const float* gyro,
  *   samples [K][3][N] -> out_mean [3][N], out_var [3][N] or NULL (variance of the raw samples, K >= 2). */
 int posekf_initial_values_f32(int64_t n_filters, int64_t n_samples, const float* samples, int normalize, float* out_mean,
                               float* out_var, void* stream);
+
+/* Measurement stream for POSEKF_WAHBA_PRECOMPUTED.  The Wahba solution of a sample does not depend on Q or R,
+ * so a tuning sweep that replays Ns trajectories N/Ns times solves it ONCE per (trajectory, step):
+ *   streams [T][9][Ns] (gyro, acc, mag) -> out_streams [T][9][Ns]: rows 0-2 gyro, rows 3-6 the quaternion of
+ *   Wahba.getQuarternion(acc, mag, |acc_z|, 1-|acc_z|) in the reference's sign convention
+ *   (PKF/ExtendedKalmanFilter.py:71, PKF/Wahba.py:49-50), rows 7-8 zero.
+ * The optional low-pass (alpha >= 0, lpf_state [6][Ns] in/out) is applied here, before the solve; the replay of
+ * a measurement stream must then run with the low-pass off.  wahba_algo: POSEKF_WAHBA_QR2 or _JACOBI. */
+int posekf_measurement_stream_f32(int64_t n_streams, int64_t n_steps, const float* streams, const float* acc_ref,
+                                  const float* mag_ref, float lpf_alpha_acc, float lpf_alpha_mag, float* lpf_state,
+                                  float* out_streams, int wahba_algo, void* stream);
 
 /* Quart2RPY over a stored trajectory: traj [M][4] (e.g. out_traj with M = T*N) -> degrees [M][3].
  * PKF/UtilityFunctions.py:3-14; C++ twin SRV/KalmanFilter.cpp:194-233 (which clamps asin; this does not,

@@ -12,7 +12,7 @@ from . import build as _build
 _i64, _int, _f32, _vp = C.c_int64, C.c_int, C.c_float, C.c_void_p
 
 EINVAL, EALIGN, ENODEV = -1, -2, -3
-WAHBA = {"qr2": 0, "jacobi": 1}
+WAHBA = {"qr2": 0, "jacobi": 1, "precomputed": 2}
 STAGING = {"auto": 0, "ldg": 1, "tma": 2, "tma_packed": 3}
 
 _SIGNATURES = {
@@ -25,6 +25,7 @@ _SIGNATURES = {
     "posekf_wahba_f32": [_i64, _vp, _vp, _int, _vp, _vp, _vp, _vp, _f32, _f32, _int, _vp, _vp, _int, _int, _vp],
     "posekf_tracks_f32": [_i64, _i64, _vp, _i64, _vp, _int, _vp, _vp, _f32, _f32, _int, _vp, _vp, _vp, _int, _vp],
     "posekf_traj2rpy_f32": [_i64, _vp, _vp, _vp],
+    "posekf_measurement_stream_f32": [_i64, _i64, _vp, _vp, _vp, _f32, _f32, _vp, _vp, _int, _vp],
     "posekf_initial_values_f32": [_i64, _i64, _vp, _int, _vp, _vp, _vp],
     "posekf_preprocess_f32": [_i64, _i64, _vp, _vp, _vp, _vp, _f32, _f32, _vp, _vp, _vp],
     "posekf_rot2quat_f32": [_i64, _vp, _vp, _vp],

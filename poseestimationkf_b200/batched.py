@@ -144,11 +144,33 @@ def _per_filter(v, n, device):
     return torch.full((n,), float(v), dtype=torch.float32, device=device)
 
 
+def measurement_stream(streams, acc_ref, mag_ref, *, lpf_alpha_acc=None, lpf_alpha_mag=None, lpf_state=None,
+                       algo: str = "qr2", out=None):
+    """Solve the Wahba problem of every (stream, step) once: streams [T,9,Ns] -> a measurement stream of the
+    same shape (rows 0-2 gyro, rows 3-6 the reference-signed Wahba quaternion, rows 7-8 zero) to be replayed
+    with `wahba="precomputed"`.  The optional low-pass is applied here (state [6,Ns] carried across chunks).
+    Returns (measurement stream, lpf_state)."""
+    _require_cuda(streams, acc_ref, mag_ref, lpf_state, out)
+    T, _, Ns = streams.shape
+    use_lpf = lpf_alpha_acc is not None or lpf_alpha_mag is not None
+    if use_lpf and lpf_state is None:
+        lpf_state = torch.zeros((6, Ns), dtype=torch.float32, device=streams.device)
+    if out is None:
+        out = torch.empty_like(streams)
+    with torch.cuda.device(streams.device):
+        rc = _lib.load().posekf_measurement_stream_f32(
+            Ns, T, _ptr(streams), _ptr(acc_ref), _ptr(mag_ref), -1.0 if lpf_alpha_acc is None else float(lpf_alpha_acc),
+            -1.0 if lpf_alpha_mag is None else float(lpf_alpha_mag), _ptr(lpf_state), _ptr(out), _lib.WAHBA[algo], _stream())
+    _lib.check(rc, "posekf_measurement_stream_f32")
+    return out, lpf_state
+
+
 def replay(streams: torch.Tensor, acc_ref: torch.Tensor, mag_ref: torch.Tensor, *, dt, q=1.0, r=0.1,
            state: ReplayState | None = None, n_filters: int | None = None, lpf_alpha_acc: float | None = None,
            lpf_alpha_mag: float | None = None, out_traj: torch.Tensor | None = None, store_trajectory: bool = False,
            store_flips: bool = False, truth: torch.Tensor | None = None, loss: torch.Tensor | None = None,
-           precise_state: bool | None = None, wahba: str = "qr2", staging: str = "auto"):
+           precise_state: bool | None = None, share_measurements: bool | None = None, wahba: str = "qr2",
+           staging: str = "auto"):
     """Run T Prediction+Correction steps for N filters in one kernel launch.
 
     streams [T,9,Ns]; acc_ref, mag_ref [3,Ns]; dt: float seconds or [T] float32 CUDA tensor;
@@ -161,6 +183,9 @@ def replay(streams: torch.Tensor, acc_ref: torch.Tensor, mag_ref: torch.Tensor, 
     ~1e-7 are not lost when R >> Q; Sherman-Morrison gain when Q >> R; +17 % time); None = automatic:
     on when q or r are per-filter tensors (a tuning sweep), when r/q >= 100 or q/r >= 1e4, off otherwise
     (the default Q=1, R=0.1 does not need it).
+    `share_measurements`: in the sweep layout (N > Ns) the Wahba solution of a sample is the same for every
+    filter that shares its trajectory, so it is solved once per (trajectory, step) (`measurement_stream`) and
+    the replay runs with `wahba="precomputed"`; None = automatic for N >= 4 Ns without a low-pass stage.
     Returns (state, traj [T,N,4] or None, flips [T,N] uint8 or None)."""
     _require_cuda(streams, acc_ref, mag_ref, out_traj)
     if streams.dim() != 3 or streams.shape[1] != 9:
@@ -171,6 +196,13 @@ def replay(streams: torch.Tensor, acc_ref: torch.Tensor, mag_ref: torch.Tensor, 
         raise ValueError("acc_ref / mag_ref must be [3, Ns]")
     dev = streams.device
     use_lpf = lpf_alpha_acc is not None or lpf_alpha_mag is not None
+    if share_measurements is None:
+        share_measurements = N > Ns and N >= 4 * Ns and wahba == "qr2" and not use_lpf and T > 0
+    if share_measurements:
+        if wahba == "precomputed" or use_lpf or N == Ns:
+            raise ValueError("share_measurements needs raw streams, N > Ns and no low-pass stage")
+        streams, _ = measurement_stream(streams, acc_ref, mag_ref, algo=wahba)
+        wahba = "precomputed"
     if not isinstance(r, torch.Tensor) and not float(r) > 0.0:
         raise ValueError("r must be > 0 (the kernel carries the covariance in units of r)")
     if state is None:

@@ -644,7 +644,10 @@ template <typename F> PKF_HD auto reference_flip(const Mat3<F>& M, const Quat<F>
 // P_post/r = K -- so the scaled form saves the r multiplications and makes the post-update
 // covariance literally equal to the gain.  Callers convert at launch boundaries (r > 0 required).
 // ------------------------------------------------------------------------------------------
-enum WahbaAlgo { WAHBA_QR2 = 0, WAHBA_JACOBI = 1 };
+// WAHBA_PRECOMPUTED: the measurement quaternion (reference sign convention) comes with the stream instead of
+// acc/mag -- a (Q,R) sweep replays every trajectory thousands of times and its Wahba solution does not
+// depend on Q or R, so it is solved once per trajectory and step (measurement_stream_kernel).
+enum WahbaAlgo { WAHBA_QR2 = 0, WAHBA_JACOBI = 1, WAHBA_PRECOMPUTED = 2 };
 constexpr int kJacobiSweepsFused = 4;
 
 template <typename F> struct FilterConst {
@@ -701,27 +704,38 @@ PKF_HD void ekf_step(Quat<F>& x, Quat<F>& xlo, Sym4<F>& P, const FilterConst<F>&
   Quat<F> z;                                                                  // |z| = 1 to rounding
   z.w = x.w + inc.w; z.x = x.x + inc.x; z.y = x.y + inc.y; z.z = x.z + inc.z;
   // ---- Correction (PKF/ExtendedKalmanFilter.py:70-80) ----
-  F ka = abs_(acc.z), km = F(1) - ka;                                         // :71
-  Mat3<F> Rm;
-  if constexpr (ALGO == WAHBA_QR2) Rm = wahba_qr2(fc.E, acc, mag, ka, km);
-  else Rm = wahba_jacobi(fc.ra, fc.rm, acc, mag, ka, km, kJacobiSweepsFused);
-  // measurement quaternion with the comparator's sign already applied            :73-75
-  F n2;
-  Quat<F> y = rotation_to_quat_aligned(Rm, z, n2);       // un-normalised: 4 (y.z) y
-  flip = FlagT();
-  if (WANT_FLIP) flip = reference_flip(Rm, y);           // only the signs of y matter
-  // innovation e = y/|y| - z, the normalisation folded into the subtraction       :76
-  const F inv = rsqrt_(n2);
-  F e0 = fma_(y.w, inv, -z.w), e1 = fma_(y.x, inv, -z.x), e2 = fma_(y.y, inv, -z.y), e3 = fma_(y.z, inv, -z.z);
-  const auto unrelated = n2 < F(0.16);
-  if (any_(unrelated)) {
-    // |y.z| < 0.1: prediction and measurement are unrelated (never in a tracking filter; can happen
-    // on the first sample of a badly initialised one).  Use the selection-based conversion there.
-    Quat<F> yf = y;
-    quat_fallback_unaligned(Rm, z, unrelated, yf);
-    if (WANT_FLIP) flip = reference_flip(Rm, yf);
-    e0 = sel_(unrelated, yf.w - z.w, e0); e1 = sel_(unrelated, yf.x - z.x, e1);
-    e2 = sel_(unrelated, yf.y - z.y, e2); e3 = sel_(unrelated, yf.z - z.z, e3);
+  F e0, e1, e2, e3;
+  if constexpr (ALGO == WAHBA_PRECOMPUTED) {
+    // stream rows 3..6 carry the Wahba quaternion in the reference's own sign convention (the output of
+    // getQuarternion, :71): apply the comparator literally -- negate when dot(y, z) < 0            :73-75
+    const Quat<F> y = {acc.x, acc.y, acc.z, mag.x};
+    const auto neg = dot4(y, z) < F(0);
+    flip = neg;
+    const F sg = sel_(neg, F(-1), F(1));
+    e0 = fma_(sg, y.w, -z.w); e1 = fma_(sg, y.x, -z.x); e2 = fma_(sg, y.y, -z.y); e3 = fma_(sg, y.z, -z.z);   // :76
+  } else {
+    F ka = abs_(acc.z), km = F(1) - ka;                                       // :71
+    Mat3<F> Rm;
+    if constexpr (ALGO == WAHBA_QR2) Rm = wahba_qr2(fc.E, acc, mag, ka, km);
+    else Rm = wahba_jacobi(fc.ra, fc.rm, acc, mag, ka, km, kJacobiSweepsFused);
+    // measurement quaternion with the comparator's sign already applied          :73-75
+    F n2;
+    Quat<F> y = rotation_to_quat_aligned(Rm, z, n2);     // un-normalised: 4 (y.z) y
+    flip = FlagT();
+    if (WANT_FLIP) flip = reference_flip(Rm, y);         // only the signs of y matter
+    // innovation e = y/|y| - z, the normalisation folded into the subtraction     :76
+    const F inv = rsqrt_(n2);
+    e0 = fma_(y.w, inv, -z.w); e1 = fma_(y.x, inv, -z.x); e2 = fma_(y.y, inv, -z.y); e3 = fma_(y.z, inv, -z.z);
+    const auto unrelated = n2 < F(0.16);
+    if (any_(unrelated)) {
+      // |y.z| < 0.1: prediction and measurement are unrelated (never in a tracking filter; can happen
+      // on the first sample of a badly initialised one).  Use the selection-based conversion there.
+      Quat<F> yf = y;
+      quat_fallback_unaligned(Rm, z, unrelated, yf);
+      if (WANT_FLIP) flip = reference_flip(Rm, yf);
+      e0 = sel_(unrelated, yf.w - z.w, e0); e1 = sel_(unrelated, yf.x - z.x, e1);
+      e2 = sel_(unrelated, yf.y - z.y, e2); e3 = sel_(unrelated, yf.z - z.z, e3);
+    }
   }
   // X = z + K e                                                              :77
   Quat<F> ke;

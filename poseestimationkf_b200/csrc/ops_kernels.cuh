@@ -214,6 +214,49 @@ __global__ void __launch_bounds__(256)
   mean[n] = o0; mean[N + n] = o1; mean[2 * N + n] = o2;
 }
 
+// Measurement stream for POSEKF_WAHBA_PRECOMPUTED: solves the Wahba problem of every (stream, step) ONCE --
+// getQuarternion(acc, mag, |acc_z|, 1-|acc_z|) with the reference's sign convention, after the optional
+// low-pass -- and writes a stream of the same [T][9][Ns] shape: rows 0-2 gyro, rows 3-6 the quaternion
+// (w,x,y,z), rows 7-8 zero.  A (Q,R) sweep then replays it N/Ns times without redoing the solve.
+struct MeasStreamParams {
+  int64_t Ns, T;
+  const float *streams, *acc_ref, *mag_ref;
+  float alpha_acc, alpha_mag;
+  float* lpf_state;    // [6][Ns] in/out or null
+  float* out;          // [T][9][Ns]
+};
+
+template <int ALGO> __global__ void __launch_bounds__(128) measurement_stream_kernel(const MeasStreamParams p) {
+  const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= p.Ns) return;
+  const int64_t Ns = p.Ns;
+  Vec3<float> ra = {p.acc_ref[n], p.acc_ref[Ns + n], p.acc_ref[2 * Ns + n]};
+  Vec3<float> rm = {p.mag_ref[n], p.mag_ref[Ns + n], p.mag_ref[2 * Ns + n]};
+  const RefFrame<float> E = frame_from_pair<float>(ra, rm);
+  Vec3<float> la = {0.f, 0.f, 0.f}, lm = {0.f, 0.f, 0.f};
+  if (p.lpf_state) {
+    la = {p.lpf_state[n], p.lpf_state[Ns + n], p.lpf_state[2 * Ns + n]};
+    lm = {p.lpf_state[3 * Ns + n], p.lpf_state[4 * Ns + n], p.lpf_state[5 * Ns + n]};
+  }
+  for (int64_t t = 0; t < p.T; ++t) {
+    const float* s = p.streams + t * kChannels * Ns + n;
+    float* o = p.out + t * kChannels * Ns + n;
+    o[0] = ldg_stream(s); o[Ns] = ldg_stream(s + Ns); o[2 * Ns] = ldg_stream(s + 2 * Ns);
+    Vec3<float> a = {ldg_stream(s + 3 * Ns), ldg_stream(s + 4 * Ns), ldg_stream(s + 5 * Ns)};
+    Vec3<float> m = {ldg_stream(s + 6 * Ns), ldg_stream(s + 7 * Ns), ldg_stream(s + 8 * Ns)};
+    if (p.alpha_acc >= 0.f) { lowpass<float>(la, a, p.alpha_acc, 1.f - p.alpha_acc); a = la; }
+    if (p.alpha_mag >= 0.f) { lowpass<float>(lm, m, p.alpha_mag, 1.f - p.alpha_mag); m = lm; }
+    const float ka = fabsf(a.z), km = 1.f - ka;                                // PKF/ExtendedKalmanFilter.py:71
+    Mat3<float> R = (ALGO == WAHBA_QR2) ? wahba_qr2<float>(E, a, m, ka, km) : wahba_jacobi<float>(ra, rm, a, m, ka, km, 6);
+    const Quat<float> q = rotation_to_quat_ref<float>(R);
+    o[3 * Ns] = q.w; o[4 * Ns] = q.x; o[5 * Ns] = q.y; o[6 * Ns] = q.z; o[7 * Ns] = 0.f; o[8 * Ns] = 0.f;
+  }
+  if (p.lpf_state) {
+    p.lpf_state[n] = la.x; p.lpf_state[Ns + n] = la.y; p.lpf_state[2 * Ns + n] = la.z;
+    p.lpf_state[3 * Ns + n] = lm.x; p.lpf_state[4 * Ns + n] = lm.y; p.lpf_state[5 * Ns + n] = lm.z;
+  }
+}
+
 // trajectory [M][4] -> roll/pitch/yaw degrees [M][3]   (PKF/UtilityFunctions.py:3-14 per row)
 __global__ void __launch_bounds__(256) traj2rpy_kernel(int64_t M, const float4* __restrict__ q, float* __restrict__ out) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;

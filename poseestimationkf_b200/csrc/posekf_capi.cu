@@ -113,14 +113,25 @@ bool packed_eligible(const ReplayParams& p) {
   return true;      // out_traj / truth are already required to be 16-byte aligned
 }
 
-template <bool LPF, bool AUX, bool COMP> int launch_replay_packed(const ReplayParams& p, cudaStream_t st) {
+template <int ALGO, bool LPF, bool AUX, bool COMP> int launch_replay_packed(const ReplayParams& p, cudaStream_t st) {
   CUtensorMap tmap;
   if (int rc = encode_stream_map(p, kTile2, kTma2Steps, &tmap)) return rc;
-  auto kern = replay_tma2_kernel<LPF, AUX, COMP>;
+  auto kern = replay_tma2_kernel<ALGO, LPF, AUX, COMP>;
   PKF_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Tma2Smem)));
   const unsigned grid = (unsigned)((p.N + kTile2 - 1) / kTile2);
   kern<<<grid, kThreads2, sizeof(Tma2Smem), st>>>(p, tmap);
   return launch_status();
+}
+
+template <int ALGO> int launch_packed_variant(const ReplayParams& p, bool lpf, cudaStream_t st) {
+  const bool comp = p.state_x_lo != nullptr;
+  const bool aux = p.out_traj != nullptr || p.out_flip != nullptr || p.truth != nullptr;
+  if (lpf) {
+    if (aux) return comp ? launch_replay_packed<ALGO, true, true, true>(p, st) : launch_replay_packed<ALGO, true, true, false>(p, st);
+    return comp ? launch_replay_packed<ALGO, true, false, true>(p, st) : launch_replay_packed<ALGO, true, false, false>(p, st);
+  }
+  if (aux) return comp ? launch_replay_packed<ALGO, false, true, true>(p, st) : launch_replay_packed<ALGO, false, true, false>(p, st);
+  return comp ? launch_replay_packed<ALGO, false, false, true>(p, st) : launch_replay_packed<ALGO, false, false, false>(p, st);
 }
 
 template <int ALGO, bool LPF> int launch_replay_aux(const ReplayParams& p, bool use_tma, cudaStream_t st) {
@@ -136,22 +147,15 @@ int replay_dispatch(const ReplayParams& p, int algo, int staging, cudaStream_t s
   if (staging == POSEKF_STAGE_LDG) use_tma = false;
   else if (staging == POSEKF_STAGE_TMA) { if (!tma_eligible(p)) return POSEKF_EALIGN; use_tma = true; }
   else if (staging == POSEKF_STAGE_TMA_PACKED) {
-    if (!tma_eligible(p) || !packed_eligible(p) || algo != POSEKF_WAHBA_QR2) return POSEKF_EALIGN;
+    if (!tma_eligible(p) || !packed_eligible(p) || algo == POSEKF_WAHBA_JACOBI) return POSEKF_EALIGN;
     use_tma = packed = true;
   } else if (staging == POSEKF_STAGE_AUTO) {
     use_tma = tma_eligible(p);
-    packed = use_tma && kAutoPrefersPacked && algo == POSEKF_WAHBA_QR2 && packed_eligible(p);
+    packed = use_tma && kAutoPrefersPacked && algo != POSEKF_WAHBA_JACOBI && packed_eligible(p);
   } else return POSEKF_EINVAL;
-  if (packed) {
-    const bool comp = p.state_x_lo != nullptr;
-    const bool aux = p.out_traj != nullptr || p.out_flip != nullptr || p.truth != nullptr;
-    if (lpf) {
-      if (aux) return comp ? launch_replay_packed<true, true, true>(p, st) : launch_replay_packed<true, true, false>(p, st);
-      return comp ? launch_replay_packed<true, false, true>(p, st) : launch_replay_packed<true, false, false>(p, st);
-    }
-    if (aux) return comp ? launch_replay_packed<false, true, true>(p, st) : launch_replay_packed<false, true, false>(p, st);
-    return comp ? launch_replay_packed<false, false, true>(p, st) : launch_replay_packed<false, false, false>(p, st);
-  }
+  if (packed)
+    return algo == POSEKF_WAHBA_QR2 ? launch_packed_variant<WAHBA_QR2>(p, lpf, st) : launch_packed_variant<WAHBA_PRECOMPUTED>(p, lpf, st);
+  if (algo == POSEKF_WAHBA_PRECOMPUTED) return lpf ? launch_replay_aux<WAHBA_PRECOMPUTED, true>(p, use_tma, st) : launch_replay_aux<WAHBA_PRECOMPUTED, false>(p, use_tma, st);
   if (algo == POSEKF_WAHBA_QR2) return lpf ? launch_replay_aux<WAHBA_QR2, true>(p, use_tma, st) : launch_replay_aux<WAHBA_QR2, false>(p, use_tma, st);
   if (algo == POSEKF_WAHBA_JACOBI) return lpf ? launch_replay_aux<WAHBA_JACOBI, true>(p, use_tma, st) : launch_replay_aux<WAHBA_JACOBI, false>(p, use_tma, st);
   return POSEKF_EINVAL;
@@ -179,6 +183,8 @@ int posekf_replay_f32(int64_t n_filters, int64_t n_steps, const float* streams, 
   if (n_streams > n_filters || (n_filters % n_streams) != 0) return POSEKF_EINVAL;
   const bool lpf = lpf_alpha_acc >= 0.f || lpf_alpha_mag >= 0.f;
   if (lpf && !state_lpf) return POSEKF_EINVAL;
+  if (wahba_algo < POSEKF_WAHBA_QR2 || wahba_algo > POSEKF_WAHBA_PRECOMPUTED) return POSEKF_EINVAL;
+  if (lpf && wahba_algo == POSEKF_WAHBA_PRECOMPUTED) return POSEKF_EINVAL;   // the low-pass belongs to the stream builder
   if ((n_filters + kThreads - 1) / kThreads > 0x7fffffffLL || n_steps > 0x7fffffffLL) return POSEKF_EINVAL;
   if (out_traj && (reinterpret_cast<uintptr_t>(out_traj) & 15) != 0) return POSEKF_EALIGN;
   if (truth && (!loss_acc || (reinterpret_cast<uintptr_t>(truth) & 15) != 0)) return truth && !loss_acc ? POSEKF_EINVAL : POSEKF_EALIGN;
@@ -417,6 +423,21 @@ int posekf_initial_values_f32(int64_t n_filters, int64_t n_samples, const float*
   if (!samples || !out_mean || (out_var && n_samples < 2)) return POSEKF_EINVAL;
   initial_values_kernel<<<blocks_for(n_filters, 256), 256, 0, (cudaStream_t)stream>>>(n_filters, n_samples, samples, normalize,
                                                                                         out_mean, out_var);
+  return launch_status();
+}
+
+int posekf_measurement_stream_f32(int64_t n_streams, int64_t n_steps, const float* streams, const float* acc_ref,
+                                  const float* mag_ref, float lpf_alpha_acc, float lpf_alpha_mag, float* lpf_state,
+                                  float* out_streams, int wahba_algo, void* stream) {
+  if (n_streams < 0 || n_steps < 0) return POSEKF_EINVAL;
+  if (n_streams == 0 || n_steps == 0) return 0;
+  if (!streams || !acc_ref || !mag_ref || !out_streams) return POSEKF_EINVAL;
+  if ((lpf_alpha_acc >= 0.f || lpf_alpha_mag >= 0.f) && !lpf_state) return POSEKF_EINVAL;
+  MeasStreamParams p{n_streams, n_steps, streams, acc_ref, mag_ref, lpf_alpha_acc, lpf_alpha_mag, lpf_state, out_streams};
+  cudaStream_t st = (cudaStream_t)stream;
+  if (wahba_algo == POSEKF_WAHBA_QR2) measurement_stream_kernel<WAHBA_QR2><<<blocks_for(n_streams, 128), 128, 0, st>>>(p);
+  else if (wahba_algo == POSEKF_WAHBA_JACOBI) measurement_stream_kernel<WAHBA_JACOBI><<<blocks_for(n_streams, 128), 128, 0, st>>>(p);
+  else return POSEKF_EINVAL;
   return launch_status();
 }
 

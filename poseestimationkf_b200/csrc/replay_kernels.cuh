@@ -239,7 +239,7 @@ __global__ void __launch_bounds__(kThreads, (COMP && (LPF || AUX)) ? (kMinCtasPe
 // Replay, TMA staging, PACKED: each thread advances TWO filters in the lanes of f32x2 values, so
 // every FP32 operation of the step is one FFMA2 / FMUL2 / FADD2.  Same tiles, same barriers and
 // the same arithmetic per filter as replay_tma_kernel (results are bit-identical); half the
-// threads.  Rank-2 Wahba only (the Jacobi variant uses the scalar kernel).
+// threads.  ALGO is WAHBA_QR2 or WAHBA_PRECOMPUTED (the Jacobi variant uses the scalar kernel).
 // ---------------------------------------------------------------------------------------------
 struct __align__(128) Tma2Smem {
   float tile[kTma2Stages][kTma2Steps][kChannels][kTile2];
@@ -255,7 +255,7 @@ struct FilterRegs2 {
   Vec3<f32x2> la, lm;
 };
 
-template <bool LPF, bool AUX, bool COMP>
+template <int ALGO, bool LPF, bool AUX, bool COMP>
 __global__ void __launch_bounds__(kThreads2, (LPF && COMP) ? (PKF_MIN_CTAS2 > 6 ? 6 : PKF_MIN_CTAS2) : PKF_MIN_CTAS2)
     replay_tma2_kernel(const ReplayParams p, const __grid_constant__ CUtensorMap tmap) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -342,7 +342,7 @@ __global__ void __launch_bounds__(kThreads2, (LPF && COMP) ? (PKF_MIN_CTAS2 > 6 
             if (p.alpha_mag >= 0.f) { lowpass<f32x2>(f.lm, m, f32x2(p.alpha_mag), f32x2(1.f - p.alpha_mag)); m = f.lm; }
           }
           mask2 flip;
-          ekf_step<f32x2, WAHBA_QR2, AUX, COMP>(f.x, f.xlo, f.P, f.fc, w, a, m, f32x2(h), flip);
+          ekf_step<f32x2, ALGO, AUX, COMP>(f.x, f.xlo, f.P, f.fc, w, a, m, f32x2(h), flip);
           if (AUX) {
             if (traj) {   // [T][N][4]: two adjacent 16-byte quaternions
               asm volatile("st.global.cs.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(traj), "f"(f.x.w.x), "f"(f.x.x.x), "f"(f.x.y.x),

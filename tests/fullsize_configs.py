@@ -48,11 +48,11 @@ if "c3" in which:
     N = G1 * G1 * Ns
     truth = imu.q_true.permute(0, 2, 1).to(torch.float32).contiguous()
     out = {}
-    for precise in (True, False):
+    for precise, share in ((True, True), (True, False), (False, True), (False, False)):
         def run():
             st = B.ReplayState.initial(N, dev, r=r_t)
             B.replay(imu.streams, imu.acc_ref, imu.mag_ref, dt=imu.dt, q=q_t, r=r_t, n_filters=N, state=st, truth=truth,
-                     precise_state=precise)
+                     precise_state=precise, share_measurements=share)
             out["st"] = st
         ms = timed(run)
         st = out["st"]
@@ -68,6 +68,7 @@ if "c3" in which:
             worst[f"q={float(qs[iq]):.0e},r={float(rs[ir]):.0e}"] = float(O.quat_angle(got, ref["X_final"]).max())
         best = np.unravel_index(surface.argmin(), surface.shape)
         print(json.dumps({"config": "C3 sweep 64x64 (Q,R) x 256 trajectories x 5000 steps", "precise_state": precise,
+                          "share_measurements": share,
                           "filters": N, "ms": ms, "gsteps_per_s": N * T / ms / 1e6,
                           "final_state_max_angle_vs_oracle": worst,
                           "loss_surface_min_at": {"q": float(qs[best[0]]), "r": float(rs[best[1]]), "mean_sin2": float(surface.min())}}))

@@ -375,3 +375,48 @@ def test_state_created_with_another_r_is_rescaled(cuda):
     B.replay(imu.streams, imu.acc_ref, imu.mag_ref, dt=imu.dt, q=2.0, r=0.5, state=st, precise_state=False)
     assert torch.equal(a.x, st.x) and torch.equal(a.p, st.p)
     torch.testing.assert_close(st.covariance(), a.covariance())
+
+
+def test_precomputed_measurement_stream_sweep(cuda):
+    """A (Q,R) sweep replays each trajectory G times; its Wahba solution does not depend on Q,R, so it is
+    solved once per (trajectory, step) and replayed with POSEKF_WAHBA_PRECOMPUTED.  Parity vs the oracle,
+    flip mask included, for every staging; the low-pass belongs to the stream builder."""
+    from oracle import c_oracle as CO
+    Ns, T = 256, 300
+    imu = make_imu(Ns, T, seed=41, sigma=0.01, device=cuda)
+    grid = [(1e-3, 1e3), (1.0, 0.1), (10.0, 0.01), (1e3, 1e-3), (0.1, 1.0)]
+    G = len(grid)
+    q_t = _dev(np.repeat([q for q, _ in grid], Ns), cuda)
+    r_t = _dev(np.repeat([r for _, r in grid], Ns), cuda)
+    S = imu.streams.cpu().numpy()
+    refs = [CO.replay(S, imu.dt * 1e9, imu.acc_ref.cpu().numpy(), imu.mag_ref.cpu().numpy(), float(np.float32(q)),
+                      float(np.float32(r))) for q, r in grid]
+    meas, _ = B.measurement_stream(imu.streams, imu.acc_ref, imu.mag_ref)
+    assert torch.equal(meas[:, 0:3], imu.streams[:, 0:3]) and (meas[:, 7:9] == 0).all()
+    _, wah, _ = B.tracks(imu.streams, imu.acc_ref, imu.mag_ref, dt=imu.dt, weights_from_acc=True, want_gyro=False)
+    assert torch.equal(meas[:, 3:7].permute(0, 2, 1), wah)               # rows 3-6 ARE the Wahba-only track
+    outs = []
+    for staging in ("ldg", "tma", "tma_packed"):
+        st, traj, fl = B.replay(meas, imu.acc_ref, imu.mag_ref, dt=imu.dt, q=q_t, r=r_t, n_filters=G * Ns, wahba="precomputed",
+                                store_trajectory=True, store_flips=True, staging=staging)
+        got = traj.cpu().numpy().reshape(T, G, Ns, 4)
+        flips = fl.cpu().numpy().reshape(T, G, Ns).astype(bool)
+        for gi in range(G):
+            assert O.quat_angle(got[:, gi], refs[gi]["X"]).max() < 1e-6, (staging, grid[gi])
+            assert (np.sum(got[:, gi] * refs[gi]["X"], axis=-1) > 0).all()
+            assert (flips[:, gi] != refs[gi]["flips"]).sum() <= 2
+        outs.append((st, traj, fl))
+    assert torch.equal(outs[0][1], outs[1][1]) and torch.equal(outs[1][1], outs[2][1]) and torch.equal(outs[1][2], outs[2][2])
+    # automatic sharing in replay(): N >= 4 Ns
+    auto, _, _ = B.replay(imu.streams, imu.acc_ref, imu.mag_ref, dt=imu.dt, q=q_t, r=r_t, n_filters=G * Ns)
+    assert torch.equal(auto.x, outs[2][0].x)
+    plain, _, _ = B.replay(imu.streams, imu.acc_ref, imu.mag_ref, dt=imu.dt, q=q_t, r=r_t, n_filters=G * Ns, share_measurements=False)
+    assert O.quat_angle(auto.x.t().cpu().numpy(), plain.x.t().cpu().numpy()).max() < 1e-6
+    # low-pass in the builder == low-pass fused in the raw replay
+    meas_lp, lp_state = B.measurement_stream(imu.streams, imu.acc_ref, imu.mag_ref, lpf_alpha_acc=0.1, lpf_alpha_mag=0.1)
+    a, _, _ = B.replay(meas_lp, imu.acc_ref, imu.mag_ref, dt=imu.dt, wahba="precomputed", precise_state=False)
+    b, _, _ = B.replay(imu.streams, imu.acc_ref, imu.mag_ref, dt=imu.dt, lpf_alpha_acc=0.1, lpf_alpha_mag=0.1, precise_state=False)
+    assert O.quat_angle(a.x.t().cpu().numpy(), b.x.t().cpu().numpy()).max() < 1e-6
+    assert torch.equal(lp_state, b.lpf)
+    with pytest.raises(_lib.PosekfError):       # a measurement stream cannot be low-passed again
+        B.replay(meas, imu.acc_ref, imu.mag_ref, dt=imu.dt, wahba="precomputed", lpf_alpha_acc=0.1)
