@@ -35,11 +35,11 @@ def opcode(line):
 out = {}
 for name, lines in funcs.items():
     m = re.search(r"replay_(tma|ldg)_kernelILi(\d)ELb(\d)ELb(\d)ELb(\d)E", name)
-    m2 = re.search(r"replay_tma2_kernelILb(\d)ELb(\d)ELb(\d)E", name)
+    m2 = re.search(r"replay_tma2_kernelILi(\d)ELb(\d)ELb(\d)ELb(\d)E", name)
     if m:
         key = f"replay_{m.group(1)}<algo={m.group(2)},lpf={m.group(3)},aux={m.group(4)},comp={m.group(5)}>"
     elif m2:
-        key = f"replay_tma2_packed<lpf={m2.group(1)},aux={m2.group(2)},comp={m2.group(3)}>"
+        key = f"replay_tma2_packed<algo={m2.group(1)},lpf={m2.group(2)},aux={m2.group(3)},comp={m2.group(4)}>"
     else:
         continue
     ops = collections.Counter(opcode(l) for l in lines)
