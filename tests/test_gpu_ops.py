@@ -340,3 +340,44 @@ def test_raw_sensor_pipeline_end_to_end(cuda):
     # the oracle consumes the float64 pre-processing output, the kernel its float32 one: the comparison
     # includes that input rounding (amplified while the low-pass state is still small)
     assert O.quat_angle(traj.cpu().numpy(), ref["X"])[5:].max() < 2e-5
+
+
+def test_size_independent_properties_of_the_operators(cuda):
+    """Properties that hold for any input size (checked at 1 Mi elements, far beyond what the oracle loops
+    over): Wahba output is a proper rotation and is equivariant under a rotation of the reference frame,
+    its quaternion round-trips, the low-pass is linear, RK4 preserves the norm."""
+    g = torch.Generator(device=cuda); g.manual_seed(0)
+    M = 1 << 20
+
+    def unit(v):
+        return v / torch.linalg.vector_norm(v, dim=0, keepdim=True)
+    ra, rm, a, m = (unit(torch.randn((3, M), generator=g, device=cuda)) for _ in range(4))
+    R, q = B.wahba(ra, rm, a, m, weights_from_acc=True, want_rotation=True)
+    Rm = R.t().reshape(M, 3, 3)
+    ok = (torch.linalg.cross(ra, rm, dim=0).norm(dim=0) > 0.2) & (torch.linalg.cross(a, m, dim=0).norm(dim=0) > 0.2) \
+        & (a[2].abs() > 0.02) & (a[2].abs() < 0.98)
+    eye = torch.eye(3, device=cuda)
+    assert ((Rm @ Rm.transpose(1, 2) - eye).abs().amax(dim=(1, 2))[ok] < 2e-5).all()          # orthonormal
+    assert ((torch.linalg.det(Rm) - 1).abs()[ok] < 2e-5).all()                                  # proper
+    # quaternion of R reproduces R:  R(q) == R
+    w, x, y, z = q
+    Rq = torch.stack([1 - 2 * (y * y + z * z), 2 * (x * y - w * z), 2 * (x * z + w * y),
+                      2 * (x * y + w * z), 1 - 2 * (x * x + z * z), 2 * (y * z - w * x),
+                      2 * (x * z - w * y), 2 * (y * z + w * x), 1 - 2 * (x * x + y * y)])
+    assert ((Rq - R).abs().amax(dim=0)[ok] < 2e-5).all()
+    # equivariance: rotating both reference vectors by Q rotates the solution by Q
+    c, s = 0.6, 0.8
+    Q = torch.tensor([[c, -s, 0.0], [s, c, 0.0], [0.0, 0.0, 1.0]], device=cuda)
+    R2, _ = B.wahba((Q @ ra).contiguous(), (Q @ rm).contiguous(), a, m, weights_from_acc=True, want_rotation=True)
+    assert (((Q @ Rm) - R2.t().reshape(M, 3, 3)).abs().amax(dim=(1, 2))[ok] < 3e-5).all()
+    # low-pass is linear:  L(a x + b y) = a L(x) + b L(y)
+    x1, x2 = torch.randn((50, 3, 4096), generator=g, device=cuda), torch.randn((50, 3, 4096), generator=g, device=cuda)
+    l12, _ = B.lowpass(2.0 * x1 - 0.5 * x2, 0.1)
+    l1, _ = B.lowpass(x1, 0.1); l2, _ = B.lowpass(x2, 0.1)
+    torch.testing.assert_close(l12, 2.0 * l1 - 0.5 * l2, rtol=1e-4, atol=1e-5)
+    # RK4 + normalise keeps unit norm; zero rate is the identity
+    q0 = unit(torch.randn((4, M), generator=g, device=cuda))
+    w3 = torch.randn((3, M), generator=g, device=cuda)
+    q1 = B.rk4(q0, 0.01, w3)
+    assert ((q1.norm(dim=0) - 1).abs() < 3e-7).all()
+    assert (B.rk4(q0, 0.01, torch.zeros_like(w3)) - q0).abs().max() < 5e-7      # only the renormalisation of q0
