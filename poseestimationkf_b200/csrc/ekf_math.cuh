@@ -250,22 +250,26 @@ PKF_HD Sym4<F> propagate_cov(const Sym4<F>& P, const Vec3<F>& hw, const Quat<F>&
   // rows of A: [0,-X,-Y,-Z], [X,0,Z,-Y], [Y,-Z,0,X], [Z,Y,-X,0]
   const F p00 = P.a00, p01 = P.a01, p02 = P.a02, p03 = P.a03, p11 = P.a11, p12 = P.a12, p13 = P.a13,
           p22 = P.a22, p23 = P.a23, p33 = P.a33;
-  F m00 = fma_(-Z, p03, fma_(-Y, p02, -(X * p01)));
-  F m01 = fma_(-Z, p13, fma_(-Y, p12, -(X * p11)));
-  F m02 = fma_(-Z, p23, fma_(-Y, p22, -(X * p12)));
-  F m03 = fma_(-Z, p33, fma_(-Y, p23, -(X * p13)));
-  F m10 = fma_(-Y, p03, fma_(Z, p02, X * p00));
-  F m11 = fma_(-Y, p13, fma_(Z, p12, X * p01));
-  F m12 = fma_(-Y, p23, fma_(Z, p22, X * p02));
-  F m13 = fma_(-Y, p33, fma_(Z, p23, X * p03));
-  F m20 = fma_(X, p03, fma_(-Z, p01, Y * p00));
-  F m21 = fma_(X, p13, fma_(-Z, p11, Y * p01));
-  F m22 = fma_(X, p23, fma_(-Z, p12, Y * p02));
-  F m23 = fma_(X, p33, fma_(-Z, p13, Y * p03));
-  F m30 = fma_(-X, p02, fma_(Y, p01, Z * p00));
-  F m31 = fma_(-X, p12, fma_(Y, p11, Z * p01));
-  F m32 = fma_(-X, p22, fma_(Y, p12, Z * p02));
-  F m33 = fma_(-X, p23, fma_(Y, p13, Z * p03));
+  // Each entry is one product plus two FMAs.  The 48 products come in +/- pairs (X p01 is needed by m00 and
+  // m11, Y p12 by m01 and m32, ...): starting both chains of a pair from the shared product lets the pair cost
+  // one multiplication instead of two -- 8 multiplications for the 16 entries.  The chains are written level
+  // by level so that consecutive instructions share their multiplier (operand-reuse cache).
+  const F xp01 = X * p01, xp02 = X * p02, xp03 = X * p03, xp12 = X * p12, xp13 = X * p13, xp23 = X * p23;
+  const F yp12 = Y * p12, yp03 = Y * p03;
+  F m00 = -xp01, m11 = xp01, m12 = xp02, m30 = -xp02, m13 = xp03, m20 = xp03;
+  F m02 = -xp12, m31 = -xp12, m03 = -xp13, m21 = xp13, m22 = xp23, m33 = -xp23;
+  F m01 = -yp12, m32 = yp12, m10 = -yp03, m23 = yp03;
+  // second term of every chain
+  m00 = fma_(-Y, p02, m00); m02 = fma_(-Y, p22, m02); m03 = fma_(-Y, p23, m03);
+  m11 = fma_(-Y, p13, m11); m12 = fma_(-Y, p23, m12); m13 = fma_(-Y, p33, m13);
+  m20 = fma_(Y, p00, m20); m21 = fma_(Y, p01, m21); m22 = fma_(Y, p02, m22);
+  m30 = fma_(Y, p01, m30); m31 = fma_(Y, p11, m31); m33 = fma_(Y, p13, m33);
+  m01 = fma_(-X, p11, m01); m10 = fma_(X, p00, m10); m23 = fma_(X, p33, m23); m32 = fma_(-X, p22, m32);
+  // third term
+  m00 = fma_(-Z, p03, m00); m01 = fma_(-Z, p13, m01); m02 = fma_(-Z, p23, m02); m03 = fma_(-Z, p33, m03);
+  m10 = fma_(Z, p02, m10); m11 = fma_(Z, p12, m11); m12 = fma_(Z, p22, m12); m13 = fma_(Z, p23, m13);
+  m20 = fma_(-Z, p01, m20); m21 = fma_(-Z, p11, m21); m22 = fma_(-Z, p12, m22); m23 = fma_(-Z, p13, m23);
+  m30 = fma_(Z, p00, m30); m31 = fma_(Z, p01, m31); m32 = fma_(Z, p02, m32); m33 = fma_(Z, p03, m33);
   Sym4<F> N;
   // N[i][j] = sum_k M[i][k] A[j][k]
   //  j=0: -X M[i][1] - Y M[i][2] - Z M[i][3]     j=1:  X M[i][0] + Z M[i][2] - Y M[i][3]
