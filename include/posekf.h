@@ -44,7 +44,19 @@ extern "C" {
 #define POSEKF_STAGE_TMA_PACKED 3 /* same ring, two filters per thread in packed f32x2 registers (FFMA2);
                                      rank-2 Wahba, N even; what AUTO picks when eligible */
 
-/* Library / build info: returns a static string such as "posekf_b200 0.1 sm_100a". */
+/* State frame flags of posekf_replay_f32 (bit mask).  The kernels run the filter in the coordinates of the
+ * reference frame E = [e1 e2 e3] built from (acc_0, mag_0) -- the recursion is equivariant under a fixed
+ * left rotation of the state, and in that frame the Wahba stage loses its 3x3 matrix product.  By default
+ * (0) state_x / state_x_lo / state_p are read and written in the reference's own coordinates and converted
+ * at both ends of the launch.  A caller that replays in time chunks sets OUT on every launch but the last
+ * and IN on every launch but the first: the state then stays in the filter frame between launches and the
+ * chunked replay equals the unchunked one bit for bit (checkpoint / resume).  A launch with n_steps = 0
+ * and exactly one flag set only converts the state.  Ignored by POSEKF_WAHBA_PRECOMPUTED launches, whose
+ * filter frame is the reference frame. */
+#define POSEKF_STATE_IN_FILTER_FRAME  1
+#define POSEKF_STATE_OUT_FILTER_FRAME 2
+
+/* Library / build info: returns a static string such as "posekf_b200 0.2 sm_100a". */
 const char* posekf_version(void);
 
 /* ---------------------------------------------------------------------------------------------
@@ -92,13 +104,14 @@ const char* posekf_version(void);
  *               trajectories (the tuning workflow of the reference's README, knobs main_file.py:21-22).
  *   wahba_algo  POSEKF_WAHBA_*
  *   staging     POSEKF_STAGE_*
+ *   state_flags POSEKF_STATE_*_FILTER_FRAME bit mask, 0 = state in the reference's coordinates on both sides
  */
 int posekf_replay_f32(int64_t n_filters, int64_t n_steps, const float* streams, int64_t n_streams,
                       const float* dt, int dt_per_step, const float* acc_ref, const float* mag_ref,
                       const float* q_scale, const float* r_scale, float lpf_alpha_acc, float lpf_alpha_mag,
                       float* state_x, float* state_x_lo, float* state_p, float* state_lpf, float* out_traj,
                       uint8_t* out_flip, const float* truth, float* loss_acc, int wahba_algo, int staging,
-                      void* stream);
+                      int state_flags, void* stream);
 
 /* Same replay with HOST buffers: streams_host [T][9][N] is streamed through the device in time
  * chunks (double-buffered H2D copies overlapped with the filter kernel, state carried across

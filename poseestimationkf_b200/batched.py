@@ -79,13 +79,17 @@ class ReplayState:
     """Filter state carried between `replay` calls (time-chunked replay, checkpoint/resume).
     x [4,N]; p [10,N] packed upper triangle of P/r (the covariance in units of each filter's r --
     the form the kernel works in, so that chunked and unchunked replays are bit-identical);
-    r: the float or [N] tensor the scaling refers to; lpf [6,N] or None."""
+    r: the float or [N] tensor the scaling refers to; lpf [6,N] or None.
+    frame: "reference" (x, p in the reference's own coordinates -- what every `replay` call returns by
+    default) or "filter" (left in the kernel's working frame by `replay(..., keep_filter_frame=True)`
+    between the chunks of a time-chunked replay; `to_reference_frame` converts)."""
     x: torch.Tensor
     p: torch.Tensor
     r: object = 0.1
     lpf: torch.Tensor | None = None
     loss: torch.Tensor | None = None     # [N] accumulated tuning objective (see replay(truth=...))
     x_lo: torch.Tensor | None = None     # [4,N] low-order part of the compensated (two-float) state
+    frame: str = "reference"
 
     @staticmethod
     def initial(n_filters: int, device, r=0.1, with_lpf: bool = False, P0: torch.Tensor | None = None) -> "ReplayState":
@@ -108,7 +112,30 @@ class ReplayState:
 
     def clone(self) -> "ReplayState":
         c = lambda t: None if t is None else t.clone()
-        return ReplayState(self.x.clone(), self.p.clone(), self.r, c(self.lpf), c(self.loss), c(self.x_lo))
+        return ReplayState(self.x.clone(), self.p.clone(), self.r, c(self.lpf), c(self.loss), c(self.x_lo), self.frame)
+
+    def to_reference_frame(self, acc_ref: torch.Tensor, mag_ref: torch.Tensor) -> "ReplayState":
+        """Convert (in place) a state that `replay(..., keep_filter_frame=True)` left in the kernel's working
+        frame back to the reference's coordinates.  acc_ref, mag_ref [3,Ns] as given to `replay`."""
+        if self.frame == "filter":
+            _convert_frame(self, acc_ref, mag_ref, FILTER_FRAME_IN)
+            self.frame = "reference"
+        return self
+
+
+FILTER_FRAME_IN, FILTER_FRAME_OUT = 1, 2      # POSEKF_STATE_IN_FILTER_FRAME / POSEKF_STATE_OUT_FILTER_FRAME
+
+
+def _convert_frame(state: "ReplayState", acc_ref, mag_ref, flags: int) -> None:
+    """A zero-step launch that only moves the state between the reference and the filter frame."""
+    _require_cuda(state.x, state.p, state.x_lo, acc_ref, mag_ref)
+    N, Ns, dev = state.x.shape[1], acc_ref.shape[1], state.x.device
+    ones = torch.ones((N,), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        rc = _lib.load().posekf_replay_f32(N, 0, None, Ns, None, 0, _ptr(acc_ref), _ptr(mag_ref), _ptr(ones), _ptr(ones),
+                                           -1.0, -1.0, _ptr(state.x), _ptr(state.x_lo), _ptr(state.p), None, None, None, None,
+                                           None, _lib.WAHBA["qr2"], _lib.STAGING["ldg"], int(flags), _stream())
+    _lib.check(rc, "posekf_replay_f32 (frame conversion)")
 
 
 _scalar_cache: dict = {}
@@ -170,7 +197,7 @@ def replay(streams: torch.Tensor, acc_ref: torch.Tensor, mag_ref: torch.Tensor, 
            lpf_alpha_mag: float | None = None, out_traj: torch.Tensor | None = None, store_trajectory: bool = False,
            store_flips: bool = False, truth: torch.Tensor | None = None, loss: torch.Tensor | None = None,
            precise_state: bool | None = None, share_measurements: bool | None = None, wahba: str = "qr2",
-           staging: str = "auto"):
+           staging: str = "auto", keep_filter_frame: bool = False):
     """Run T Prediction+Correction steps for N filters in one kernel launch.
 
     streams [T,9,Ns]; acc_ref, mag_ref [3,Ns]; dt: float seconds or [T] float32 CUDA tensor;
@@ -186,6 +213,11 @@ def replay(streams: torch.Tensor, acc_ref: torch.Tensor, mag_ref: torch.Tensor, 
     `share_measurements`: in the sweep layout (N > Ns) the Wahba solution of a sample is the same for every
     filter that shares its trajectory, so it is solved once per (trajectory, step) (`measurement_stream`) and
     the replay runs with `wahba="precomputed"`; None = automatic for N >= 4 Ns without a low-pass stage.
+    `keep_filter_frame`: leave `state` in the kernel's working frame (the coordinates of the frame built from
+    acc_ref / mag_ref, in which the Wahba stage is cheapest) instead of converting it back at the end of the
+    launch.  Pass it on every chunk but the last of a time-chunked replay: the chunked replay is then
+    bit-identical to the unchunked one.  `state.frame` records where the state is; a state left in the filter
+    frame is accepted by the next `replay` call and converted by `state.to_reference_frame(acc_ref, mag_ref)`.
     Returns (state, traj [T,N,4] or None, flips [T,N] uint8 or None)."""
     _require_cuda(streams, acc_ref, mag_ref, out_traj)
     if streams.dim() != 3 or streams.shape[1] != 9:
@@ -232,6 +264,12 @@ def replay(streams: torch.Tensor, acc_ref: torch.Tensor, mag_ref: torch.Tensor, 
     else:
         dt_t, per_step = _scalar_tensor(dt, dev), 0
     q_t, r_t = _per_filter(q, N, dev), _per_filter(r, N, dev)
+    if wahba == "precomputed":
+        # no Wahba stage in the kernel: its working frame is the reference frame
+        state.to_reference_frame(acc_ref, mag_ref)
+        frame_flags = 0
+    else:
+        frame_flags = (FILTER_FRAME_IN if state.frame == "filter" else 0) | (FILTER_FRAME_OUT if keep_filter_frame else 0)
     if store_trajectory and out_traj is None:
         out_traj = torch.empty((T, N, 4), dtype=torch.float32, device=dev)
     if out_traj is not None and out_traj.shape != (T, N, 4):
@@ -251,8 +289,10 @@ def replay(streams: torch.Tensor, acc_ref: torch.Tensor, mag_ref: torch.Tensor, 
             -1.0 if lpf_alpha_mag is None else float(lpf_alpha_mag),
             _ptr(state.x), _ptr(state.x_lo if precise_state else None), _ptr(state.p), _ptr(state.lpf), _ptr(out_traj),
             _ptr(flips), _ptr(truth),
-            _ptr(loss if truth is not None else None), _lib.WAHBA[wahba], _lib.STAGING[staging], _stream())
+            _ptr(loss if truth is not None else None), _lib.WAHBA[wahba], _lib.STAGING[staging], frame_flags, _stream())
     _lib.check(rc, "posekf_replay_f32")
+    if wahba != "precomputed":
+        state.frame = "filter" if keep_filter_frame else "reference"
     return state, out_traj, flips
 
 

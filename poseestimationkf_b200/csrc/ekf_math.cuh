@@ -423,8 +423,12 @@ template <typename F> PKF_HD Sym4<F> kalman_gain_sm(const Sym4<F>& M, const Quat
 // decides the reference's answer ("parity unpinned"); here it yields the
 // limit of the rank-2 formula (or NaN if a vector is zero).
 // ------------------------------------------------------------------------------------------
+// wahba_qr2_local returns the rotation IN THE COORDINATES OF THE REFERENCE FRAME E, i.e. E^T R =
+// blockdiag(Uc Vc^T, det) F^T -- twelve multiply-adds instead of the 39 of the full product.  The fused
+// step runs the whole filter in that frame (see "filter frame" below); wahba_qr2 = E * local is the
+// reference's R for the stand-alone entry points.
 template <typename F>
-PKF_HD Mat3<F> wahba_qr2(const RefFrame<F>& E, const Vec3<F>& a, const Vec3<F>& m, F ka, F km) {
+PKF_HD Mat3<F> wahba_qr2_local(const RefFrame<F>& E, const Vec3<F>& a, const Vec3<F>& m, F ka, F km) {
   RefFrame<F> Fb = frame_from_pair(a, m);
   // (every product that feeds a sum is an explicit fma_: nothing is left to the compiler's
   //  contraction heuristics, so the scalar, packed and host builds round identically)
@@ -439,26 +443,55 @@ PKF_HD Mat3<F> wahba_qr2(const RefFrame<F>& E, const Vec3<F>& a, const Vec3<F>& 
   F r = fma_(E.s22, g, -c01);              // c10 - sg c01
   F inv = rsqrt_(fma_(p, p, r * r));
   F cs = p * inv, sn = r * inv;
-  // W = E * blockdiag([[cs, -sg sn],[sn, sg cs]], sg)
-  Vec3<F> w1, w2, w3 = E.e3;
-  w1.x = fma_(sn, E.e2.x, cs * E.e1.x); w1.y = fma_(sn, E.e2.y, cs * E.e1.y); w1.z = fma_(sn, E.e2.z, cs * E.e1.z);
-  w2.x = fma_(cs, E.e2.x, -(sn * E.e1.x)); w2.y = fma_(cs, E.e2.y, -(sn * E.e1.y)); w2.z = fma_(cs, E.e2.z, -(sn * E.e1.z));
+  // rows of blockdiag([[cs, -sg sn],[sn, sg cs]], sg) F^T
+  F g01 = -sn, g11 = cs;
+  Vec3<F> f3 = Fb.e3;
   if (any_(neg)) {
-    w2.x = sel_(neg, -w2.x, w2.x); w2.y = sel_(neg, -w2.y, w2.y); w2.z = sel_(neg, -w2.z, w2.z);
-    w3.x = sel_(neg, -w3.x, w3.x); w3.y = sel_(neg, -w3.y, w3.y); w3.z = sel_(neg, -w3.z, w3.z);
+    g01 = sel_(neg, sn, g01); g11 = sel_(neg, -cs, g11);
+    f3.x = sel_(neg, -f3.x, f3.x); f3.y = sel_(neg, -f3.y, f3.y); f3.z = sel_(neg, -f3.z, f3.z);
   }
+  const Vec3<F>&f1 = Fb.e1, &f2 = Fb.e2;
   Mat3<F> R;
-  const Vec3<F>&f1 = Fb.e1, &f2 = Fb.e2, &f3 = Fb.e3;
-  R.m[0][0] = fma_(w3.x, f3.x, fma_(w2.x, f2.x, w1.x * f1.x));
-  R.m[0][1] = fma_(w3.x, f3.y, fma_(w2.x, f2.y, w1.x * f1.y));
-  R.m[0][2] = fma_(w3.x, f3.z, fma_(w2.x, f2.z, w1.x * f1.z));
-  R.m[1][0] = fma_(w3.y, f3.x, fma_(w2.y, f2.x, w1.y * f1.x));
-  R.m[1][1] = fma_(w3.y, f3.y, fma_(w2.y, f2.y, w1.y * f1.y));
-  R.m[1][2] = fma_(w3.y, f3.z, fma_(w2.y, f2.z, w1.y * f1.z));
-  R.m[2][0] = fma_(w3.z, f3.x, fma_(w2.z, f2.x, w1.z * f1.x));
-  R.m[2][1] = fma_(w3.z, f3.y, fma_(w2.z, f2.y, w1.z * f1.y));
-  R.m[2][2] = fma_(w3.z, f3.z, fma_(w2.z, f2.z, w1.z * f1.z));
+  R.m[0][0] = fma_(g01, f2.x, cs * f1.x); R.m[0][1] = fma_(g01, f2.y, cs * f1.y); R.m[0][2] = fma_(g01, f2.z, cs * f1.z);
+  R.m[1][0] = fma_(g11, f2.x, sn * f1.x); R.m[1][1] = fma_(g11, f2.y, sn * f1.y); R.m[1][2] = fma_(g11, f2.z, sn * f1.z);
+  R.m[2][0] = f3.x; R.m[2][1] = f3.y; R.m[2][2] = f3.z;
   return R;
+}
+
+// columns of E times the rows of a local-frame matrix:  R = E L
+template <typename F> PKF_HD Mat3<F> frame_times(const RefFrame<F>& E, const Mat3<F>& L) {
+  Mat3<F> R;
+  const F ex[3] = {E.e1.x, E.e1.y, E.e1.z}, ey[3] = {E.e2.x, E.e2.y, E.e2.z}, ez[3] = {E.e3.x, E.e3.y, E.e3.z};
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int i = 0; i < 3; ++i) {
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int j = 0; j < 3; ++j) R.m[i][j] = fma_(ez[i], L.m[2][j], fma_(ey[i], L.m[1][j], ex[i] * L.m[0][j]));
+  }
+  return R;
+}
+// E^T R: a reference-frame rotation expressed in the coordinates of E
+template <typename F> PKF_HD Mat3<F> frame_transposed_times(const RefFrame<F>& E, const Mat3<F>& R) {
+  Mat3<F> L;
+  const Vec3<F> e[3] = {E.e1, E.e2, E.e3};
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int k = 0; k < 3; ++k) {
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int j = 0; j < 3; ++j) L.m[k][j] = fma_(e[k].z, R.m[2][j], fma_(e[k].y, R.m[1][j], e[k].x * R.m[0][j]));
+  }
+  return L;
+}
+
+template <typename F>
+PKF_HD Mat3<F> wahba_qr2(const RefFrame<F>& E, const Vec3<F>& a, const Vec3<F>& m, F ka, F km) {
+  return frame_times(E, wahba_qr2_local(E, a, m, ka, km));
 }
 
 // ------------------------------------------------------------------------------------------
@@ -604,6 +637,60 @@ template <typename F> PKF_HD Quat<F> rotation_to_quat_ref(const Mat3<F>& M) {
   return q;
 }
 
+// Rotation matrix -> unit quaternion of EITHER sign from the best-conditioned Shepperd candidate; no
+// reference sign rule and no NaN at the identity (used for the filter-frame quaternion of E).
+template <typename F> PKF_HD Quat<F> rotation_to_quat_best(const Mat3<F>& M) {
+  const F r00 = M.m[0][0], r11 = M.m[1][1], r22 = M.m[2][2];
+  F tr1 = F(1) + r00 - r11 - r22, tr2 = F(1) - r00 + r11 - r22, tr3 = F(1) - r00 - r11 + r22, tr0 = F(1) + r00 + r11 + r22;
+  F dx = M.m[2][1] - M.m[1][2], dy = M.m[0][2] - M.m[2][0], dz = M.m[1][0] - M.m[0][1];
+  F sxy = M.m[0][1] + M.m[1][0], sxz = M.m[0][2] + M.m[2][0], syz = M.m[1][2] + M.m[2][1];
+  auto w_gt_x = tr0 > tr1, y_gt_z = tr2 > tr3;
+  F mwx = sel_(w_gt_x, tr0, tr1), myz = sel_(y_gt_z, tr2, tr3);
+  auto lo = mwx > myz;
+  auto kw = lo && w_gt_x, kx = lo && !w_gt_x, ky = !lo && y_gt_z;
+  Quat<F> c;
+  c.w = sel_(kw, tr0, sel_(kx, dx, sel_(ky, dy, dz)));
+  c.x = sel_(kw, dx, sel_(kx, tr1, sel_(ky, sxy, sxz)));
+  c.y = sel_(kw, dy, sel_(kx, sxy, sel_(ky, tr2, syz)));
+  c.z = sel_(kw, dz, sel_(kx, sxz, sel_(ky, syz, tr3)));
+  F inv = rsqrt_(dot4(c, c));
+  c.w *= inv; c.x *= inv; c.y *= inv; c.z *= inv;
+  return c;
+}
+
+// Hamilton product a (x) b, scalar first
+template <typename F> PKF_HD Quat<F> qmul(const Quat<F>& a, const Quat<F>& b) {
+  Quat<F> c;
+  c.w = fma_(-a.z, b.z, fma_(-a.y, b.y, fma_(-a.x, b.x, a.w * b.w)));
+  c.x = fma_(-a.z, b.y, fma_(a.y, b.z, fma_(a.x, b.w, a.w * b.x)));
+  c.y = fma_(a.z, b.x, fma_(a.y, b.w, fma_(-a.x, b.z, a.w * b.y)));
+  c.z = fma_(a.z, b.w, fma_(-a.y, b.x, fma_(a.x, b.y, a.w * b.z)));
+  return c;
+}
+template <typename F> PKF_HD Quat<F> qconj(const Quat<F>& a) { Quat<F> c = {a.w, -a.x, -a.y, -a.z}; return c; }
+
+// L(p) P L(p)^T for the left-multiplication matrix L(p) of a unit quaternion p (orthogonal), P symmetric:
+// the covariance of p (x) x when P is the covariance of x.
+template <typename F> PKF_HD Sym4<F> rotate_cov(const Quat<F>& p, const Sym4<F>& P) {
+  const F a = p.w, b = p.x, c = p.y, d = p.z;
+  const F L[4][4] = {{a, -b, -c, -d}, {b, a, -d, c}, {c, d, a, -b}, {d, -c, b, a}};
+  const F S[4][4] = {{P.a00, P.a01, P.a02, P.a03}, {P.a01, P.a11, P.a12, P.a13}, {P.a02, P.a12, P.a22, P.a23},
+                     {P.a03, P.a13, P.a23, P.a33}};
+  F M[4][4];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int i = 0; i < 4; ++i) {
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int j = 0; j < 4; ++j) M[i][j] = fma_(L[i][3], S[3][j], fma_(L[i][2], S[2][j], fma_(L[i][1], S[1][j], L[i][0] * S[0][j])));
+  }
+  auto e = [&](int i, int j) { return fma_(M[i][3], L[j][3], fma_(M[i][2], L[j][2], fma_(M[i][1], L[j][1], M[i][0] * L[j][0]))); };
+  Sym4<F> N = {e(0, 0), e(0, 1), e(0, 2), e(0, 3), e(1, 1), e(1, 2), e(1, 3), e(2, 2), e(2, 3), e(3, 3)};
+  return N;
+}
+
 // ------------------------------------------------------------------------------------------
 // Rotation matrix -> quaternion ALIGNED WITH A PREDICTION z (fused-step form).
 // For a rotation M = R(y) the symmetric 4x4 matrix built from the four Shepperd candidates is
@@ -641,6 +728,21 @@ template <typename F> PKF_HD auto reference_flip(const Mat3<F>& M, const Quat<F>
   return sel_(b1, y.x, sel_(b2, y.y, y.z)) < F(0);
 }
 
+// Same decision when the rotation Ml and the aligned measurement yl are given in the filter frame: the
+// reference's branch rule looks at the diagonal of R = E Ml and at the components of qE (x) yl.
+template <typename F, typename FC>
+PKF_HD auto reference_flip_local(const FC& fc, const Mat3<F>& Ml, const Quat<F>& yl) -> decltype(yl.w < yl.w) {
+  const RefFrame<F>& E = fc.E;
+  const F r00 = fma_(E.e3.x, Ml.m[2][0], fma_(E.e2.x, Ml.m[1][0], E.e1.x * Ml.m[0][0]));
+  const F r11 = fma_(E.e3.y, Ml.m[2][1], fma_(E.e2.y, Ml.m[1][1], E.e1.y * Ml.m[0][1]));
+  const F r22 = fma_(E.e3.z, Ml.m[2][2], fma_(E.e2.z, Ml.m[1][2], E.e1.z * Ml.m[0][2]));
+  F tr1 = F(1) + r00 - r11 - r22, tr2 = F(1) - r00 + r11 - r22, tr3 = F(1) - r00 - r11 + r22;
+  auto b1 = (tr1 > tr2) && (tr1 > tr3);
+  auto b2 = !b1 && ((tr2 > tr1) && (tr2 > tr3));
+  const Quat<F> y = qmul(fc.qE, yl);
+  return sel_(b1, y.x, sel_(b2, y.y, y.z)) < F(0);
+}
+
 // ------------------------------------------------------------------------------------------
 // One fused filter step (Prediction + Correction, PKF/main_file.py:39,43), scalar Q and R.
 // The covariance argument P is carried IN UNITS OF r (P/r): with R = r I the whole recursion is
@@ -658,6 +760,7 @@ template <typename F> struct FilterConst {
   RefFrame<F> E;          // from (acc_0, mag_0)
   Vec3<F> ra, rm;         // raw reference vectors (used by the Jacobi variant only)
   F g;                    // Q/(4R): process noise in units of r
+  Quat<F> qE;             // unit quaternion of the rotation [e1 e2 e3]: filter frame -> reference frame
 };
 
 PKF_HD void quat_fallback_unaligned(const Mat3<float>& Rm, const Quat<float>& z, bool, Quat<float>& y) {
@@ -721,14 +824,15 @@ PKF_HD void ekf_step(Quat<F>& x, Quat<F>& xlo, Sym4<F>& P, const FilterConst<F>&
     e0 = fma_(sg, y.w, -z.w); e1 = fma_(sg, y.x, -z.x); e2 = fma_(sg, y.y, -z.y); e3 = fma_(sg, y.z, -z.z);   // :76
   } else {
     F ka = abs_(acc.z), km = F(1) - ka;                                       // :71
+    // Rm: the Wahba rotation in the filter frame (E^T R)
     Mat3<F> Rm;
-    if constexpr (ALGO == WAHBA_QR2) Rm = wahba_qr2(fc.E, acc, mag, ka, km);
-    else Rm = wahba_jacobi(fc.ra, fc.rm, acc, mag, ka, km, kJacobiSweepsFused);
+    if constexpr (ALGO == WAHBA_QR2) Rm = wahba_qr2_local(fc.E, acc, mag, ka, km);
+    else Rm = frame_transposed_times(fc.E, wahba_jacobi(fc.ra, fc.rm, acc, mag, ka, km, kJacobiSweepsFused));
     // measurement quaternion with the comparator's sign already applied          :73-75
     F n2;
     Quat<F> y = rotation_to_quat_aligned(Rm, z, n2);     // un-normalised: 4 (y.z) y
     flip = FlagT();
-    if (WANT_FLIP && flip_wanted) flip = reference_flip(Rm, y);         // only the signs of y matter
+    if (WANT_FLIP && flip_wanted) flip = reference_flip_local(fc, Rm, y);   // only the signs of y matter
     // innovation e = y/|y| - z, the normalisation folded into the subtraction     :76
     const F inv = rsqrt_(n2);
     e0 = fma_(y.w, inv, -z.w); e1 = fma_(y.x, inv, -z.x); e2 = fma_(y.y, inv, -z.y); e3 = fma_(y.z, inv, -z.z);
@@ -738,7 +842,7 @@ PKF_HD void ekf_step(Quat<F>& x, Quat<F>& xlo, Sym4<F>& P, const FilterConst<F>&
       // on the first sample of a badly initialised one).  Use the selection-based conversion there.
       Quat<F> yf = y;
       quat_fallback_unaligned(Rm, z, unrelated, yf);
-      if (WANT_FLIP && flip_wanted) flip = reference_flip(Rm, yf);
+      if (WANT_FLIP && flip_wanted) flip = reference_flip_local(fc, Rm, yf);
       e0 = sel_(unrelated, yf.w - z.w, e0); e1 = sel_(unrelated, yf.x - z.x, e1);
       e2 = sel_(unrelated, yf.y - z.y, e2); e3 = sel_(unrelated, yf.z - z.z, e3);
     }
@@ -775,7 +879,43 @@ PKF_HD FilterConst<F> make_filter_const(const Vec3<F>& acc_ref, const Vec3<F>& m
   fc.E = frame_from_pair(acc_ref, mag_ref);
   fc.ra = acc_ref; fc.rm = mag_ref;
   fc.g = (F(0.25) * q) / r;
+  Mat3<F> Em;
+  Em.m[0][0] = fc.E.e1.x; Em.m[1][0] = fc.E.e1.y; Em.m[2][0] = fc.E.e1.z;
+  Em.m[0][1] = fc.E.e2.x; Em.m[1][1] = fc.E.e2.y; Em.m[2][1] = fc.E.e2.z;
+  Em.m[0][2] = fc.E.e3.x; Em.m[1][2] = fc.E.e3.y; Em.m[2][2] = fc.E.e3.z;
+  fc.qE = rotation_to_quat_best(Em);
   return fc;
+}
+
+// ------------------------------------------------------------------------------------------
+// FILTER FRAME.  The whole recursion is equivariant under a fixed left rotation of the state: with
+// x' = p (x) x and P' = L(p) P L(p)^T (L orthogonal), RK4 (a right multiplication) commutes with L(p),
+// B Q B^T = (q/4)(|x|^2 I - x x^T) and R = r I transform covariantly, the gain is a spectral function of
+// P, and the comparator's dot product is invariant.  The fused step therefore runs in the coordinates of
+// the reference frame E = [e1 e2 e3] built from (acc_0, mag_0), p = conj(qE): there the Wahba rotation
+// is blockdiag(G, det G) F^T (wahba_qr2_local) and the 27 multiply-adds of E * (...) per step disappear.
+// State enters and leaves the frame once per launch (or not at all when the caller keeps it there between
+// launches, see POSEKF_STATE_*_FILTER_FRAME); outputs per step (trajectory, flip mask, loss) are mapped back.
+// WAHBA_PRECOMPUTED launches have no Wahba stage: their filter frame IS the reference frame.
+// ------------------------------------------------------------------------------------------
+template <int ALGO> PKF_HD constexpr bool uses_filter_frame() { return ALGO != WAHBA_PRECOMPUTED; }
+
+template <typename F>
+PKF_HD void enter_filter_frame(const FilterConst<F>& fc, Quat<F>& x, Quat<F>& xlo, Sym4<F>& P, bool comp) {
+  const Quat<F> p = qconj(fc.qE);
+  x = qmul(p, x);
+  if (comp) xlo = qmul(p, xlo);
+  P = rotate_cov(p, P);
+}
+template <typename F>
+PKF_HD void leave_filter_frame(const FilterConst<F>& fc, Quat<F>& x, Quat<F>& xlo, Sym4<F>& P, bool comp) {
+  x = qmul(fc.qE, x);
+  if (comp) xlo = qmul(fc.qE, xlo);
+  P = rotate_cov(fc.qE, P);
+}
+// the state of one step in the reference frame (what the reference's X_k list holds)
+template <typename F> PKF_HD Quat<F> state_in_reference_frame(const FilterConst<F>& fc, const Quat<F>& x) {
+  return qmul(fc.qE, x);
 }
 
 // ------------------------------------------------------------------------------------------

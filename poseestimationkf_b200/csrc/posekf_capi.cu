@@ -170,16 +170,25 @@ inline unsigned blocks_for(int64_t n, int threads) { return (unsigned)((n + thre
 // =============================================================================================
 extern "C" {
 
-const char* posekf_version(void) { return "posekf_b200 0.1 sm_100a"; }
+const char* posekf_version(void) { return "posekf_b200 0.2 sm_100a"; }
 
 int posekf_replay_f32(int64_t n_filters, int64_t n_steps, const float* streams, int64_t n_streams, const float* dt,
                       int dt_per_step, const float* acc_ref, const float* mag_ref, const float* q_scale,
                       const float* r_scale, float lpf_alpha_acc, float lpf_alpha_mag, float* state_x, float* state_x_lo,
                       float* state_p, float* state_lpf, float* out_traj, uint8_t* out_flip, const float* truth, float* loss_acc,
-                      int wahba_algo, int staging, void* stream) {
+                      int wahba_algo, int staging, int state_flags, void* stream) {
   if (n_filters < 0 || n_steps < 0 || n_streams <= 0 && n_filters > 0) return POSEKF_EINVAL;
-  if (n_filters == 0 || n_steps == 0) return 0;
-  if (!streams || !dt || !acc_ref || !mag_ref || !q_scale || !r_scale || !state_x || !state_p) return POSEKF_EINVAL;
+  if (state_flags & ~(POSEKF_STATE_IN_FILTER_FRAME | POSEKF_STATE_OUT_FILTER_FRAME)) return POSEKF_EINVAL;
+  if (n_filters == 0) return 0;
+  if (n_steps == 0) {
+    // nothing to replay; a launch is still needed when the state has to change frames
+    const bool in_f = state_flags & POSEKF_STATE_IN_FILTER_FRAME, out_f = state_flags & POSEKF_STATE_OUT_FILTER_FRAME;
+    if (in_f == out_f || wahba_algo == POSEKF_WAHBA_PRECOMPUTED) return 0;
+    if (!acc_ref || !mag_ref || !q_scale || !r_scale || !state_x || !state_p) return POSEKF_EINVAL;
+    if (n_streams > n_filters || (n_filters % n_streams) != 0) return POSEKF_EINVAL;
+    staging = POSEKF_STAGE_LDG;
+  } else if (!streams || !dt) return POSEKF_EINVAL;
+  if (!acc_ref || !mag_ref || !q_scale || !r_scale || !state_x || !state_p) return POSEKF_EINVAL;
   if (n_streams > n_filters || (n_filters % n_streams) != 0) return POSEKF_EINVAL;
   const bool lpf = lpf_alpha_acc >= 0.f || lpf_alpha_mag >= 0.f;
   if (lpf && !state_lpf) return POSEKF_EINVAL;
@@ -194,6 +203,7 @@ int posekf_replay_f32(int64_t n_filters, int64_t n_steps, const float* streams, 
   p.alpha_acc = lpf_alpha_acc; p.alpha_mag = lpf_alpha_mag;
   p.state_x = state_x; p.state_x_lo = state_x_lo; p.state_p = state_p; p.state_lpf = state_lpf; p.out_traj = out_traj; p.out_flip = out_flip;
   p.truth = truth; p.loss_acc = loss_acc;
+  p.state_flags = state_flags;
   return replay_dispatch(p, wahba_algo, staging, (cudaStream_t)stream);
 }
 
@@ -334,9 +344,11 @@ int posekf_replay_host_f32(int64_t N, int64_t T, const float* streams_host, floa
     if (c + 1 < n_chunks) TRY(issue_copy(c + 1));                             // keep the copy engine one chunk ahead
     TRY(cudaStreamWaitEvent(s_comp, w->ev_in[b], 0));
     if (traj && c >= 2) TRY(cudaStreamWaitEvent(s_comp, w->ev_tfree[b], 0));  // D2H of chunk c-2 done with d_traj[b]
+    // the state stays in the filter frame between chunks, so that chunking does not change a single bit
+    const int frames = (c > 0 ? POSEKF_STATE_IN_FILTER_FRAME : 0) | (c + 1 < n_chunks ? POSEKF_STATE_OUT_FILTER_FRAME : 0);
     rc = posekf_replay_f32(N, tc, w->d_in[b], N, d_dt, 0, d_ref, d_ref + 3 * N, d_qr, d_qr + N, lpf_alpha_acc,
                            lpf_alpha_mag, d_x, d_xlo, d_p, d_lpf, traj ? w->d_traj[b] : nullptr, nullptr, nullptr, nullptr,
-                           wahba_algo, POSEKF_STAGE_AUTO, s_comp);
+                           wahba_algo, POSEKF_STAGE_AUTO, frames, s_comp);
     if (rc != 0) { if (own) host_ws_free(w); return rc; }
     TRY(cudaEventRecord(w->ev_free[b], s_comp));
     if (traj) {

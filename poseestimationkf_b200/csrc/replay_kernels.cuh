@@ -26,7 +26,9 @@ struct ReplayParams {
   uint8_t* out_flip;
   const float* truth;   // [T][Ns][4] reference track for the tuning objective, or null
   float* loss_acc;      // [N] in/out: sum over steps of 1 - (x . truth)^2
+  int state_flags;      // POSEKF_STATE_IN_FILTER_FRAME | POSEKF_STATE_OUT_FILTER_FRAME (include/posekf.h)
 };
+constexpr int kStateInFilterFrame = 1, kStateOutFilterFrame = 2;
 
 struct FilterRegs {
   Quat<float> x;
@@ -36,7 +38,7 @@ struct FilterRegs {
   Vec3<float> la, lm;   // low-pass state
 };
 
-template <bool LPF, bool COMP>
+template <int ALGO, bool LPF, bool COMP>
 __device__ __forceinline__ void load_filter(const ReplayParams& p, int64_t n, int64_t col, FilterRegs& f) {
   const int64_t N = p.N, Ns = p.Ns;
   Vec3<float> ra = {p.acc_ref[col], p.acc_ref[Ns + col], p.acc_ref[2 * Ns + col]};
@@ -52,11 +54,14 @@ __device__ __forceinline__ void load_filter(const ReplayParams& p, int64_t n, in
     f.la = {sl[0], sl[N], sl[2 * N]};
     f.lm = {sl[3 * N], sl[4 * N], sl[5 * N]};
   }
+  // the step runs in the filter frame (ekf_math.cuh); the state buffers hold the reference frame unless flagged
+  if (uses_filter_frame<ALGO>() && !(p.state_flags & kStateInFilterFrame)) enter_filter_frame(f.fc, f.x, f.xlo, f.P, COMP);
 }
 
-template <bool LPF, bool COMP>
-__device__ __forceinline__ void store_filter(const ReplayParams& p, int64_t n, const FilterRegs& f) {
+template <int ALGO, bool LPF, bool COMP>
+__device__ __forceinline__ void store_filter(const ReplayParams& p, int64_t n, FilterRegs& f) {
   const int64_t N = p.N;
+  if (uses_filter_frame<ALGO>() && !(p.state_flags & kStateOutFilterFrame)) leave_filter_frame(f.fc, f.x, f.xlo, f.P, COMP);
   p.state_x[n] = f.x.w; p.state_x[N + n] = f.x.x; p.state_x[2 * N + n] = f.x.y; p.state_x[3 * N + n] = f.x.z;
   if (COMP) {
     p.state_x_lo[n] = f.xlo.w; p.state_x_lo[N + n] = f.xlo.x; p.state_x_lo[2 * N + n] = f.xlo.y; p.state_x_lo[3 * N + n] = f.xlo.z;
@@ -99,9 +104,12 @@ __device__ __forceinline__ void filter_step(const ReplayParams& p, FilterRegs& f
   bool flip;
   ekf_step<float, ALGO, AUX, COMP>(f.x, f.xlo, f.P, f.fc, w, a, m, h, flip, aux.flips != nullptr);
   if (AUX) {
+    // per-step outputs are in the reference frame (the reference's X_k)
+    Quat<float> xr = f.x;
+    if (uses_filter_frame<ALGO>() && (aux.traj || aux.truth)) xr = state_in_reference_frame(f.fc, f.x);
     if (aux.traj) {   // [T][N][4]: one 16-byte store per filter-step, consecutive filters consecutive
-      asm volatile("st.global.cs.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(aux.traj), "f"(f.x.w), "f"(f.x.x), "f"(f.x.y),
-                   "f"(f.x.z)
+      asm volatile("st.global.cs.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(aux.traj), "f"(xr.w), "f"(xr.x), "f"(xr.y),
+                   "f"(xr.z)
                    : "memory");
       aux.traj += p.N;
     }
@@ -112,7 +120,7 @@ __device__ __forceinline__ void filter_step(const ReplayParams& p, FilterRegs& f
       // sin^2 of the angle as the squared 4-D wedge product |X ^ q_ref|^2 = |X|^2 |q_ref|^2 - (X.q_ref)^2
       // (Lagrange identity): the six 2x2 minors are small numbers computed without the 1 - d^2
       // cancellation and without sensitivity to the 1e-7 norm error of either quaternion.
-      const float xw = f.x.w, xx = f.x.x, xy = f.x.y, xz = f.x.z, qw = qt.x, qx = qt.y, qy = qt.z, qz = qt.w;
+      const float xw = xr.w, xx = xr.x, xy = xr.y, xz = xr.z, qw = qt.x, qx = qt.y, qy = qt.z, qz = qt.w;
       const float m01 = fmaf(xw, qx, -(xx * qw)), m02 = fmaf(xw, qy, -(xy * qw)), m03 = fmaf(xw, qz, -(xz * qw));
       const float m12 = fmaf(xx, qy, -(xy * qx)), m13 = fmaf(xx, qz, -(xz * qx)), m23 = fmaf(xy, qz, -(xz * qy));
       aux.loss += fmaf(m23, m23, fmaf(m13, m13, fmaf(m12, m12, fmaf(m03, m03, fmaf(m02, m02, m01 * m01)))));
@@ -125,22 +133,22 @@ __device__ __forceinline__ void filter_step(const ReplayParams& p, FilterRegs& f
 // current one is computed.
 // ---------------------------------------------------------------------------------------------
 template <int ALGO, bool LPF, bool AUX, bool COMP>
-__global__ void __launch_bounds__(kThreads, ALGO == WAHBA_JACOBI ? 4 : ((COMP || LPF) ? (kMinCtasPerSm > 5 ? 5 : kMinCtasPerSm) : kMinCtasPerSm))
+__global__ void __launch_bounds__(kThreads, (ALGO == WAHBA_JACOBI || (COMP && LPF && AUX)) ? 4 : ((COMP || LPF) ? (kMinCtasPerSm > 5 ? 5 : kMinCtasPerSm) : kMinCtasPerSm))
     replay_ldg_kernel(const ReplayParams p) {
   const int64_t n = (int64_t)blockIdx.x * kThreads + threadIdx.x;
   if (n >= p.N) return;
   const int64_t Ns = p.Ns;
   const int64_t col = (Ns == p.N) ? n : (n % Ns);
   FilterRegs f;
-  load_filter<LPF, COMP>(p, n, col, f);
+  load_filter<ALGO, LPF, COMP>(p, n, col, f);
   AuxPtrs aux = make_aux<AUX>(p, n, col, true);
   const float* s = p.streams + col;
   const int64_t step_stride = kChannels * Ns;
   float cur[kChannels], nxt[kChannels];
+  const int T = (int)p.T;     // T == 0: a frame conversion of the state only (no stream is read)
 #pragma unroll
-  for (int c = 0; c < kChannels; ++c) cur[c] = ldg_stream(s + c * Ns);
-  const float dt0 = p.dt[0];
-  const int T = (int)p.T;
+  for (int c = 0; c < kChannels; ++c) cur[c] = T > 0 ? ldg_stream(s + c * Ns) : 0.f;
+  const float dt0 = T > 0 ? p.dt[0] : 0.f;
   for (int t = 0; t < T; ++t) {
     if (t + 1 < T) s += step_stride;
 #pragma unroll
@@ -150,7 +158,7 @@ __global__ void __launch_bounds__(kThreads, ALGO == WAHBA_JACOBI ? 4 : ((COMP ||
 #pragma unroll
     for (int c = 0; c < kChannels; ++c) cur[c] = nxt[c];
   }
-  store_filter<LPF, COMP>(p, n, f);
+  store_filter<ALGO, LPF, COMP>(p, n, f);
   if (AUX && aux.truth) p.loss_acc[n] = aux.loss;
 }
 
@@ -168,7 +176,7 @@ struct __align__(128) TmaSmem {
 constexpr uint32_t kTileBytes = kTmaSteps * kChannels * kThreads * sizeof(float);
 
 template <int ALGO, bool LPF, bool AUX, bool COMP>
-__global__ void __launch_bounds__(kThreads, (COMP && (LPF || AUX)) ? (kMinCtasPerSm > 5 ? 5 : kMinCtasPerSm) : kMinCtasPerSm)
+__global__ void __launch_bounds__(kThreads, ALGO == WAHBA_JACOBI ? 4 : ((COMP && (LPF || AUX)) ? (kMinCtasPerSm > 5 ? 5 : kMinCtasPerSm) : kMinCtasPerSm))
     replay_tma_kernel(const ReplayParams p, const __grid_constant__ CUtensorMap tmap) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   TmaSmem& sm = *reinterpret_cast<TmaSmem*>(smem_raw);
@@ -198,7 +206,7 @@ __global__ void __launch_bounds__(kThreads, (COMP && (LPF || AUX)) ? (kMinCtasPe
   }
 
   FilterRegs f;
-  if (valid) load_filter<LPF, COMP>(p, n, (int64_t)col0 + tid, f);
+  if (valid) load_filter<ALGO, LPF, COMP>(p, n, (int64_t)col0 + tid, f);
   AuxPtrs aux = make_aux<AUX>(p, n, (int64_t)col0 + tid, valid);
   const float dt0 = p.dt[0];
 
@@ -231,7 +239,7 @@ __global__ void __launch_bounds__(kThreads, (COMP && (LPF || AUX)) ? (kMinCtasPe
     if ((tid & 31) == 0) mbar_arrive(&sm.empty[stage]);
     if (++stage == kTmaStages) { stage = 0; parity ^= 1; }
   }
-  if (valid) store_filter<LPF, COMP>(p, n, f);
+  if (valid) store_filter<ALGO, LPF, COMP>(p, n, f);
   if (AUX && valid && aux.truth) p.loss_acc[n] = aux.loss;
 }
 
@@ -303,6 +311,7 @@ __global__ void __launch_bounds__(kThreads2, (LPF && COMP) ? (PKF_MIN_CTAS2 > 6 
       f.la = {ld2(sl), ld2(sl + N), ld2(sl + 2 * N)};
       f.lm = {ld2(sl + 3 * N), ld2(sl + 4 * N), ld2(sl + 5 * N)};
     }
+    if (uses_filter_frame<ALGO>() && !(p.state_flags & kStateInFilterFrame)) enter_filter_frame(f.fc, f.x, f.xlo, f.P, COMP);
   }
   const float dt0 = p.dt[0];
   // auxiliary outputs: this thread's pair of adjacent slots
@@ -344,11 +353,13 @@ __global__ void __launch_bounds__(kThreads2, (LPF && COMP) ? (PKF_MIN_CTAS2 > 6 
           mask2 flip;
           ekf_step<f32x2, ALGO, AUX, COMP>(f.x, f.xlo, f.P, f.fc, w, a, m, f32x2(h), flip, flips != nullptr);
           if (AUX) {
+            Quat<f32x2> xr = f.x;     // per-step outputs are in the reference frame
+            if (uses_filter_frame<ALGO>() && (traj || truth)) xr = state_in_reference_frame(f.fc, f.x);
             if (traj) {   // [T][N][4]: two adjacent 16-byte quaternions
-              asm volatile("st.global.cs.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(traj), "f"(f.x.w.x), "f"(f.x.x.x), "f"(f.x.y.x),
-                           "f"(f.x.z.x) : "memory");
-              asm volatile("st.global.cs.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(traj + 1), "f"(f.x.w.y), "f"(f.x.x.y),
-                           "f"(f.x.y.y), "f"(f.x.z.y) : "memory");
+              asm volatile("st.global.cs.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(traj), "f"(xr.w.x), "f"(xr.x.x), "f"(xr.y.x),
+                           "f"(xr.z.x) : "memory");
+              asm volatile("st.global.cs.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(traj + 1), "f"(xr.w.y), "f"(xr.x.y),
+                           "f"(xr.y.y), "f"(xr.z.y) : "memory");
               traj += N;
             }
             if (flips) { *reinterpret_cast<uchar2*>(flips) = make_uchar2(flip.x ? 1 : 0, flip.y ? 1 : 0); flips += N; }
@@ -356,7 +367,7 @@ __global__ void __launch_bounds__(kThreads2, (LPF && COMP) ? (PKF_MIN_CTAS2 > 6 
               const float4 t0 = __ldg(truth), t1 = __ldg(truth + 1);
               truth += Ns;
               const f32x2 qw(t0.x, t1.x), qx(t0.y, t1.y), qy(t0.z, t1.z), qz(t0.w, t1.w);
-              const f32x2 xw = f.x.w, xx = f.x.x, xy = f.x.y, xz = f.x.z;
+              const f32x2 xw = xr.w, xx = xr.x, xy = xr.y, xz = xr.z;
               const f32x2 m01 = fma_(xw, qx, -(xx * qw)), m02 = fma_(xw, qy, -(xy * qw)), m03 = fma_(xw, qz, -(xz * qw));
               const f32x2 m12 = fma_(xx, qy, -(xy * qx)), m13 = fma_(xx, qz, -(xz * qx)), m23 = fma_(xy, qz, -(xz * qy));
               loss = loss + fma_(m23, m23, fma_(m13, m13, fma_(m12, m12, fma_(m03, m03, fma_(m02, m02, m01 * m01)))));
@@ -370,6 +381,7 @@ __global__ void __launch_bounds__(kThreads2, (LPF && COMP) ? (PKF_MIN_CTAS2 > 6 
     if (++stage == kTma2Stages) { stage = 0; parity ^= 1; }
   }
   if (valid) {
+    if (uses_filter_frame<ALGO>() && !(p.state_flags & kStateOutFilterFrame)) leave_filter_frame(f.fc, f.x, f.xlo, f.P, COMP);
     st2(p.state_x + n, f.x.w); st2(p.state_x + N + n, f.x.x); st2(p.state_x + 2 * N + n, f.x.y); st2(p.state_x + 3 * N + n, f.x.z);
     if (COMP) {
       st2(p.state_x_lo + n, f.xlo.w); st2(p.state_x_lo + N + n, f.xlo.x); st2(p.state_x_lo + 2 * N + n, f.xlo.y);

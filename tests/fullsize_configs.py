@@ -112,7 +112,7 @@ if "c5" in which:
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        B.replay(buf[: t1 - t0], acc_ref, mag_ref, dt=base.dt, q=q, r=r, state=st, precise_state=False)
+        B.replay(buf[: t1 - t0], acc_ref, mag_ref, dt=base.dt, q=q, r=r, state=st, precise_state=False, keep_filter_frame=t1 < T)
         e1.record(); torch.cuda.synchronize()
         total_ms += e0.elapsed_time(e1)
     ref = CO.replay(base.streams[:, :, :512].cpu().numpy(), base.dt * 1e9, base.acc_ref[:, :512].cpu().numpy(),

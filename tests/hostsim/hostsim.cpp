@@ -22,6 +22,7 @@ static void replay_t(int64_t N, int64_t T, const float* streams, const double* d
     const F ir = F(1) / (F)r[n];   // the step carries P/r
     Sym4<F> P = {ir, F(0), F(0), F(0), ir, F(0), F(0), ir, F(0), ir};
     Vec3<F> la = {F(0), F(0), F(0)}, lm = {F(0), F(0), F(0)};
+    enter_filter_frame(fc, x, xlo, P, COMP);     // as the kernels do at the start of a launch
     for (int64_t t = 0; t < T; ++t) {
       const float* s = streams + (size_t)t * 9 * N + n;
       Vec3<F> w = {(F)s[0 * N], (F)s[1 * N], (F)s[2 * N]};
@@ -33,11 +34,13 @@ static void replay_t(int64_t N, int64_t T, const float* streams, const double* d
       bool flip;
       ekf_step<F, ALGO, true, COMP>(x, xlo, P, fc, w, a, m, h, flip);
       if (out_traj) {
+        const Quat<F> xr = state_in_reference_frame(fc, x);
         double* o = out_traj + (size_t)t * 4 * N + n;
-        o[0 * N] = x.w; o[1 * N] = x.x; o[2 * N] = x.y; o[3 * N] = x.z;
+        o[0 * N] = xr.w; o[1 * N] = xr.x; o[2 * N] = xr.y; o[3 * N] = xr.z;
       }
       if (out_flip) out_flip[(size_t)t * N + n] = flip;
     }
+    leave_filter_frame(fc, x, xlo, P, COMP);
     if (out_P) {
       const F p[10] = {P.a00, P.a01, P.a02, P.a03, P.a11, P.a12, P.a13, P.a22, P.a23, P.a33};
       for (int k = 0; k < 10; ++k) out_P[(size_t)k * N + n] = (F)r[n] * p[k];
@@ -60,6 +63,7 @@ static void replay_packed_t(int64_t N, int64_t T, const float* streams, const do
     const F ir = F(1.f / r[n], 1.f / r[n + 1]);
     Sym4<F> P = {ir, F(0.f), F(0.f), F(0.f), ir, F(0.f), F(0.f), ir, F(0.f), ir};
     Vec3<F> la = {F(0.f), F(0.f), F(0.f)}, lm = {F(0.f), F(0.f), F(0.f)};
+    enter_filter_frame(fc, x, xlo, P, COMP);
     for (int64_t t = 0; t < T; ++t) {
       const float* s = streams + (size_t)t * 9 * N + n;
       Vec3<F> w = {F(s[0], s[1]), F(s[N], s[N + 1]), F(s[2 * N], s[2 * N + 1])};
@@ -72,11 +76,13 @@ static void replay_packed_t(int64_t N, int64_t T, const float* streams, const do
       ekf_step<F, WAHBA_QR2, true, COMP>(x, xlo, P, fc, w, a, m, h, flip);
       if (out_flip) { out_flip[(size_t)t * N + n] = flip.x; out_flip[(size_t)t * N + n + 1] = flip.y; }
       if (out_traj) {
+        const Quat<F> xr = state_in_reference_frame(fc, x);
         double* o = out_traj + (size_t)t * 4 * N + n;
-        o[0] = x.w.x; o[1] = x.w.y; o[N] = x.x.x; o[N + 1] = x.x.y; o[2 * N] = x.y.x; o[2 * N + 1] = x.y.y;
-        o[3 * N] = x.z.x; o[3 * N + 1] = x.z.y;
+        o[0] = xr.w.x; o[1] = xr.w.y; o[N] = xr.x.x; o[N + 1] = xr.x.y; o[2 * N] = xr.y.x; o[2 * N + 1] = xr.y.y;
+        o[3 * N] = xr.z.x; o[3 * N + 1] = xr.z.y;
       }
     }
+    leave_filter_frame(fc, x, xlo, P, COMP);
     if (out_P) {
       const F p[10] = {P.a00, P.a01, P.a02, P.a03, P.a11, P.a12, P.a13, P.a22, P.a23, P.a33};
       for (int k = 0; k < 10; ++k) { out_P[(size_t)k * N + n] = r[n] * p[k].x; out_P[(size_t)k * N + n + 1] = r[n + 1] * p[k].y; }

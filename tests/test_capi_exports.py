@@ -49,11 +49,13 @@ def test_argument_validation_without_gpu():
     lib = _lib.load()
     # negative sizes / null pointers are rejected before any CUDA call
     assert lib.posekf_replay_f32(-1, 1, None, 1, None, 0, None, None, None, None, -1.0, -1.0, None, None, None, None,
-                                 None, None, None, None, 0, 0, None) == _lib.EINVAL
+                                 None, None, None, None, 0, 0, 0, None) == _lib.EINVAL
     assert lib.posekf_replay_f32(8, 4, None, 8, None, 0, None, None, None, None, -1.0, -1.0, None, None, None, None,
-                                 None, None, None, None, 0, 0, None) == _lib.EINVAL
+                                 None, None, None, None, 0, 0, 0, None) == _lib.EINVAL
     assert lib.posekf_replay_f32(0, 4, None, 8, None, 0, None, None, None, None, -1.0, -1.0, None, None, None, None,
-                                 None, None, None, None, 0, 0, None) == 0          # empty batch is a no-op
+                                 None, None, None, None, 0, 0, 0, None) == 0          # empty batch is a no-op
+    assert lib.posekf_replay_f32(8, 4, None, 8, None, 0, None, None, None, None, -1.0, -1.0, None, None, None, None,
+                                 None, None, None, None, 0, 0, 4, None) == _lib.EINVAL  # unknown state flag
     assert lib.posekf_wahba_f32(4, None, None, 0, None, None, None, None, 0.5, 0.5, 0, None, None, 0, 0, None) == _lib.EINVAL
     assert lib.posekf_rot2quat_f32(0, None, None, None) == 0
     try:

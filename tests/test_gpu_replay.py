@@ -99,14 +99,30 @@ def test_time_chunking_is_bit_exact(cuda, staging):
     N, T = 1536, 203          # odd T exercises the partial TMA tile
     imu = make_imu(N, T, seed=33, sigma=0.01, device=cuda)
     whole, traj, _ = B.replay(imu.streams, imu.acc_ref, imu.mag_ref, dt=imu.dt, store_trajectory=True, staging=staging)
+    # (the state stays in the kernel's working frame between chunks: keep_filter_frame on all but the last)
     st = B.ReplayState.initial(N, cuda, r=0.1)
     parts = []
-    for t0, t1 in ((0, 1), (1, 64), (64, 65), (65, 200), (200, 203)):
+    cuts = ((0, 1), (1, 64), (64, 65), (65, 200), (200, 203))
+    for t0, t1 in cuts:
         _, tr, _ = B.replay(imu.streams[t0:t1].contiguous(), imu.acc_ref, imu.mag_ref, dt=imu.dt, state=st,
-                            store_trajectory=True, staging=staging)
+                            store_trajectory=True, staging=staging, keep_filter_frame=t1 < T)
+        assert st.frame == ("filter" if t1 < T else "reference")
         parts.append(tr)
     assert torch.equal(torch.cat(parts), traj)
     assert torch.equal(st.x, whole.x) and torch.equal(st.p, whole.p)
+    # a state left in the filter frame converts to the same bits with an explicit call
+    st_f = B.ReplayState.initial(N, cuda, r=0.1)
+    B.replay(imu.streams, imu.acc_ref, imu.mag_ref, dt=imu.dt, state=st_f, staging=staging, keep_filter_frame=True)
+    assert st_f.frame == "filter" and not torch.equal(st_f.x, whole.x)
+    st_f.to_reference_frame(imu.acc_ref, imu.mag_ref)
+    assert st_f.frame == "reference" and torch.equal(st_f.x, whole.x) and torch.equal(st_f.p, whole.p)
+    # without the flag every chunk boundary converts out and in again: equal to rounding, not to the bit
+    st_r = B.ReplayState.initial(N, cuda, r=0.1)
+    for t0, t1 in cuts:
+        B.replay(imu.streams[t0:t1].contiguous(), imu.acc_ref, imu.mag_ref, dt=imu.dt, state=st_r, staging=staging)
+    ang = O.quat_angle(st_r.x.t().cpu().numpy().astype(np.float64), whole.x.t().cpu().numpy().astype(np.float64))
+    assert ang.max() < 2e-6
+    torch.testing.assert_close(st_r.p, whole.p, rtol=0, atol=2e-6)
 
 
 def test_stagings_agree_bitwise(cuda):
@@ -221,7 +237,7 @@ def test_full_size_properties(cuda):
     # chunked == unchunked at full width
     st2 = B.ReplayState.initial(N, cuda, r=r)
     for t0, t1 in ((0, 31), (31, 64)):
-        B.replay(streams[t0:t1].contiguous(), acc_ref, mag_ref, dt=base.dt, q=q, r=r, state=st2)
+        B.replay(streams[t0:t1].contiguous(), acc_ref, mag_ref, dt=base.dt, q=q, r=r, state=st2, keep_filter_frame=t1 < 64)
     assert torch.equal(st2.x, st.x) and torch.equal(st2.p, st.p)
     # oracle on a random subset
     idx = torch.randperm(N, generator=torch.Generator().manual_seed(0))[:1024].to(cuda)
@@ -297,7 +313,7 @@ def test_compensated_state_long_replay_extreme_tunings(cuda):
     st_c = B.ReplayState.initial(G * Ns, cuda, r=r_t)
     for t0, t1 in ((0, 1777), (1777, T)):
         B.replay(imu.streams[t0:t1].contiguous(), imu.acc_ref, imu.mag_ref, dt=imu.dt, q=q_t, r=r_t, n_filters=G * Ns,
-                 state=st_c, precise_state=True)
+                 state=st_c, precise_state=True, keep_filter_frame=t1 < T)
     assert torch.equal(st_c.x, st_auto.x) and torch.equal(st_c.x_lo, st_auto.x_lo) and torch.equal(st_c.p, st_auto.p)
 
 

