@@ -33,7 +33,10 @@ BYTES_PER_STEP = 36            # 9 float32 inputs (final-state-only replay)
 # flops of the algorithm the kernel EXECUTES (FMA = 2, mul/add/rcp/rsqrt = 1; compares and selects
 # not counted), stage by stage in DESIGN.md "Roofline"; the SASS FFMA/FMUL/FADD/MUFU census of the
 # loop body gives the same number.  (SURVEY.md's 1570 is the un-restructured reference algorithm.)
-FLOPS = {"qr2": 514, "jacobi": 1292}
+# qr2: dynamic opcode census of the shipped packed kernel (profiles/r01_replay_packed_opcode_census.json):
+# 168.0 FMA + 90.4 MUL + 32.1 ADD lane operations + 9 MUFU per filter-step = 467.5 flops, 290.5 FP32 lane operations.
+FLOPS = {"qr2": 468, "jacobi": 1292}
+FP32_LANE_OPS = {"qr2": 290.5}    # FP32-pipe lane operations per filter-step (FMA, MUL and ADD each occupy one lane-cycle)
 FLOPS_COMPENSATED_EXTRA = 32      # two-sum folding of the state (ncu: 536 + 10 MUFU flops per filter-step)
 
 
@@ -399,6 +402,12 @@ def run_ours(args):
                  "peak_source": "FFMA probe kernel measured in this run (posekf_fp32_peak_tflops)"},
         "hbm": {"achieved_gbs": ach_gbs, "peak_gbs": hbm_peak, "frac": ach_gbs / hbm_peak, "peak_source": hbm_src},
         "roofline_steps_per_s_per_gpu": 1.0 / max(t_fp32, t_hbm),
+        # the flop count has 1.6 flops per FP32 instruction (MUL and ADD carry one), so a 100 % busy pipe is < 100 % of
+        # the FFMA peak; the share of the pipe's lane-cycles (148 SMs x 128 lanes x SM clock) the kernel fills:
+        "fp32_pipe_lane_cycles_frac": (steps_per_s_kernel * FP32_LANE_OPS[args.wahba]
+                                       / (torch.cuda.get_device_properties(dev).multi_processor_count * 128
+                                          * (clocks or {}).get("sm_mhz", 0) * 1e6)
+                                       if args.wahba in FP32_LANE_OPS and not args.precise_state and (clocks or {}).get("sm_mhz") else None),
         "frac_of_roofline": steps_per_s_kernel * max(t_fp32, t_hbm),
     }
     # ncu traffic: dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of this kernel

@@ -270,40 +270,70 @@ __global__ void __launch_bounds__(256) traj2rpy_kernel(int64_t M, const float4* 
 
 // Packed form of the rank-2 Wahba kernel: two solves per thread in f32x2 lanes (N even, per-pair or
 // shared references).  Same arithmetic per solve as wahba_kernel<WAHBA_QR2>.
-__global__ void __launch_bounds__(256) wahba2_kernel(const WahbaParams p) {
-  const int64_t n = 2 * ((int64_t)blockIdx.x * blockDim.x + threadIdx.x);
-  if (n >= p.N) return;
+// The kernel is memory-bound (40 B per solve against ~250 FP32 operations), so it is written as a
+// grid-stride loop over a resident grid with the NEXT pair's six 8-byte loads issued before the current
+// pair is solved and stored: every thread always has 48-96 B of reads in flight instead of alternating
+// between a load phase and a compute/store phase.  With shared references the frame of (acc_0, mag_0) is
+// built once per thread, outside the loop.
+struct Wahba2Inputs { Vec3<f32x2> a, m; f32x2 ka, km; };
+__device__ __forceinline__ f32x2 ld2_stream(const float* q) {
+  float2 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(q));
+  return f32x2(v.x, v.y);
+}
+__device__ __forceinline__ void st2_stream(float* q, const f32x2& v) {
+  asm volatile("st.global.cs.v2.f32 [%0], {%1, %2};" ::"l"(q), "f"(v.x), "f"(v.y) : "memory");
+}
+__device__ __forceinline__ Wahba2Inputs wahba2_load(const WahbaParams& p, int64_t n) {
   const int64_t N = p.N;
-  Vec3<f32x2> ra, rm;
+  Wahba2Inputs in;
+  in.a = {ld2_stream(p.acc + n), ld2_stream(p.acc + N + n), ld2_stream(p.acc + 2 * N + n)};
+  in.m = {ld2_stream(p.mag + n), ld2_stream(p.mag + N + n), ld2_stream(p.mag + 2 * N + n)};
+  if (p.k_acc) { in.ka = ld2_stream(p.k_acc + n); in.km = ld2_stream(p.k_mag + n); }
+  else { in.ka = f32x2(p.k_acc_s); in.km = f32x2(p.k_mag_s); }
+  return in;
+}
+#ifndef PKF_WAHBA2_MIN_CTAS
+#define PKF_WAHBA2_MIN_CTAS 3
+#endif
+__global__ void __launch_bounds__(256, PKF_WAHBA2_MIN_CTAS) wahba2_kernel(const WahbaParams p) {
+  const int64_t N = p.N;
+  const int64_t stride = 2 * (int64_t)gridDim.x * blockDim.x;
+  int64_t n = 2 * ((int64_t)blockIdx.x * blockDim.x + threadIdx.x);
+  if (n >= N) return;
+  RefFrame<f32x2> E;
   if (p.ref_shared) {
-    ra = {f32x2(__ldg(p.acc_ref)), f32x2(__ldg(p.acc_ref + 1)), f32x2(__ldg(p.acc_ref + 2))};
-    rm = {f32x2(__ldg(p.mag_ref)), f32x2(__ldg(p.mag_ref + 1)), f32x2(__ldg(p.mag_ref + 2))};
-  } else {
-    ra = {ld2(p.acc_ref + n), ld2(p.acc_ref + N + n), ld2(p.acc_ref + 2 * N + n)};
-    rm = {ld2(p.mag_ref + n), ld2(p.mag_ref + N + n), ld2(p.mag_ref + 2 * N + n)};
+    const Vec3<f32x2> ra = {f32x2(__ldg(p.acc_ref)), f32x2(__ldg(p.acc_ref + 1)), f32x2(__ldg(p.acc_ref + 2))};
+    const Vec3<f32x2> rm = {f32x2(__ldg(p.mag_ref)), f32x2(__ldg(p.mag_ref + 1)), f32x2(__ldg(p.mag_ref + 2))};
+    E = frame_from_pair<f32x2>(ra, rm);
   }
-  auto ld2s = [](const float* q) {
-    float2 v;
-    asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(q));
-    return f32x2(v.x, v.y);
-  };
-  Vec3<f32x2> a = {ld2s(p.acc + n), ld2s(p.acc + N + n), ld2s(p.acc + 2 * N + n)};
-  Vec3<f32x2> m = {ld2s(p.mag + n), ld2s(p.mag + N + n), ld2s(p.mag + 2 * N + n)};
-  f32x2 ka, km;
-  if (p.k_acc) { ka = ld2s(p.k_acc + n); km = ld2s(p.k_mag + n); }
-  else if (p.weights_from_acc) { ka = abs_<f32x2>(a.z); km = f32x2(1.f) - ka; }
-  else { ka = f32x2(p.k_acc_s); km = f32x2(p.k_mag_s); }
-  const Mat3<f32x2> R = wahba_qr2<f32x2>(frame_from_pair<f32x2>(ra, rm), a, m, ka, km);
-  auto st2s = [](float* q, const f32x2& v) { asm volatile("st.global.cs.v2.f32 [%0], {%1, %2};" ::"l"(q), "f"(v.x), "f"(v.y) : "memory"); };
-  if (p.out_rot) {
+  Wahba2Inputs cur = wahba2_load(p, n);
+  while (true) {
+    const int64_t nn = n + stride;
+    const bool more = nn < N;
+    Wahba2Inputs nxt = cur;
+    if (more) nxt = wahba2_load(p, nn);              // in flight while the current pair is solved
+    if (!p.ref_shared) {
+      const Vec3<f32x2> ra = {ld2(p.acc_ref + n), ld2(p.acc_ref + N + n), ld2(p.acc_ref + 2 * N + n)};
+      const Vec3<f32x2> rm = {ld2(p.mag_ref + n), ld2(p.mag_ref + N + n), ld2(p.mag_ref + 2 * N + n)};
+      E = frame_from_pair<f32x2>(ra, rm);
+    }
+    f32x2 ka = cur.ka, km = cur.km;
+    if (!p.k_acc && p.weights_from_acc) { ka = abs_<f32x2>(cur.a.z); km = f32x2(1.f) - ka; }   // PKF/ExtendedKalmanFilter.py:71
+    const Mat3<f32x2> R = wahba_qr2<f32x2>(E, cur.a, cur.m, ka, km);
+    if (p.out_rot) {
 #pragma unroll
-    for (int r = 0; r < 3; ++r)
+      for (int r = 0; r < 3; ++r)
 #pragma unroll
-      for (int c = 0; c < 3; ++c) st2s(p.out_rot + (3 * r + c) * N + n, R.m[r][c]);
-  }
-  if (p.out_quat) {
-    const Quat<f32x2> q = rotation_to_quat_ref<f32x2>(R);
-    st2s(p.out_quat + n, q.w); st2s(p.out_quat + N + n, q.x); st2s(p.out_quat + 2 * N + n, q.y); st2s(p.out_quat + 3 * N + n, q.z);
+        for (int c = 0; c < 3; ++c) st2_stream(p.out_rot + (3 * r + c) * N + n, R.m[r][c]);
+    }
+    if (p.out_quat) {
+      const Quat<f32x2> q = rotation_to_quat_ref<f32x2>(R);
+      st2_stream(p.out_quat + n, q.w); st2_stream(p.out_quat + N + n, q.x);
+      st2_stream(p.out_quat + 2 * N + n, q.y); st2_stream(p.out_quat + 3 * N + n, q.z);
+    }
+    if (!more) break;
+    cur = nxt; n = nn;
   }
 }
 
