@@ -241,65 +241,67 @@ template <typename F> PKF_HD void two_sum(F a, F b, F& hi, F& lo) {
 // ------------------------------------------------------------------------------------------
 // Covariance propagation  P <- A P A^T + B(x) (q I3) B(x)^T,  A = 0.5*Omega(w)  (hw = 0.5 w),
 // x = state BEFORE the RK4 step.        (PKF/ExtendedKalmanFilter.py:59-61)
-//   B B^T = 0.25 (|x|^2 I - x x^T)  =>  second term = qq (|x|^2 I - x x^T), qq = q/4.
+//   B B^T = 0.25 (|x|^2 I - x x^T)  =>  second term = qq (|x|^2 I - x x^T), qq = q/4; the caller passes
+//   s = qq |x|^2 (the fused step knows |x| = 1 after its own normalisation and passes qq itself).
+//
+// A is the matrix of a RIGHT quaternion multiplication by the pure quaternion (0, hw).  Symmetric 4x4
+// matrices split as  P = alpha I + sum_ij T_ij L_i R_j  (L_i / R_j: left / right multiplication by the
+// imaginary units; each L_i R_j is a symmetric signed permutation), and a right multiplication acts on
+// the 3x3 coefficient matrix T alone:
+//     A P A^T  <->  alpha' = |hw|^2 alpha,   T' = 2 (T hw) hw^T - |hw|^2 T
+// (|hw|^2 times a half-turn about hw).  With D_i = 4 T_ii and the pair sums/differences of the
+// off-diagonal entries (14 additions), U = 2 T hw (12 operations), the result follows entry by entry:
+//     diagonal:      alpha' -/+ T'_00 -/+ T'_11 -/+ T'_22,   T'_ii = U_i hw_i - (|hw|^2/4) D_i
+//     off-diagonal:  e.g. P'_03 = Y U_0 - X U_1 - |hw|^2 P_03   (the pair sums collapse back to P_03)
+// 74 operations including the process noise, against 88 for the two sparse products (A P) A^T.
 // ------------------------------------------------------------------------------------------
 template <typename F, bool NOISE = true>
-PKF_HD Sym4<F> propagate_cov(const Sym4<F>& P, const Vec3<F>& hw, const Quat<F>& x, F qq) {
+PKF_HD Sym4<F> propagate_cov(const Sym4<F>& P, const Vec3<F>& hw, const Quat<F>& x, F qq, F s) {
   const F X = hw.x, Y = hw.y, Z = hw.z;
-  // M = A P (full 4x4; P symmetric so P[k][j] is read from the upper triangle)
-  // rows of A: [0,-X,-Y,-Z], [X,0,Z,-Y], [Y,-Z,0,X], [Z,Y,-X,0]
   const F p00 = P.a00, p01 = P.a01, p02 = P.a02, p03 = P.a03, p11 = P.a11, p12 = P.a12, p13 = P.a13,
           p22 = P.a22, p23 = P.a23, p33 = P.a33;
-  // Each entry is one product plus two FMAs.  The 48 products come in +/- pairs (X p01 is needed by m00 and
-  // m11, Y p12 by m01 and m32, ...): starting both chains of a pair from the shared product lets the pair cost
-  // one multiplication instead of two -- 8 multiplications for the 16 entries.  The chains are written level
-  // by level so that consecutive instructions share their multiplier (operand-reuse cache).
-  const F xp01 = X * p01, xp02 = X * p02, xp03 = X * p03, xp12 = X * p12, xp13 = X * p13, xp23 = X * p23;
-  const F yp12 = Y * p12, yp03 = Y * p03;
-  F m00 = -xp01, m11 = xp01, m12 = xp02, m30 = -xp02, m13 = xp03, m20 = xp03;
-  F m02 = -xp12, m31 = -xp12, m03 = -xp13, m21 = xp13, m22 = xp23, m33 = -xp23;
-  F m01 = -yp12, m32 = yp12, m10 = -yp03, m23 = yp03;
-  // second term of every chain
-  m00 = fma_(-Y, p02, m00); m02 = fma_(-Y, p22, m02); m03 = fma_(-Y, p23, m03);
-  m11 = fma_(-Y, p13, m11); m12 = fma_(-Y, p23, m12); m13 = fma_(-Y, p33, m13);
-  m20 = fma_(Y, p00, m20); m21 = fma_(Y, p01, m21); m22 = fma_(Y, p02, m22);
-  m30 = fma_(Y, p01, m30); m31 = fma_(Y, p11, m31); m33 = fma_(Y, p13, m33);
-  m01 = fma_(-X, p11, m01); m10 = fma_(X, p00, m10); m23 = fma_(X, p33, m23); m32 = fma_(-X, p22, m32);
-  // third term
-  m00 = fma_(-Z, p03, m00); m01 = fma_(-Z, p13, m01); m02 = fma_(-Z, p23, m02); m03 = fma_(-Z, p33, m03);
-  m10 = fma_(Z, p02, m10); m11 = fma_(Z, p12, m11); m12 = fma_(Z, p22, m12); m13 = fma_(Z, p23, m13);
-  m20 = fma_(-Z, p01, m20); m21 = fma_(-Z, p11, m21); m22 = fma_(-Z, p12, m22); m23 = fma_(-Z, p13, m23);
-  m30 = fma_(Z, p00, m30); m31 = fma_(Z, p01, m31); m32 = fma_(Z, p02, m32); m33 = fma_(Z, p03, m33);
+  // 4 alpha, 4 T_ii and twice the off-diagonal T_ij (E_ij = 2 T_ij, F_ij = -2 T_ij)
+  const F s1 = p00 + p11, s2 = p22 + p33, d1 = p11 - p00, d2 = p33 - p22;
+  const F A4 = s1 + s2, D0 = s2 - s1, D1 = d1 + d2, D2 = d1 - d2;
+  const F E01 = p03 - p12, F10 = p03 + p12;
+  const F F02 = p02 + p13, E20 = p02 - p13;
+  const F E12 = p01 - p23, F21 = p01 + p23;
+  // U = 2 T hw
+  const F qX = F(0.5) * X, qY = F(0.5) * Y, qZ = F(0.5) * Z;
+  const F U0 = fma_(-F02, Z, fma_(E01, Y, D0 * qX));
+  const F U1 = fma_(E12, Z, fma_(-F10, X, D1 * qY));
+  const F U2 = fma_(-F21, Y, fma_(E20, X, D2 * qZ));
+  const F w2 = dot3(hw, hw);
+  const F c4 = F(0.25) * w2;
+  const F T00 = fma_(U0, X, -(c4 * D0)), T11 = fma_(U1, Y, -(c4 * D1)), T22 = fma_(U2, Z, -(c4 * D2));
+  const F t1 = T11 + T22, t2 = T22 - T11;
   Sym4<F> N;
-  // N[i][j] = sum_k M[i][k] A[j][k]
-  //  j=0: -X M[i][1] - Y M[i][2] - Z M[i][3]     j=1:  X M[i][0] + Z M[i][2] - Y M[i][3]
-  //  j=2:  Y M[i][0] - Z M[i][1] + X M[i][3]     j=3:  Z M[i][0] + Y M[i][1] - X M[i][2]
   if constexpr (NOISE) {
-    // process-noise term, used as the start value of the accumulation chains
-    F yw = qq * x.w, yx = qq * x.x, yy = qq * x.y, yz = qq * x.z;
-    F s = fma_(yz, x.z, fma_(yy, x.y, fma_(yx, x.x, yw * x.w)));   // qq |x|^2
-    N.a00 = fma_(-Z, m03, fma_(-Y, m02, fma_(-X, m01, fma_(-yw, x.w, s))));
-    N.a01 = fma_(-Y, m03, fma_(Z, m02, fma_(X, m00, -(yw * x.x))));
-    N.a02 = fma_(X, m03, fma_(-Z, m01, fma_(Y, m00, -(yw * x.y))));
-    N.a03 = fma_(-X, m02, fma_(Y, m01, fma_(Z, m00, -(yw * x.z))));
-    N.a11 = fma_(-Y, m13, fma_(Z, m12, fma_(X, m10, fma_(-yx, x.x, s))));
-    N.a12 = fma_(X, m13, fma_(-Z, m11, fma_(Y, m10, -(yx * x.y))));
-    N.a13 = fma_(-X, m12, fma_(Y, m11, fma_(Z, m10, -(yx * x.z))));
-    N.a22 = fma_(X, m23, fma_(-Z, m21, fma_(Y, m20, fma_(-yy, x.y, s))));
-    N.a23 = fma_(-X, m22, fma_(Y, m21, fma_(Z, m20, -(yy * x.z))));
-    N.a33 = fma_(-X, m32, fma_(Y, m31, fma_(Z, m30, fma_(-yz, x.z, s))));
+    const F al = fma_(c4, A4, s);                      // alpha' + qq |x|^2
+    const F am = al - T00, ap = al + T00;
+    const F yw = qq * x.w, yx = qq * x.x, yy = qq * x.y, yz = qq * x.z;
+    N.a00 = fma_(-yw, x.w, am - t1);
+    N.a11 = fma_(-yx, x.x, am + t1);
+    N.a22 = fma_(-yy, x.y, ap + t2);
+    N.a33 = fma_(-yz, x.z, ap - t2);
+    N.a01 = fma_(Z, U1, fma_(-Y, U2, fma_(-w2, p01, -(yw * x.x))));
+    N.a02 = fma_(X, U2, fma_(-Z, U0, fma_(-w2, p02, -(yw * x.y))));
+    N.a03 = fma_(Y, U0, fma_(-X, U1, fma_(-w2, p03, -(yw * x.z))));
+    N.a12 = fma_(-Y, U0, fma_(-X, U1, fma_(-w2, p12, -(yx * x.y))));
+    N.a13 = fma_(-Z, U0, fma_(-X, U2, fma_(-w2, p13, -(yx * x.z))));
+    N.a23 = fma_(-Z, U1, fma_(-Y, U2, fma_(-w2, p23, -(yy * x.z))));
   } else {
     // A P A^T alone (the caller handles the process noise separately, see kalman_gain_sm)
-    N.a00 = fma_(-Z, m03, fma_(-Y, m02, -(X * m01)));
-    N.a01 = fma_(-Y, m03, fma_(Z, m02, X * m00));
-    N.a02 = fma_(X, m03, fma_(-Z, m01, Y * m00));
-    N.a03 = fma_(-X, m02, fma_(Y, m01, Z * m00));
-    N.a11 = fma_(-Y, m13, fma_(Z, m12, X * m10));
-    N.a12 = fma_(X, m13, fma_(-Z, m11, Y * m10));
-    N.a13 = fma_(-X, m12, fma_(Y, m11, Z * m10));
-    N.a22 = fma_(X, m23, fma_(-Z, m21, Y * m20));
-    N.a23 = fma_(-X, m22, fma_(Y, m21, Z * m20));
-    N.a33 = fma_(-X, m32, fma_(Y, m31, Z * m30));
+    // (explicit fma_: a bare product feeding a sum is what a compiler may or may not contract, and the scalar and
+    //  packed builds must round identically)
+    const F am = fma_(c4, A4, -T00), ap = fma_(c4, A4, T00);
+    N.a00 = am - t1; N.a11 = am + t1; N.a22 = ap + t2; N.a33 = ap - t2;
+    N.a01 = fma_(Z, U1, fma_(-Y, U2, -(w2 * p01)));
+    N.a02 = fma_(X, U2, fma_(-Z, U0, -(w2 * p02)));
+    N.a03 = fma_(Y, U0, fma_(-X, U1, -(w2 * p03)));
+    N.a12 = fma_(-Y, U0, fma_(-X, U1, -(w2 * p12)));
+    N.a13 = fma_(-Z, U0, fma_(-X, U2, -(w2 * p13)));
+    N.a23 = fma_(-Z, U1, fma_(-Y, U2, -(w2 * p23)));
   }
   return N;
 }
@@ -760,6 +762,7 @@ template <typename F> struct FilterConst {
   RefFrame<F> E;          // from (acc_0, mag_0)
   Vec3<F> ra, rm;         // raw reference vectors (used by the Jacobi variant only)
   F g;                    // Q/(4R): process noise in units of r
+  F gs;                   // g |x|^2 of the CURRENT state: g after any step of the filter (it normalises), see noise_scale
   Quat<F> qE;             // unit quaternion of the rotation [e1 e2 e3]: filter frame -> reference frame
 };
 
@@ -794,7 +797,7 @@ PKF_HD void quat_fallback_unaligned(const Mat3<f32x2>& Rm, const Quat<f32x2>& z,
 // sums the step's three small terms (RK4 increment, K e, norm correction) first and folds them into
 // the state with one exact two-sum per component.
 template <typename F, int ALGO, bool WANT_FLIP, bool COMP, typename FlagT>
-PKF_HD void ekf_step(Quat<F>& x, Quat<F>& xlo, Sym4<F>& P, const FilterConst<F>& fc, const Vec3<F>& gyro,
+PKF_HD void ekf_step(Quat<F>& x, Quat<F>& xlo, Sym4<F>& P, FilterConst<F>& fc, const Vec3<F>& gyro,
                      const Vec3<F>& acc, const Vec3<F>& mag, F h, FlagT& flip, bool flip_wanted = true) {
   // flip_wanted: launch-uniform run-time switch under WANT_FLIP -- a launch that stores the trajectory but
   // not the flip mask skips the reference's branch rule (three traces, compares, selects) altogether
@@ -803,10 +806,10 @@ PKF_HD void ekf_step(Quat<F>& x, Quat<F>& xlo, Sym4<F>& P, const FilterConst<F>&
   // ---- Prediction (PKF/ExtendedKalmanFilter.py:58-68) ----
   Sym4<F> K;
   if constexpr (COMP) {
-    Sym4<F> M = propagate_cov<F, false>(P, hw, x, fc.g);                      // :59-61, noise kept apart
+    Sym4<F> M = propagate_cov<F, false>(P, hw, x, fc.g, fc.gs);               // :59-61, noise kept apart
     K = kalman_gain_sm(M, x, fc.g);                                           // :63-66
   } else {
-    Sym4<F> Pp = propagate_cov<F, true>(P, hw, x, fc.g);                      // :59-61 (in units of r)
+    Sym4<F> Pp = propagate_cov<F, true>(P, hw, x, fc.g, fc.gs);               // :59-61 (in units of r)
     K = kalman_gain_unit(Pp);                                                 // :63-66
   }
   Quat<F> inc = rk4_increment(x, hw, h);                                      // :62
@@ -871,6 +874,16 @@ PKF_HD void ekf_step(Quat<F>& x, Quat<F>& xlo, Sym4<F>& P, const FilterConst<F>&
   }
   // P = P - K P = r K  (R = r I): in units of r the new covariance IS the gain     :78
   P = K;
+  fc.gs = fc.g;        // the state leaves every step normalised: |x|^2 = 1 for the next step's B Q B^T
+}
+
+// Process-noise scale g |x|^2 for the FIRST step of a launch.  A state within 1e-5 of unit norm (the initial
+// [1,0,0,0], or any state this filter produced: it normalises every step, to ~2e-7) counts as unit, so that a
+// replay cut into chunks is bit-identical to the unchunked one; a caller-supplied state that is not normalised
+// gets its true |x|^2, as B(x) Q B(x)^T has in the reference (PKF/ExtendedKalmanFilter.py:51-56,61).
+template <typename F> PKF_HD F noise_scale(F g, const Quat<F>& x) {
+  const F n2 = dot4(x, x);
+  return sel_(abs_(n2 - F(1)) < F(1e-5), g, g * n2);
 }
 
 template <typename F>
@@ -879,6 +892,7 @@ PKF_HD FilterConst<F> make_filter_const(const Vec3<F>& acc_ref, const Vec3<F>& m
   fc.E = frame_from_pair(acc_ref, mag_ref);
   fc.ra = acc_ref; fc.rm = mag_ref;
   fc.g = (F(0.25) * q) / r;
+  fc.gs = fc.g;
   Mat3<F> Em;
   Em.m[0][0] = fc.E.e1.x; Em.m[1][0] = fc.E.e1.y; Em.m[2][0] = fc.E.e1.z;
   Em.m[0][1] = fc.E.e2.x; Em.m[1][1] = fc.E.e2.y; Em.m[2][1] = fc.E.e2.z;
