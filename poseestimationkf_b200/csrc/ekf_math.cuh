@@ -68,6 +68,48 @@ template <> inline double rsqrt_<double>(double a) { return 1.0 / sqrt(a); }
 
 template <typename F> PKF_HD F sel_(bool c, F a, F b) { return c ? a : b; }
 PKF_HD bool any_(bool m) { return m; }
+// Sign-bit helpers.  On sm_100 FSEL issues to the FP32 (FMA) pipe -- the pipe that bounds the fused step -- while
+// the integer ALU is nearly idle, so the selections and conditional negations of the hot path are written on the
+// bit patterns (LOP3 / SHF):
+//   flipsign_(v, s)      v with its sign flipped when the sign bit of s is set
+//   selsign_(s, a, b)    a when the sign bit of s is set, else b   (lop3 0xCA through inline PTX: the
+//                        compiler folds a C-level bit blend back into a float select)
+//   one_with_sign_(s)    +1 or -1 carrying the sign bit of s
+//   signbit_(s)          that bit as a mask
+#ifndef PKF_SEL_MODE
+#define PKF_SEL_MODE 0
+#endif
+#if defined(__CUDA_ARCH__)
+__device__ __forceinline__ float flipsign_(float v, float s) {
+#if PKF_SEL_MODE == 0
+  return __float_as_int(s) < 0 ? -v : v;
+#else
+  return __uint_as_float(__float_as_uint(v) ^ (__float_as_uint(s) & 0x80000000u));
+#endif
+}
+__device__ __forceinline__ float selsign_(float s, float a, float b) {
+#if PKF_SEL_MODE == 1
+  int r;
+  asm("lop3.b32 %0, %1, %2, %3, 0xCA;" : "=r"(r) : "r"(__float_as_int(s) >> 31), "r"(__float_as_int(a)), "r"(__float_as_int(b)));
+  return __int_as_float(r);
+#else
+  return __float_as_int(s) < 0 ? a : b;
+#endif
+}
+__device__ __forceinline__ bool signbit_(float s) { return (__float_as_uint(s) >> 31) != 0u; }
+__device__ __forceinline__ float one_with_sign_(float s) {
+  return __uint_as_float((__float_as_uint(s) & 0x80000000u) | 0x3f800000u);
+}
+#else
+inline float flipsign_(float v, float s) { return __builtin_signbit(s) ? -v : v; }
+inline float selsign_(float s, float a, float b) { return __builtin_signbit(s) ? a : b; }
+inline bool signbit_(float s) { return __builtin_signbit(s); }
+inline float one_with_sign_(float s) { return __builtin_signbit(s) ? -1.0f : 1.0f; }
+inline double flipsign_(double v, double s) { return __builtin_signbit(s) ? -v : v; }
+inline double selsign_(double s, double a, double b) { return __builtin_signbit(s) ? a : b; }
+inline bool signbit_(double s) { return __builtin_signbit(s); }
+inline double one_with_sign_(double s) { return __builtin_signbit(s) ? -1.0 : 1.0; }
+#endif
 
 // ------------------------------------------------------------------------------------------
 // f32x2: TWO filters per thread in the lanes of a 64-bit register pair.  On sm_100 every operator maps
@@ -107,6 +149,10 @@ PKF_HD mask2 operator<(const f32x2& a, const f32x2& b) { return mask2{a.x < b.x,
 PKF_HD mask2 operator>(const f32x2& a, const f32x2& b) { return mask2{a.x > b.x, a.y > b.y}; }
 PKF_HD mask2 operator==(const f32x2& a, const f32x2& b) { return mask2{a.x == b.x, a.y == b.y}; }
 PKF_HD f32x2 sel_(mask2 c, const f32x2& a, const f32x2& b) { return f32x2(c.x ? a.x : b.x, c.y ? a.y : b.y); }
+PKF_HD f32x2 selsign_(const f32x2& s, const f32x2& a, const f32x2& b) { return f32x2(selsign_(s.x, a.x, b.x), selsign_(s.y, a.y, b.y)); }
+PKF_HD f32x2 flipsign_(const f32x2& v, const f32x2& s) { return f32x2(flipsign_(v.x, s.x), flipsign_(v.y, s.y)); }
+PKF_HD mask2 signbit_(const f32x2& s) { return mask2{signbit_(s.x), signbit_(s.y)}; }
+PKF_HD f32x2 one_with_sign_(const f32x2& s) { return f32x2(one_with_sign_(s.x), one_with_sign_(s.y)); }
 template <> PKF_HD f32x2 fma_<f32x2>(f32x2 a, f32x2 b, f32x2 c) {
 #if defined(__CUDA_ARCH__)
   float2 r = __ffma2_rn(f2_(a), f2_(b), f2_(c));
@@ -460,6 +506,63 @@ PKF_HD Mat3<F> wahba_qr2_local(const RefFrame<F>& E, const Vec3<F>& a, const Vec
   return R;
 }
 
+// ------------------------------------------------------------------------------------------
+// Wahba, two observations, solved DIRECTLY AS A QUATERNION in the filter frame (fused step).
+// For two weighted observations the maximiser of tr(R B^T) has a closed form in the quaternion
+// itself (F. L. Markley, "Fast quaternion attitude estimation from two vector measurements", 2002):
+// with the unit normals b3 = u1 x u2 / |.| of the reference pair and r3 = v1 x v2 / |.| of the
+// measured pair, S = sum w_i u_i.v_i and V = sum w_i u_i x v_i,
+//     alpha = (1 + b3.r3) S + (b3 x r3).V,   beta = (b3 + r3).V,   gamma = hypot(alpha, beta),
+//     q ~ [ (gamma+alpha)(1 + b3.r3) ;  (gamma+alpha)(b3 x r3) + beta (b3 + r3) ]        alpha >= 0
+//     q ~ [  beta (1 + b3.r3)        ;   beta (b3 x r3) + (gamma-alpha)(b3 + r3) ]       alpha <  0
+// (vector part conjugated for the Hamilton body->reference convention of the reference's
+// RotationMatrix2Quart).  It is the same rotation as U diag(1,1,det U det V^T) V^T of PKF/Wahba.py:14-16
+// whenever both weights are positive (rank-2 B): like wahba_qr2 it never forms B, the weights enter
+// linearly, so it stays accurate to float32 rounding for |a_z| -> 0 or 1.  Un-normalised vectors are
+// weights (w_1 u_1.v_1 = ka (r_a.a), ...), so nothing but the normal r3 is normalised.
+// In the filter frame r_a = (s11,0,0), r_m = (s12,s22,0), b3 = (0,0,1), and most products vanish.
+// 1 + b3.r3 -> 0 (measured normal opposite to the reference normal) is the formula's singularity:
+// when r3.z < 0 the measured pair is first half-turned about the body x axis (y and z components
+// negated, so r3.z -> |r3.z|) and the half-turn is composed back into the result, q (x) (0,1,0,0) =
+// (-x, w, z, -y); 1 + b3.r3 >= 1 always.
+// 54 FP32 operations + 3 MUFU for the UNIT quaternion (sign arbitrary), against 92 for frame, 2x2 polar
+// factor, rotation matrix and matrix->quaternion.
+// ------------------------------------------------------------------------------------------
+template <typename F>
+PKF_HD Quat<F> wahba_quat2_local(const RefFrame<F>& E, const Vec3<F>& a, const Vec3<F>& m, F ka, F km) {
+  const Vec3<F> c = cross3(a, m);
+  // half-turn of the measured pair when c.z < 0: sigma = sign(c.z) multiplies the y and z components of a, m
+  // and c; it cancels in every product of two flipped quantities, four conditional negations remain
+  const F ays = flipsign_(a.y, c.z), mys = flipsign_(m.y, c.z);
+  const F ic = rsqrt_(dot3(c, c));
+  const F rx = c.x * ic, ry0 = c.y * ic;                          // r3 = (rx, sigma ry0, |c.z| ic)
+  const F rxs = flipsign_(rx, c.z), ry = flipsign_(ry0, c.z);
+  const F A1 = ka * E.s11, B1 = km * E.s12, B2 = km * E.s22;
+  const F S = fma_(B2, mys, fma_(B1, m.x, A1 * a.x));             // sum w_i u_i.v_i
+  const F Vx0 = B2 * m.z;                                         // sum w_i u_i x v_i = (sigma Vx0, sigma Vy0, Vz)
+  const F Vy0 = -fma_(B1, m.z, A1 * a.z);
+  const F Vz = fma_(-B2, m.x, fma_(B1, mys, A1 * ays));
+  const F d = fma_(abs_(c.z), ic, F(1));                          // 1 + b3.r3  (explicit fma_: see propagate_cov)
+  const F al = fma_(-ry0, Vx0, fma_(rxs, Vy0, d * S));
+  const F be = fma_(d, Vz, fma_(ry0, Vy0, rxs * Vx0));
+  const F g2 = fma_(al, al, be * be);
+  const F t = fma_(g2, rsqrt_(g2), abs_(al));                     // gamma + |alpha|
+  const F p = selsign_(al, be, t), q = selsign_(al, t, be);       // alpha < 0: the other, cancellation-free form
+  // [sc; vec] = [p d; p (b3 x r3) + q (b3 + r3)],  b3 x r3 = (-ry, rx, 0),  b3 + r3 = (rx, ry, d)
+  Quat<F> y;
+  y.w = p * d;
+  y.x = -fma_(q, rx, -(p * ry));
+  y.y = -fma_(q, ry, p * rx);
+  y.z = -(q * d);
+  const F in = rsqrt_(dot4(y, y));
+  y.w *= in; y.x *= in; y.y *= in; y.z *= in;
+  // undo the half-turn of the measured pair:  y (x) (0,1,0,0) = (-x, w, z, -y)
+  Quat<F> o;
+  o.w = flipsign_(selsign_(c.z, y.x, y.w), c.z); o.x = selsign_(c.z, y.w, y.x);
+  o.y = selsign_(c.z, y.z, y.y); o.z = flipsign_(selsign_(c.z, y.y, y.z), c.z);
+  return o;
+}
+
 // columns of E times the rows of a local-frame matrix:  R = E L
 template <typename F> PKF_HD Mat3<F> frame_times(const RefFrame<F>& E, const Mat3<F>& L) {
   Mat3<F> R;
@@ -745,6 +848,19 @@ PKF_HD auto reference_flip_local(const FC& fc, const Mat3<F>& Ml, const Quat<F>&
   return sel_(b1, y.x, sel_(b2, y.y, y.z)) < F(0);
 }
 
+// The same decision from the quaternion alone: for a rotation matrix the three traces of
+// RotationMatrix2Quart are 4x^2, 4y^2, 4z^2 of its quaternion, so the reference's branch is the largest of
+// |x|, |y|, |z| (strictly; else the third), its raw quaternion has that component >= 0, and it negated iff the
+// comparator-aligned quaternion (sg * y, expressed in the reference frame) has it negative.
+template <typename F, typename FC>
+PKF_HD auto reference_flip_quat(const FC& fc, const Quat<F>& yl, F sg) -> decltype(yl.w < yl.w) {
+  const Quat<F> y = qmul(fc.qE, yl);
+  const F ax = y.x * y.x, ay = y.y * y.y, az = y.z * y.z;
+  auto b1 = (ax > ay) && (ax > az);
+  auto b2 = !b1 && ((ay > ax) && (ay > az));
+  return (sg * sel_(b1, y.x, sel_(b2, y.y, y.z))) < F(0);
+}
+
 // ------------------------------------------------------------------------------------------
 // One fused filter step (Prediction + Correction, PKF/main_file.py:39,43), scalar Q and R.
 // The covariance argument P is carried IN UNITS OF r (P/r): with R = r I the whole recursion is
@@ -796,15 +912,14 @@ PKF_HD void quat_fallback_unaligned(const Mat3<f32x2>& Rm, const Quat<f32x2>& z,
 // reference does not (2.4e-5 rad apart after 5000 steps at Q=1e-3, R=1e3).  The compensated form
 // sums the step's three small terms (RK4 increment, K e, norm correction) first and folds them into
 // the state with one exact two-sum per component.
-template <typename F, int ALGO, bool WANT_FLIP, bool COMP, typename FlagT>
-PKF_HD void ekf_step(Quat<F>& x, Quat<F>& xlo, Sym4<F>& P, FilterConst<F>& fc, const Vec3<F>& gyro,
-                     const Vec3<F>& acc, const Vec3<F>& mag, F h, FlagT& flip, bool flip_wanted = true) {
-  // flip_wanted: launch-uniform run-time switch under WANT_FLIP -- a launch that stores the trajectory but
-  // not the flip mask skips the reference's branch rule (three traces, compares, selects) altogether
+// ---- the three parts of a step -------------------------------------------------------------------
+// Prediction (PKF/ExtendedKalmanFilter.py:58-68): gain K (= the post-update covariance in units of r), RK4
+// increment inc and predicted state z = x + inc.
+template <typename F, bool COMP>
+PKF_HD void ekf_predict(const Quat<F>& x, const Sym4<F>& P, const FilterConst<F>& fc, const Vec3<F>& gyro, F h,
+                        Sym4<F>& K, Quat<F>& inc, Quat<F>& z) {
   Vec3<F> hw;
   hw.x = F(0.5) * gyro.x; hw.y = F(0.5) * gyro.y; hw.z = F(0.5) * gyro.z;
-  // ---- Prediction (PKF/ExtendedKalmanFilter.py:58-68) ----
-  Sym4<F> K;
   if constexpr (COMP) {
     Sym4<F> M = propagate_cov<F, false>(P, hw, x, fc.g, fc.gs);               // :59-61, noise kept apart
     K = kalman_gain_sm(M, x, fc.g);                                           // :63-66
@@ -812,44 +927,14 @@ PKF_HD void ekf_step(Quat<F>& x, Quat<F>& xlo, Sym4<F>& P, FilterConst<F>& fc, c
     Sym4<F> Pp = propagate_cov<F, true>(P, hw, x, fc.g, fc.gs);               // :59-61 (in units of r)
     K = kalman_gain_unit(Pp);                                                 // :63-66
   }
-  Quat<F> inc = rk4_increment(x, hw, h);                                      // :62
-  Quat<F> z;                                                                  // |z| = 1 to rounding
-  z.w = x.w + inc.w; z.x = x.x + inc.x; z.y = x.y + inc.y; z.z = x.z + inc.z;
-  // ---- Correction (PKF/ExtendedKalmanFilter.py:70-80) ----
-  F e0, e1, e2, e3;
-  if constexpr (ALGO == WAHBA_PRECOMPUTED) {
-    // stream rows 3..6 carry the Wahba quaternion in the reference's own sign convention (the output of
-    // getQuarternion, :71): apply the comparator literally -- negate when dot(y, z) < 0            :73-75
-    const Quat<F> y = {acc.x, acc.y, acc.z, mag.x};
-    const auto neg = dot4(y, z) < F(0);
-    flip = neg;
-    const F sg = sel_(neg, F(-1), F(1));
-    e0 = fma_(sg, y.w, -z.w); e1 = fma_(sg, y.x, -z.x); e2 = fma_(sg, y.y, -z.y); e3 = fma_(sg, y.z, -z.z);   // :76
-  } else {
-    F ka = abs_(acc.z), km = F(1) - ka;                                       // :71
-    // Rm: the Wahba rotation in the filter frame (E^T R)
-    Mat3<F> Rm;
-    if constexpr (ALGO == WAHBA_QR2) Rm = wahba_qr2_local(fc.E, acc, mag, ka, km);
-    else Rm = frame_transposed_times(fc.E, wahba_jacobi(fc.ra, fc.rm, acc, mag, ka, km, kJacobiSweepsFused));
-    // measurement quaternion with the comparator's sign already applied          :73-75
-    F n2;
-    Quat<F> y = rotation_to_quat_aligned(Rm, z, n2);     // un-normalised: 4 (y.z) y
-    flip = FlagT();
-    if (WANT_FLIP && flip_wanted) flip = reference_flip_local(fc, Rm, y);   // only the signs of y matter
-    // innovation e = y/|y| - z, the normalisation folded into the subtraction     :76
-    const F inv = rsqrt_(n2);
-    e0 = fma_(y.w, inv, -z.w); e1 = fma_(y.x, inv, -z.x); e2 = fma_(y.y, inv, -z.y); e3 = fma_(y.z, inv, -z.z);
-    const auto unrelated = n2 < F(0.16);
-    if (any_(unrelated)) {
-      // |y.z| < 0.1: prediction and measurement are unrelated (never in a tracking filter; can happen
-      // on the first sample of a badly initialised one).  Use the selection-based conversion there.
-      Quat<F> yf = y;
-      quat_fallback_unaligned(Rm, z, unrelated, yf);
-      if (WANT_FLIP && flip_wanted) flip = reference_flip_local(fc, Rm, yf);
-      e0 = sel_(unrelated, yf.w - z.w, e0); e1 = sel_(unrelated, yf.x - z.x, e1);
-      e2 = sel_(unrelated, yf.y - z.y, e2); e3 = sel_(unrelated, yf.z - z.z, e3);
-    }
-  }
+  inc = rk4_increment(x, hw, h);                                              // :62
+  z.w = x.w + inc.w; z.x = x.x + inc.x; z.y = x.y + inc.y; z.z = x.z + inc.z;   // |z| = 1 to rounding
+}
+
+// State and covariance update (PKF/ExtendedKalmanFilter.py:77-79) from the innovation e = y - z.
+template <typename F, bool COMP>
+PKF_HD void ekf_update(Quat<F>& x, Quat<F>& xlo, Sym4<F>& P, FilterConst<F>& fc, const Sym4<F>& K, const Quat<F>& z,
+                       const Quat<F>& inc, F e0, F e1, F e2, F e3) {
   // X = z + K e                                                              :77
   Quat<F> ke;
   ke.w = fma_(K.a03, e3, fma_(K.a02, e2, fma_(K.a01, e1, K.a00 * e0)));
@@ -875,6 +960,83 @@ PKF_HD void ekf_step(Quat<F>& x, Quat<F>& xlo, Sym4<F>& P, FilterConst<F>& fc, c
   // P = P - K P = r K  (R = r I): in units of r the new covariance IS the gain     :78
   P = K;
   fc.gs = fc.g;        // the state leaves every step normalised: |x|^2 = 1 for the next step's B Q B^T
+}
+
+// The measurement of one sample: getQuarternion(acc, mag, |a_z|, 1 - |a_z|) (PKF/ExtendedKalmanFilter.py:71) as a
+// unit quaternion in the filter frame, sign arbitrary.  It depends on the sample and the filter's reference frame
+// only -- not on the state -- so a kernel may compute it ahead of the step that consumes it.
+template <typename F> PKF_HD Quat<F> measure_quat(const FilterConst<F>& fc, const Vec3<F>& acc, const Vec3<F>& mag) {
+  const F ka = abs_(acc.z), km = F(1) - ka;
+  Quat<F> y = wahba_quat2_local(fc.E, acc, mag, ka, km);
+  const auto reflected = km < F(0);      // |a_z| > 1 (un-normalised accelerometer): a negative weight, the closed
+  if (any_(reflected)) {                 // form does not apply -- rank-2 SVD form for those lanes (rare path)
+    const Quat<F> yr = rotation_to_quat_best(wahba_qr2_local(fc.E, acc, mag, ka, km));
+    y.w = sel_(reflected, yr.w, y.w); y.x = sel_(reflected, yr.x, y.x);
+    y.y = sel_(reflected, yr.y, y.y); y.z = sel_(reflected, yr.z, y.z);
+  }
+  return y;
+}
+
+// Prediction + Correction with the measurement quaternion y (filter frame, any sign) already computed.
+template <typename F, bool WANT_FLIP, bool COMP, typename FlagT>
+PKF_HD void ekf_step_measured(Quat<F>& x, Quat<F>& xlo, Sym4<F>& P, FilterConst<F>& fc, const Vec3<F>& gyro,
+                              const Quat<F>& y, F h, FlagT& flip, bool flip_wanted = true) {
+  Sym4<F> K;
+  Quat<F> inc, z;
+  ekf_predict<F, COMP>(x, P, fc, gyro, h, K, inc, z);
+  const F sg = one_with_sign_(dot4(y, z));        // the comparator, literally: -1 when dot(y, z) < 0      :73-75
+  flip = FlagT();
+  if (WANT_FLIP && flip_wanted) flip = reference_flip_quat(fc, y, sg);
+  const F e0 = fma_(sg, y.w, -z.w), e1 = fma_(sg, y.x, -z.x), e2 = fma_(sg, y.y, -z.y), e3 = fma_(sg, y.z, -z.z);   // :76
+  ekf_update<F, COMP>(x, xlo, P, fc, K, z, inc, e0, e1, e2, e3);
+}
+
+template <typename F, int ALGO, bool WANT_FLIP, bool COMP, typename FlagT>
+PKF_HD void ekf_step(Quat<F>& x, Quat<F>& xlo, Sym4<F>& P, FilterConst<F>& fc, const Vec3<F>& gyro,
+                     const Vec3<F>& acc, const Vec3<F>& mag, F h, FlagT& flip, bool flip_wanted = true) {
+  // flip_wanted: launch-uniform run-time switch under WANT_FLIP -- a launch that stores the trajectory but
+  // not the flip mask skips the reference's branch rule altogether
+  if constexpr (ALGO == WAHBA_QR2) {
+    ekf_step_measured<F, WANT_FLIP, COMP>(x, xlo, P, fc, gyro, measure_quat(fc, acc, mag), h, flip, flip_wanted);
+  } else {
+    Sym4<F> K;
+    Quat<F> inc, z;
+    ekf_predict<F, COMP>(x, P, fc, gyro, h, K, inc, z);
+    // ---- Correction (PKF/ExtendedKalmanFilter.py:70-80) ----
+    F e0, e1, e2, e3;
+    if constexpr (ALGO == WAHBA_PRECOMPUTED) {
+      // stream rows 3..6 carry the Wahba quaternion in the reference's own sign convention (the output of
+      // getQuarternion, :71): apply the comparator literally -- negate when dot(y, z) < 0            :73-75
+      const Quat<F> y = {acc.x, acc.y, acc.z, mag.x};
+      const auto neg = dot4(y, z) < F(0);
+      flip = neg;
+      const F sg = sel_(neg, F(-1), F(1));
+      e0 = fma_(sg, y.w, -z.w); e1 = fma_(sg, y.x, -z.x); e2 = fma_(sg, y.y, -z.y); e3 = fma_(sg, y.z, -z.z);   // :76
+    } else {
+      F ka = abs_(acc.z), km = F(1) - ka;                                       // :71
+      // Rm: the Wahba rotation in the filter frame (E^T R)
+      Mat3<F> Rm = frame_transposed_times(fc.E, wahba_jacobi(fc.ra, fc.rm, acc, mag, ka, km, kJacobiSweepsFused));
+      // measurement quaternion with the comparator's sign already applied          :73-75
+      F n2;
+      Quat<F> y = rotation_to_quat_aligned(Rm, z, n2);     // un-normalised: 4 (y.z) y
+      flip = FlagT();
+      if (WANT_FLIP && flip_wanted) flip = reference_flip_local(fc, Rm, y);   // only the signs of y matter
+      // innovation e = y/|y| - z, the normalisation folded into the subtraction     :76
+      const F inv = rsqrt_(n2);
+      e0 = fma_(y.w, inv, -z.w); e1 = fma_(y.x, inv, -z.x); e2 = fma_(y.y, inv, -z.y); e3 = fma_(y.z, inv, -z.z);
+      const auto unrelated = n2 < F(0.16);
+      if (any_(unrelated)) {
+        // |y.z| < 0.1: prediction and measurement are unrelated (never in a tracking filter; can happen
+        // on the first sample of a badly initialised one).  Use the selection-based conversion there.
+        Quat<F> yf = y;
+        quat_fallback_unaligned(Rm, z, unrelated, yf);
+        if (WANT_FLIP && flip_wanted) flip = reference_flip_local(fc, Rm, yf);
+        e0 = sel_(unrelated, yf.w - z.w, e0); e1 = sel_(unrelated, yf.x - z.x, e1);
+        e2 = sel_(unrelated, yf.y - z.y, e2); e3 = sel_(unrelated, yf.z - z.z, e3);
+      }
+    }
+    ekf_update<F, COMP>(x, xlo, P, fc, K, z, inc, e0, e1, e2, e3);
+  }
 }
 
 // Process-noise scale g |x|^2 for the FIRST step of a launch.  A state within 1e-5 of unit norm (the initial
