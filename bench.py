@@ -55,6 +55,7 @@ def parse():
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target wall time of the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-numa-bind", action="store_true", help="do not pin the process to the CPUs local to its GPU")
     ap.add_argument("--no-variants", action="store_true", help="skip the context measurements of the other kernels")
     ap.add_argument("--precise-state", action="store_true",
                     help="compensated two-float state (needed for R >> Q sweeps, not for the Q=1, R=0.1 headline config)")
@@ -220,6 +221,9 @@ def run_ours(args):
     assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback)"
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    # one process per GPU: keep this rank's pinned staging memory (e2e) on the socket its GPU hangs off
+    all_cpus = os.sched_getaffinity(0)
+    affinity = None if args.no_numa_bind else SH.bind_host_to_gpu(local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
@@ -364,7 +368,7 @@ def run_ours(args):
                "timesteps": Te, "seconds_per_pass": dt_e,
                "note": "posekf_replay_host_f32: pinned host [T,9,N] stream -> double-buffered H2D chunks -> kernel -> "
                        "D2H of final X,P; bound by the host link (36 B per filter-step)",
-               "h2d_gbs": h2d / dt_e / 1e9, "host_link_plain_copy_gbs": link_gbs}
+               "h2d_gbs": h2d / dt_e / 1e9, "host_link_plain_copy_gbs": link_gbs, "host_affinity": affinity}
         del host
 
     if rank != 0:
@@ -412,10 +416,11 @@ def run_ours(args):
         "frac_of_roofline": steps_per_s_kernel * max(t_fp32, t_hbm),
     }
     # ncu traffic: dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of this kernel
-    # (profiles/r01_replay_tma*_ncu_full.json, taken at 200 timesteps), scaled per launch to this run's timesteps
+    # (profiles/r01_replay_packed_ncu_full.json, taken at 200 timesteps), scaled per launch to this run's timesteps;
+    # the scalar and precise kernels have older captures under profiles/history/
     try:
-        name = ("r01_replay_tma_compensated_ncu_full.json" if args.precise_state else
-                "r01_replay_packed_ncu_full.json" if packed else "r01_replay_tma_ncu_full.json")
+        name = ("history/r01_replay_tma_compensated_ncu_full.json" if args.precise_state else
+                "r01_replay_packed_ncu_full.json" if packed else "history/r01_replay_tma_ncu_full.json")
         prof = json.load(open(os.path.join(ROOT, "profiles", name)))
         per_step = prof["dram_bytes_per_launch"] / prof["workload"]["filter_steps"]
         roofline["traffic"] = per_step * N * T
@@ -440,6 +445,7 @@ def run_ours(args):
         "variants_gsteps_per_s_1gpu_250_timesteps": variants,
     }
     if not args.no_cpu_baseline:
+        os.sched_setaffinity(0, all_cpus)          # the CPU arm uses every host core again
         line["cpu_baseline"] = cpu_baseline(args.cpu_seconds)
         try:
             line["cpu_baseline_compiled"] = cpu_baseline_compiled()

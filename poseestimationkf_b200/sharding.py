@@ -71,3 +71,44 @@ def max_over_ranks(value: float, device, group=None) -> float:
     t = torch.tensor([value], dtype=torch.float64, device=device)
     dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
     return float(t.item())
+
+
+def _parse_cpulist(text: str) -> set[int]:
+    cpus: set[int] = set()
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        lo, _, hi = part.partition("-")
+        cpus.update(range(int(lo), int(hi or lo) + 1))
+    return cpus
+
+
+def gpu_local_cpus(device_index: int) -> set[int]:
+    """CPUs of the NUMA node the GPU's PCIe root hangs off (sysfs `local_cpulist`); empty if unknown."""
+    import os
+
+    try:
+        props = torch.cuda.get_device_properties(device_index)
+        bdf = f"{props.pci_domain_id:04x}:{props.pci_bus_id:02x}:{props.pci_device_id:02x}.0"
+        with open(f"/sys/bus/pci/devices/{bdf}/local_cpulist") as fh:
+            cpus = _parse_cpulist(fh.read())
+        return cpus & set(os.sched_getaffinity(0))
+    except Exception:
+        return set()
+
+
+def bind_host_to_gpu(device_index: int) -> str | None:
+    """Pin this process to the CPUs next to its GPU BEFORE it allocates pinned host buffers.
+
+    The host-buffer replay (`replay_host`) streams 36 B per filter-step over PCIe; with one process per GPU
+    on a two-socket box, a staging buffer that lives on the other socket makes every H2D copy cross the
+    inter-socket link, which several ranks then share.  Linux allocates (and CUDA pins) pages on the node of the
+    allocating thread, so binding first keeps each rank's stream on its own socket.  Returns a description of
+    what was done (for logs), or None when the topology is not exposed."""
+    import os
+
+    cpus = gpu_local_cpus(device_index)
+    if not cpus:
+        return None
+    os.sched_setaffinity(0, cpus)
+    return f"{len(cpus)} cpus local to gpu {device_index} ({min(cpus)}-{max(cpus)})"

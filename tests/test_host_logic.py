@@ -131,3 +131,13 @@ def test_log_reader_matches_the_reference_reader():
     assert streams.shape == (d.n_steps(), 9, 1) and dt.shape == (d.n_steps(),)
     np.testing.assert_allclose(dt.numpy(), 0.01, rtol=1e-6)
     np.testing.assert_allclose(streams[:, 3:6, 0].numpy(), np.asarray(d.acc_1), rtol=1e-6)
+
+
+def test_cpulist_parsing_and_numa_binding_without_gpu():
+    from poseestimationkf_b200 import sharding as SH
+    assert SH._parse_cpulist("0-3,8,10-11\n") == {0, 1, 2, 3, 8, 10, 11}
+    assert SH._parse_cpulist("") == set()
+    # no CUDA device / no sysfs topology: binding is a no-op that says so
+    import torch
+    if not torch.cuda.is_available():
+        assert SH.bind_host_to_gpu(0) is None
