@@ -50,7 +50,7 @@ def wahba(acc_ref, mag_ref, acc, mag, ka, km, *, precision="f32", algo="qr2", sw
     km = np.ascontiguousarray(np.broadcast_to(np.asarray(km, dtype=np.float32), (N,)))
     q = np.empty((4, N))
     R = np.empty((9, N)) if want_R else None
-    rc = lib().hostsim_wahba(C.c_int(0 if precision == "f32" else 1), C.c_int(0 if algo == "qr2" else 1),
+    rc = lib().hostsim_wahba(C.c_int(0 if precision == "f32" else 1), C.c_int({"qr2": 0, "jacobi": 1, "quat2": 2}[algo]),
                              C.c_int(sweeps), C.c_int64(N), *[_p(a, C.c_float) for a in arrs],
                              _p(ka, C.c_float), _p(km, C.c_float), _p(q, C.c_double), _p(R, C.c_double))
     assert rc == 0

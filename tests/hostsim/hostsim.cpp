@@ -126,6 +126,13 @@ int hostsim_wahba(int precision, int algo, int sweeps, int64_t N, const float* a
       Vec3<F> rm = {(F)mag_ref[n], (F)mag_ref[N + n], (F)mag_ref[2 * N + n]};
       Vec3<F> a = {(F)acc[n], (F)acc[N + n], (F)acc[2 * N + n]};
       Vec3<F> m = {(F)mag[n], (F)mag[N + n], (F)mag[2 * N + n]};
+      if (algo == 2) {
+        // the fused step's measurement: closed-form quaternion in the filter frame, mapped back by qE (sign arbitrary)
+        FilterConst<F> fc = make_filter_const<F>(ra, rm, F(1), F(1));
+        Quat<F> qq = qmul(fc.qE, wahba_quat2_local<F>(fc.E, a, m, (F)ka[n], (F)km[n]));
+        out_q[n] = qq.w; out_q[N + n] = qq.x; out_q[2 * N + n] = qq.y; out_q[3 * N + n] = qq.z;
+        return;
+      }
       Mat3<F> R = algo == 0 ? wahba_qr2<F>(frame_from_pair<F>(ra, rm), a, m, (F)ka[n], (F)km[n])
                             : wahba_jacobi<F>(ra, rm, a, m, (F)ka[n], (F)km[n], sweeps);
       Quat<F> qq = rotation_to_quat_ref<F>(R);

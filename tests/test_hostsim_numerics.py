@@ -171,3 +171,59 @@ def test_packed_lanes_equal_scalar(golden_traj):
     b, _, fb = H.replay_packed(S, 0.01, ar, mr, 1.0, 0.1)
     np.testing.assert_array_equal(a, b)
     np.testing.assert_array_equal(fa, fb)
+
+
+@pytest.mark.parametrize("tag", ["half", "refw"])
+def test_closed_form_measurement_quaternion_f32(golden_wahba, tag):
+    """wahba_quat2_local (the fused step's measurement: Markley's two-observation closed form in the filter frame)
+    against the reference's getQuarternion outputs, float32 and float64; sign is the comparator's business."""
+    g = golden_wahba
+    for prec, tol in (("f64", 1e-9), ("f32", 2e-6)):
+        q = H.wahba(g["acc_ref"].T, g["mag_ref"].T, g["acc"].T, g["mag"].T, g[f"{tag}_ka"], g[f"{tag}_km"],
+                    precision=prec, algo="quat2")
+        assert np.isfinite(q).all()
+        np.testing.assert_allclose(np.linalg.norm(q, axis=0), 1.0, atol=1e-6)
+        ang = O.quat_angle(q.T, g[f"{tag}_q"])
+        assert ang.max() < tol, (prec, ang.max())
+
+
+def test_closed_form_measurement_near_its_singularity_and_both_alpha_signs():
+    """The closed form divides by 1 + b3.r3 (reference normal . measured normal); the half-turn of the measured
+    pair keeps that >= 1.  Attitudes are drawn uniformly AND concentrated where the un-turned formula is singular
+    (measured normal opposite to the reference normal, to 1e-7 rad), with the reference's near-rank-1 weights."""
+    rng = np.random.default_rng(11)
+    M = 4000
+
+    def unit(v):
+        return v / np.linalg.norm(v, axis=-1, keepdims=True)
+
+    def rot(axis, ang):
+        axis = unit(axis)
+        K = np.zeros(axis.shape[:-1] + (3, 3))
+        K[..., 0, 1], K[..., 0, 2], K[..., 1, 0] = -axis[..., 2], axis[..., 1], axis[..., 2]
+        K[..., 1, 2], K[..., 2, 0], K[..., 2, 1] = -axis[..., 0], -axis[..., 1], axis[..., 0]
+        a = ang[..., None, None]
+        return np.eye(3) + np.sin(a) * K + (1 - np.cos(a)) * (K @ K)
+
+    acc_ref, mag_ref = unit(rng.normal(size=(M, 3))), unit(rng.normal(size=(M, 3)))
+    n_ref = unit(np.cross(acc_ref, mag_ref))
+    # body->reference rotations: half are half-turns about an axis perpendicular to the reference normal (which send
+    # the normal to its opposite), perturbed by 10^-7 .. 10^-1 rad; the rest uniform
+    perp = unit(np.cross(n_ref, rng.normal(size=(M, 3))))
+    R = rot(perp, np.full(M, np.pi)) @ rot(rng.normal(size=(M, 3)), 10.0 ** rng.uniform(-7, -1, M))
+    uni = rng.random(M) < 0.5
+    R[uni] = rot(rng.normal(size=(M, 3)), rng.uniform(0, np.pi, M))[uni]
+    acc = np.einsum("nji,nj->ni", R, acc_ref).astype(np.float32)       # measured = R^T reference
+    mag = np.einsum("nji,nj->ni", R, mag_ref).astype(np.float32)
+    ka = np.abs(acc[:, 2]).astype(np.float32)
+    ka[::7] = 10.0 ** rng.uniform(-6, -2, ka[::7].shape)               # near rank-1 weights on top
+    km = (1.0 - ka).astype(np.float32)
+    ar32, mr32 = acc_ref.astype(np.float32), mag_ref.astype(np.float32)
+    qref = O.wahba_batched(ar32.astype(np.float64), mr32.astype(np.float64), acc.astype(np.float64), mag.astype(np.float64),
+                           ka.astype(np.float64), km.astype(np.float64))
+    qref = qref[1] if isinstance(qref, tuple) else qref
+    for prec, tol in (("f64", 1e-8), ("f32", 3e-6)):
+        q = H.wahba(ar32.T, mr32.T, acc.T, mag.T, ka, km, precision=prec, algo="quat2")
+        good = np.isfinite(qref).all(axis=1)          # the reference's own 3-branch conversion is NaN/garbage at identity
+        ang = O.quat_angle(q.T[good], qref[good])
+        assert ang.max() < tol, (prec, ang.max())
