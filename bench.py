@@ -34,10 +34,10 @@ BYTES_PER_STEP = 36            # 9 float32 inputs (final-state-only replay)
 # not counted), stage by stage in DESIGN.md "Roofline"; the SASS FFMA/FMUL/FADD/MUFU census of the
 # loop body gives the same number.  (SURVEY.md's 1570 is the un-restructured reference algorithm.)
 # qr2: dynamic opcode census of the shipped packed kernel (profiles/r01_replay_packed_opcode_census.json):
-# 121.0 FMA + 83.4 MUL + 39.1 ADD lane operations + 8 MUFU per filter-step = 372.5 flops, 243.5 FP32 lane operations
-# (+ 12 FSEL, which also issue to the FP32 pipe on sm_100).
-FLOPS = {"qr2": 372.5, "jacobi": 1292}
-FP32_LANE_OPS = {"qr2": 255.5}    # FP32-pipe lane operations per filter-step (FMA, MUL and ADD each occupy one lane-cycle)
+# 121.0 FMA + 79.4 MUL + 39.1 ADD lane operations + 8 MUFU per filter-step = 368.6 flops, 239.5 FP32 lane operations
+# (+ 10 FSEL, which also issue to the FP32 pipe on sm_100).
+FLOPS = {"qr2": 368.6, "jacobi": 1292}
+FP32_LANE_OPS = {"qr2": 249.5}    # FP32-pipe lane operations per filter-step (FMA, MUL and ADD each occupy one lane-cycle)
 FLOPS_COMPENSATED_EXTRA = 32      # two-sum folding of the state (ncu: 536 + 10 MUFU flops per filter-step)
 
 

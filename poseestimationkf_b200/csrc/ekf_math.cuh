@@ -184,6 +184,7 @@ template <typename F> struct Mat4 { F m[4][4]; };
 template <typename F> struct RefFrame {
   Vec3<F> e1, e2, e3;
   F s11, s12, s22;
+  F r12, r22;       // s12/s11, s22/s11 (used by the closed-form measurement, whose scale is free)
 };
 
 template <typename F> PKF_HD F dot3(const Vec3<F>& a, const Vec3<F>& b) {
@@ -217,6 +218,7 @@ template <typename F> PKF_HD RefFrame<F> frame_from_pair(const Vec3<F>& a, const
   fr.e2.x = mp.x * ip; fr.e2.y = mp.y * ip; fr.e2.z = mp.z * ip;
   fr.s22 = np2 * ip;
   fr.e3 = cross3(fr.e1, fr.e2);
+  fr.r12 = fr.s12 * ia; fr.r22 = fr.s22 * ia;      // ia = 1/s11
   return fr;
 }
 
@@ -525,11 +527,13 @@ PKF_HD Mat3<F> wahba_qr2_local(const RefFrame<F>& E, const Vec3<F>& a, const Vec
 // when r3.z < 0 the measured pair is first half-turned about the body x axis (y and z components
 // negated, so r3.z -> |r3.z|) and the half-turn is composed back into the result, q (x) (0,1,0,0) =
 // (-x, w, z, -y); 1 + b3.r3 >= 1 always.
-// 54 FP32 operations + 3 MUFU for the UNIT quaternion (sign arbitrary), against 92 for frame, 2x2 polar
-// factor, rotation matrix and matrix->quaternion.
+// 50 FP32 operations + 3 MUFU for the quaternion and its inverse norm (sign arbitrary), against 92 for frame, 2x2
+// polar factor, rotation matrix and matrix->quaternion.
 // ------------------------------------------------------------------------------------------
+// Returns the UN-NORMALISED quaternion and, through inv_norm, 1/|y|: the fused step folds the normalisation into
+// its innovation (e = (sg/|y|) y - z), one multiplication instead of four.
 template <typename F>
-PKF_HD Quat<F> wahba_quat2_local(const RefFrame<F>& E, const Vec3<F>& a, const Vec3<F>& m, F ka, F km) {
+PKF_HD Quat<F> wahba_quat2_local(const RefFrame<F>& E, const Vec3<F>& a, const Vec3<F>& m, F ka, F km, F& inv_norm) {
   const Vec3<F> c = cross3(a, m);
   // half-turn of the measured pair when c.z < 0: sigma = sign(c.z) multiplies the y and z components of a, m
   // and c; it cancels in every product of two flipped quantities, four conditional negations remain
@@ -537,7 +541,8 @@ PKF_HD Quat<F> wahba_quat2_local(const RefFrame<F>& E, const Vec3<F>& a, const V
   const F ic = rsqrt_(dot3(c, c));
   const F rx = c.x * ic, ry0 = c.y * ic;                          // r3 = (rx, sigma ry0, |c.z| ic)
   const F rxs = flipsign_(rx, c.z), ry = flipsign_(ry0, c.z);
-  const F A1 = ka * E.s11, B1 = km * E.s12, B2 = km * E.s22;
+  // weights times the reference pair (s11,0,0), (s12,s22,0), all divided by s11 (the result's scale is free)
+  const F A1 = ka, B1 = km * E.r12, B2 = km * E.r22;
   const F S = fma_(B2, mys, fma_(B1, m.x, A1 * a.x));             // sum w_i u_i.v_i
   const F Vx0 = B2 * m.z;                                         // sum w_i u_i x v_i = (sigma Vx0, sigma Vy0, Vz)
   const F Vy0 = -fma_(B1, m.z, A1 * a.z);
@@ -554,8 +559,7 @@ PKF_HD Quat<F> wahba_quat2_local(const RefFrame<F>& E, const Vec3<F>& a, const V
   y.x = -fma_(q, rx, -(p * ry));
   y.y = -fma_(q, ry, p * rx);
   y.z = -(q * d);
-  const F in = rsqrt_(dot4(y, y));
-  y.w *= in; y.x *= in; y.y *= in; y.z *= in;
+  inv_norm = rsqrt_(dot4(y, y));
   // undo the half-turn of the measured pair:  y (x) (0,1,0,0) = (-x, w, z, -y)
   Quat<F> o;
   o.w = flipsign_(selsign_(c.z, y.x, y.w), c.z); o.x = selsign_(c.z, y.w, y.x);
@@ -963,31 +967,34 @@ PKF_HD void ekf_update(Quat<F>& x, Quat<F>& xlo, Sym4<F>& P, FilterConst<F>& fc,
 }
 
 // The measurement of one sample: getQuarternion(acc, mag, |a_z|, 1 - |a_z|) (PKF/ExtendedKalmanFilter.py:71) as a
-// unit quaternion in the filter frame, sign arbitrary.  It depends on the sample and the filter's reference frame
-// only -- not on the state -- so a kernel may compute it ahead of the step that consumes it.
-template <typename F> PKF_HD Quat<F> measure_quat(const FilterConst<F>& fc, const Vec3<F>& acc, const Vec3<F>& mag) {
+// quaternion in the filter frame, sign arbitrary, un-normalised, with 1/|y| in inv_norm.  It depends on the sample
+// and the filter's reference frame only -- not on the state.
+template <typename F>
+PKF_HD Quat<F> measure_quat(const FilterConst<F>& fc, const Vec3<F>& acc, const Vec3<F>& mag, F& inv_norm) {
   const F ka = abs_(acc.z), km = F(1) - ka;
-  Quat<F> y = wahba_quat2_local(fc.E, acc, mag, ka, km);
+  Quat<F> y = wahba_quat2_local(fc.E, acc, mag, ka, km, inv_norm);
   const auto reflected = km < F(0);      // |a_z| > 1 (un-normalised accelerometer): a negative weight, the closed
   if (any_(reflected)) {                 // form does not apply -- rank-2 SVD form for those lanes (rare path)
     const Quat<F> yr = rotation_to_quat_best(wahba_qr2_local(fc.E, acc, mag, ka, km));
     y.w = sel_(reflected, yr.w, y.w); y.x = sel_(reflected, yr.x, y.x);
     y.y = sel_(reflected, yr.y, y.y); y.z = sel_(reflected, yr.z, y.z);
+    inv_norm = sel_(reflected, F(1), inv_norm);
   }
   return y;
 }
 
-// Prediction + Correction with the measurement quaternion y (filter frame, any sign) already computed.
+// Prediction + Correction with the measurement quaternion y (filter frame, any sign, norm 1/inv_norm) already computed.
 template <typename F, bool WANT_FLIP, bool COMP, typename FlagT>
 PKF_HD void ekf_step_measured(Quat<F>& x, Quat<F>& xlo, Sym4<F>& P, FilterConst<F>& fc, const Vec3<F>& gyro,
-                              const Quat<F>& y, F h, FlagT& flip, bool flip_wanted = true) {
+                              const Quat<F>& y, F inv_norm, F h, FlagT& flip, bool flip_wanted = true) {
   Sym4<F> K;
   Quat<F> inc, z;
   ekf_predict<F, COMP>(x, P, fc, gyro, h, K, inc, z);
   const F sg = one_with_sign_(dot4(y, z));        // the comparator, literally: -1 when dot(y, z) < 0      :73-75
   flip = FlagT();
   if (WANT_FLIP && flip_wanted) flip = reference_flip_quat(fc, y, sg);
-  const F e0 = fma_(sg, y.w, -z.w), e1 = fma_(sg, y.x, -z.x), e2 = fma_(sg, y.y, -z.y), e3 = fma_(sg, y.z, -z.z);   // :76
+  const F sn = sg * inv_norm;                     // e = sg y/|y| - z                                      :76
+  const F e0 = fma_(sn, y.w, -z.w), e1 = fma_(sn, y.x, -z.x), e2 = fma_(sn, y.y, -z.y), e3 = fma_(sn, y.z, -z.z);
   ekf_update<F, COMP>(x, xlo, P, fc, K, z, inc, e0, e1, e2, e3);
 }
 
@@ -997,7 +1004,9 @@ PKF_HD void ekf_step(Quat<F>& x, Quat<F>& xlo, Sym4<F>& P, FilterConst<F>& fc, c
   // flip_wanted: launch-uniform run-time switch under WANT_FLIP -- a launch that stores the trajectory but
   // not the flip mask skips the reference's branch rule altogether
   if constexpr (ALGO == WAHBA_QR2) {
-    ekf_step_measured<F, WANT_FLIP, COMP>(x, xlo, P, fc, gyro, measure_quat(fc, acc, mag), h, flip, flip_wanted);
+    F inv_norm;
+    const Quat<F> y = measure_quat(fc, acc, mag, inv_norm);
+    ekf_step_measured<F, WANT_FLIP, COMP>(x, xlo, P, fc, gyro, y, inv_norm, h, flip, flip_wanted);
   } else {
     Sym4<F> K;
     Quat<F> inc, z;

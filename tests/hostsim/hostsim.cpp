@@ -129,7 +129,10 @@ int hostsim_wahba(int precision, int algo, int sweeps, int64_t N, const float* a
       if (algo == 2) {
         // the fused step's measurement: closed-form quaternion in the filter frame, mapped back by qE (sign arbitrary)
         FilterConst<F> fc = make_filter_const<F>(ra, rm, F(1), F(1));
-        Quat<F> qq = qmul(fc.qE, wahba_quat2_local<F>(fc.E, a, m, (F)ka[n], (F)km[n]));
+        F inv;
+        Quat<F> yl = wahba_quat2_local<F>(fc.E, a, m, (F)ka[n], (F)km[n], inv);
+        yl.w *= inv; yl.x *= inv; yl.y *= inv; yl.z *= inv;
+        Quat<F> qq = qmul(fc.qE, yl);
         out_q[n] = qq.w; out_q[N + n] = qq.x; out_q[2 * N + n] = qq.y; out_q[3 * N + n] = qq.z;
         return;
       }

@@ -7,6 +7,7 @@ TAG=${1:-r01x}
 mkdir -p gpurun_out
 python -m pytest tests -m gpu -x -q > gpurun_out/${TAG}_pytest_gpu.log 2>&1; echo "pytest exit $?"; tail -3 gpurun_out/${TAG}_pytest_gpu.log
 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/${TAG}_smoke.log 2>&1; echo "smoke exit $?"; tail -3 gpurun_out/${TAG}_smoke.log
+python tests/parity_report.py gpurun_out/${TAG}_parity_report.json > /dev/null 2> gpurun_out/${TAG}_parity_report.err; echo "parity report exit $?"
 python bench.py > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err; echo "bench exit $?"
 python -c "
 import json; d=json.load(open('gpurun_out/${TAG}_bench.json'))
