@@ -289,8 +289,9 @@ template <typename F> PKF_HD void two_sum(F a, F b, F& hi, F& lo) {
 // ------------------------------------------------------------------------------------------
 // Covariance propagation  P <- A P A^T + B(x) (q I3) B(x)^T,  A = 0.5*Omega(w)  (hw = 0.5 w),
 // x = state BEFORE the RK4 step.        (PKF/ExtendedKalmanFilter.py:59-61)
-//   B B^T = 0.25 (|x|^2 I - x x^T)  =>  second term = qq (|x|^2 I - x x^T), qq = q/4; the caller passes
-//   s = qq |x|^2 (the fused step knows |x| = 1 after its own normalisation and passes qq itself).
+//   B B^T = 0.25 (|x|^2 I - x x^T)  =>  second term = s (I - x^ x^T) with x^ = x/|x| and s = (q/4)|x|^2: the fused
+//   step keeps its state normalised and passes s = q/4, except on the first step of a launch that was handed a
+//   non-unit state (adopt_state); qq is unused when the noise is added here.
 //
 // A is the matrix of a RIGHT quaternion multiplication by the pure quaternion (0, hw).  Symmetric 4x4
 // matrices split as  P = alpha I + sum_ij T_ij L_i R_j  (L_i / R_j: left / right multiplication by the
@@ -327,7 +328,7 @@ PKF_HD Sym4<F> propagate_cov(const Sym4<F>& P, const Vec3<F>& hw, const Quat<F>&
   if constexpr (NOISE) {
     const F al = fma_(c4, A4, s);                      // alpha' + qq |x|^2
     const F am = al - T00, ap = al + T00;
-    const F yw = qq * x.w, yx = qq * x.x, yy = qq * x.y, yz = qq * x.z;
+    const F yw = s * x.w, yx = s * x.x, yy = s * x.y, yz = s * x.z;     // |x| = 1 inside a launch (adopt_state)
     N.a00 = fma_(-yw, x.w, am - t1);
     N.a11 = fma_(-yx, x.x, am + t1);
     N.a22 = fma_(-yy, x.y, ap + t2);
@@ -882,7 +883,7 @@ template <typename F> struct FilterConst {
   RefFrame<F> E;          // from (acc_0, mag_0)
   Vec3<F> ra, rm;         // raw reference vectors (used by the Jacobi variant only)
   F g;                    // Q/(4R): process noise in units of r
-  F gs;                   // g |x|^2 of the CURRENT state: g after any step of the filter (it normalises), see noise_scale
+  F gs;                   // g |x|^2 of the CURRENT state: g after any step of the filter (it normalises), see adopt_state
   Quat<F> qE;             // unit quaternion of the rotation [e1 e2 e3]: filter frame -> reference frame
 };
 
@@ -926,7 +927,7 @@ PKF_HD void ekf_predict(const Quat<F>& x, const Sym4<F>& P, const FilterConst<F>
   hw.x = F(0.5) * gyro.x; hw.y = F(0.5) * gyro.y; hw.z = F(0.5) * gyro.z;
   if constexpr (COMP) {
     Sym4<F> M = propagate_cov<F, false>(P, hw, x, fc.g, fc.gs);               // :59-61, noise kept apart
-    K = kalman_gain_sm(M, x, fc.g);                                           // :63-66
+    K = kalman_gain_sm(M, x, fc.gs);                                          // :63-66
   } else {
     Sym4<F> Pp = propagate_cov<F, true>(P, hw, x, fc.g, fc.gs);               // :59-61 (in units of r)
     K = kalman_gain_unit(Pp);                                                 // :63-66
@@ -1048,13 +1049,19 @@ PKF_HD void ekf_step(Quat<F>& x, Quat<F>& xlo, Sym4<F>& P, FilterConst<F>& fc, c
   }
 }
 
-// Process-noise scale g |x|^2 for the FIRST step of a launch.  A state within 1e-5 of unit norm (the initial
-// [1,0,0,0], or any state this filter produced: it normalises every step, to ~2e-7) counts as unit, so that a
-// replay cut into chunks is bit-identical to the unchunked one; a caller-supplied state that is not normalised
-// gets its true |x|^2, as B(x) Q B(x)^T has in the reference (PKF/ExtendedKalmanFilter.py:51-56,61).
-template <typename F> PKF_HD F noise_scale(F g, const Quat<F>& x) {
+// A state handed to a launch.  The reference normalises at the end of every step (and the predicted state right
+// after RK4, PKF/ExtendedKalmanFilter.py:40), so the only place a non-unit |x| ever acts is the process noise of the
+// FIRST step, B(x) Q B(x)^T = (q/4)|x|^2 (I - x^ x^T); RK4 is linear, so everything else sees x^ = x/|x|.  The
+// launch therefore normalises the incoming state once and carries g|x|^2 as the noise scale of its first step
+// (fc.gs; every later step has g).  A state within 1e-5 of unit norm -- the initial [1,0,0,0], or anything this
+// filter produced -- is taken as is, so that a replay cut into chunks stays bit-identical to the unchunked one.
+template <typename F> PKF_HD void adopt_state(FilterConst<F>& fc, Quat<F>& x, Quat<F>& xlo) {
   const F n2 = dot4(x, x);
-  return sel_(abs_(n2 - F(1)) < F(1e-5), g, g * n2);
+  const auto unit = abs_(n2 - F(1)) < F(1e-5);
+  fc.gs = sel_(unit, fc.g, fc.g * n2);
+  const F sc = sel_(unit, F(1), rsqrt_(n2));
+  x.w *= sc; x.x *= sc; x.y *= sc; x.z *= sc;
+  xlo.w *= sc; xlo.x *= sc; xlo.y *= sc; xlo.z *= sc;
 }
 
 template <typename F>

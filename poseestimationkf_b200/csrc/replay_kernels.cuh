@@ -55,7 +55,7 @@ __device__ __forceinline__ void load_filter(const ReplayParams& p, int64_t n, in
     f.lm = {sl[3 * N], sl[4 * N], sl[5 * N]};
   }
   // the step runs in the filter frame (ekf_math.cuh); the state buffers hold the reference frame unless flagged
-  f.fc.gs = noise_scale(f.fc.g, f.x);
+  adopt_state(f.fc, f.x, f.xlo);
   if (uses_filter_frame<ALGO>() && !(p.state_flags & kStateInFilterFrame)) enter_filter_frame(f.fc, f.x, f.xlo, f.P, COMP);
 }
 
@@ -312,7 +312,7 @@ __global__ void __launch_bounds__(kThreads2, (LPF && COMP) ? (PKF_MIN_CTAS2 > 6 
       f.la = {ld2(sl), ld2(sl + N), ld2(sl + 2 * N)};
       f.lm = {ld2(sl + 3 * N), ld2(sl + 4 * N), ld2(sl + 5 * N)};
     }
-    f.fc.gs = noise_scale(f.fc.g, f.x);
+    adopt_state(f.fc, f.x, f.xlo);
     if (uses_filter_frame<ALGO>() && !(p.state_flags & kStateInFilterFrame)) enter_filter_frame(f.fc, f.x, f.xlo, f.P, COMP);
   }
   const float dt0 = p.dt[0];

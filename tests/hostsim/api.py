@@ -20,8 +20,9 @@ def _p(a, t):
 
 
 def replay(streams, dt, acc_ref, mag_ref, q, r, *, precision="f32", algo="qr2", lpf_acc=-1.0, lpf_mag=-1.0,
-           compensated=False):
+           compensated=False, x0=None, p0_over_r=None):
     """streams [T,9,N] f32, acc_ref/mag_ref [3,N] f32, q/r [N] f32, dt scalar or [T] f32 (seconds).
+    x0 [4,N] / p0_over_r [10,N] (upper triangle of P0/r): initial state as the kernels' state buffers hold it.
     Returns traj [T,4,N] f64, flips [T,N] bool, P [10,N] f64."""
     streams = np.ascontiguousarray(streams, dtype=np.float32)
     T, _, N = streams.shape
@@ -33,11 +34,13 @@ def replay(streams, dt, acc_ref, mag_ref, q, r, *, precision="f32", algo="qr2", 
     traj = np.empty((T, 4, N))
     flips = np.empty((T, N), dtype=np.uint8)
     P = np.empty((10, N))
+    x0 = None if x0 is None else np.ascontiguousarray(x0, dtype=np.float32)
+    p0 = None if p0_over_r is None else np.ascontiguousarray(p0_over_r, dtype=np.float32)
     rc = lib().hostsim_replay(C.c_int(0 if precision == "f32" else 1), C.c_int(0 if algo == "qr2" else 1),
                               C.c_int(int(compensated)), C.c_int64(N), C.c_int64(T), _p(streams, C.c_float), _p(dt, C.c_double),
                               C.c_int(int(dt.size > 1)), _p(acc_ref, C.c_float), _p(mag_ref, C.c_float),
                               _p(q, C.c_float), _p(r, C.c_float), C.c_float(lpf_acc), C.c_float(lpf_mag),
-                              _p(traj, C.c_double), _p(flips, C.c_uint8), _p(P, C.c_double))
+                              _p(traj, C.c_double), _p(flips, C.c_uint8), _p(P, C.c_double), _p(x0, C.c_float), _p(p0, C.c_float))
     assert rc == 0
     return traj, flips.astype(bool), P
 

@@ -13,7 +13,8 @@ using namespace pkf;
 template <typename F, int ALGO, bool COMP>
 static void replay_t(int64_t N, int64_t T, const float* streams, const double* dt, int dt_per_step,
                      const float* acc_ref, const float* mag_ref, const float* q, const float* r,
-                     float lpf_acc, float lpf_mag, double* out_traj, uint8_t* out_flip, double* out_P) {
+                     float lpf_acc, float lpf_mag, double* out_traj, uint8_t* out_flip, double* out_P,
+                     const float* x0 = nullptr, const float* p0 = nullptr) {
   for (int64_t n = 0; n < N; ++n) {
     Vec3<F> ra = {(F)acc_ref[0 * N + n], (F)acc_ref[1 * N + n], (F)acc_ref[2 * N + n]};
     Vec3<F> rm = {(F)mag_ref[0 * N + n], (F)mag_ref[1 * N + n], (F)mag_ref[2 * N + n]};
@@ -22,6 +23,10 @@ static void replay_t(int64_t N, int64_t T, const float* streams, const double* d
     const F ir = F(1) / (F)r[n];   // the step carries P/r
     Sym4<F> P = {ir, F(0), F(0), F(0), ir, F(0), F(0), ir, F(0), ir};
     Vec3<F> la = {F(0), F(0), F(0)}, lm = {F(0), F(0), F(0)};
+    if (x0) x = {(F)x0[n], (F)x0[N + n], (F)x0[2 * N + n], (F)x0[3 * N + n]};          // state buffers as the kernels take them:
+    if (p0) P = {(F)p0[n], (F)p0[N + n], (F)p0[2 * N + n], (F)p0[3 * N + n], (F)p0[4 * N + n], (F)p0[5 * N + n],   // X [4][N], P/r [10][N]
+                 (F)p0[6 * N + n], (F)p0[7 * N + n], (F)p0[8 * N + n], (F)p0[9 * N + n]};
+    adopt_state(fc, x, xlo);
     enter_filter_frame(fc, x, xlo, P, COMP);     // as the kernels do at the start of a launch
     for (int64_t t = 0; t < T; ++t) {
       const float* s = streams + (size_t)t * 9 * N + n;
@@ -104,8 +109,9 @@ int hostsim_replay_packed(int comp, int64_t N, int64_t T, const float* streams, 
 // precision: 0 = float32, 1 = float64 ; algo: 0 = QR2, 1 = Jacobi
 int hostsim_replay(int precision, int algo, int comp, int64_t N, int64_t T, const float* streams, const double* dt,
                    int dt_per_step, const float* acc_ref, const float* mag_ref, const float* q, const float* r,
-                   float lpf_acc, float lpf_mag, double* out_traj, uint8_t* out_flip, double* out_P) {
-#define GO(F, A) if (comp) replay_t<F, A, true>(N, T, streams, dt, dt_per_step, acc_ref, mag_ref, q, r, lpf_acc, lpf_mag, out_traj, out_flip, out_P); else replay_t<F, A, false>(N, T, streams, dt, dt_per_step, acc_ref, mag_ref, q, r, lpf_acc, lpf_mag, out_traj, out_flip, out_P)
+                   float lpf_acc, float lpf_mag, double* out_traj, uint8_t* out_flip, double* out_P, const float* x0,
+                   const float* p0) {
+#define GO(F, A) if (comp) replay_t<F, A, true>(N, T, streams, dt, dt_per_step, acc_ref, mag_ref, q, r, lpf_acc, lpf_mag, out_traj, out_flip, out_P, x0, p0); else replay_t<F, A, false>(N, T, streams, dt, dt_per_step, acc_ref, mag_ref, q, r, lpf_acc, lpf_mag, out_traj, out_flip, out_P, x0, p0)
   if (precision == 0 && algo == 0) GO(float, WAHBA_QR2);
   else if (precision == 0 && algo == 1) GO(float, WAHBA_JACOBI);
   else if (precision == 1 && algo == 0) GO(double, WAHBA_QR2);

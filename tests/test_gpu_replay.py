@@ -443,3 +443,39 @@ def test_precomputed_measurement_stream_sweep(cuda):
     assert torch.equal(lp_state, b.lpf)
     with pytest.raises(_lib.PosekfError):       # a measurement stream cannot be low-passed again
         B.replay(meas, imu.acc_ref, imu.mag_ref, dt=imu.dt, wahba="precomputed", lpf_alpha_acc=0.1)
+
+
+@pytest.mark.parametrize("staging", ["ldg", "tma", "tma_packed"])
+def test_unnormalised_sensors_and_caller_supplied_initial_state(cuda, staging):
+    """What the reference accepts, the replay accepts: accelerometer in units of 1.6 g (|a_z| crosses 1, so the
+    reference's weight 1 - |a_z| changes sign -> reflected Wahba branch), magnetometer in arbitrary units, and an
+    initial state that is neither [1,0,0,0] nor normalised with a full initial covariance (B(x) Q B(x)^T scales
+    with |x|^2 on the first step only: the reference normalises at the end of every step)."""
+    N, T = 512, 200
+    imu = make_imu(N, T, seed=17, sigma=0.01, device=cuda)
+    streams = imu.streams.clone()
+    streams[:, 3:6] *= 1.6
+    streams[:, 6:9] *= 47.0
+    az = streams[:, 5].abs().cpu().numpy()
+    assert (az > 1).mean() > 0.1 and (az < 1).mean() > 0.1
+    rng = np.random.default_rng(2)
+    x0 = rng.normal(size=(N, 4)) * rng.uniform(0.5, 2.0, (N, 1))
+    x0[::5] = [1.0, 0.0, 0.0, 0.0]
+    M = rng.normal(size=(N, 4, 4)) * 0.3
+    P0 = M @ M.transpose(0, 2, 1) + 0.5 * np.eye(4)
+    x0_32, P0_32 = x0.astype(np.float32), P0.astype(np.float32)
+    P0_32 = (P0_32 + P0_32.transpose(0, 2, 1)) / 2
+    st = B.ReplayState.initial(N, cuda, r=0.1, P0=torch.from_numpy(P0_32))
+    st.x.copy_(torch.from_numpy(x0_32.T.copy()))
+    _, traj, _ = B.replay(streams, imu.acc_ref, imu.mag_ref, dt=imu.dt, q=1.0, r=0.1, state=st, store_trajectory=True,
+                          staging=staging, precise_state=False)
+    ref = _oracle(streams, imu.acc_ref, imu.mag_ref, imu.dt, 1.0, float(np.float32(0.1)), x0=x0_32.astype(np.float64),
+                  P0=P0_32.astype(np.float64))
+    got = traj.cpu().numpy().astype(np.float64)
+    assert np.isfinite(got).all()
+    # samples with 1 - |a_z| ~ 0 are rank-1 Wahba problems (parity undefined, DESIGN.md section 2)
+    ok = (np.abs(1 - az) > 1e-3).all(axis=0)
+    assert ok.sum() > N // 2
+    ang = O.quat_angle(got[:, ok], ref["X"][:, ok])
+    assert ang.max() < TOL, ang.max()
+    assert (np.sum(got[:, ok] * ref["X"][:, ok], axis=-1) > 0).all()
