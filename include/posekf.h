@@ -32,7 +32,9 @@ extern "C" {
 #define POSEKF_ENODEV (-3)      /* no sm_100 device / driver entry point unavailable      */
 
 /* Wahba solver selection (see DESIGN.md "Wahba stage") */
-#define POSEKF_WAHBA_QR2    0   /* rank-2 SVD: QR of both vector pairs + closed-form 2x2 polar factor */
+#define POSEKF_WAHBA_QR2    0   /* rank-2 forms that never build B: stand-alone entry points use the QR of both vector
+                                   pairs + closed-form 2x2 polar factor; the fused replay solves for the quaternion
+                                   directly (two-observation closed form) and keeps the former for negative weights */
 #define POSEKF_WAHBA_JACOBI 1   /* B formed as in PKF/Wahba.py:11-13, one-sided Jacobi SVD in registers */
 #define POSEKF_WAHBA_PRECOMPUTED 2 /* posekf_replay_f32 only: stream rows 3-6 already hold the Wahba quaternion
                                       (posekf_measurement_stream_f32) -- for (Q,R) sweeps over shared streams */
