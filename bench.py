@@ -154,8 +154,11 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * base["seconds"], "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "reference Python EKF replay (oracle port) on host cores, bounded sample",
-                       "filters_per_gpu": args.filters, "timesteps": args.timesteps},
+            "config": {"workload": f"batched EKF replay: {args.filters} independent filters x {args.timesteps} steps per GPU, Q=1, R=0.1, "
+                                   "dt=0.01 (BASELINE.json configs[1]); reference arm = the reference's Python EKF (oracle port, "
+                                   "float64 numpy) on all host cores, each step a bounded sample of that workload (one independent "
+                                   "trajectory per core)",
+                       "filters_per_gpu": args.filters, "timesteps": args.timesteps, "sample": base["sample"]},
             "cpu_baseline": base,
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
