@@ -23,7 +23,12 @@
 //   * P is kept as its upper triangle (10 values).
 //   * rank(B_wahba) = 2 always (two observations), so the SVD is taken on the 2x2 core of a QR
 //     factorisation of both vector pairs (see wahba_qr2) -- this is also what makes fp32 safe when
-//     the reference's weights ka=|a_z|, km=1-|a_z| drive B towards rank 1.
+//     the reference's weights ka=|a_z|, km=1-|a_z| drive B towards rank 1.  The fused step goes one step
+//     further and evaluates the two-observation optimum directly as a quaternion (wahba_quat2_local).
+//   * A = 0.5*Omega(w) is a right quaternion multiplication: in the (1 + 3x3) split of symmetric 4x4 matrices
+//     A P A^T touches the 3x3 block only (propagate_cov).
+//   * The recursion is equivariant under a fixed left rotation of the state, so the fused step runs in the
+//     coordinates of the reference frame built from (acc_0, mag_0) ("filter frame").
 #pragma once
 
 #include <math.h>
