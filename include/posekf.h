@@ -157,7 +157,7 @@ int posekf_wahba_f32(int64_t n, const float* acc_ref, const float* mag_ref, int 
                      void* stream);
 
 /* Comparison tracks of the tuning workflow (the curves the reference plots beside the filter,
- * PKF/main_file.py:40-46,50-52 and Results/*.png): for N filters over T steps of the same stream
+ * PKF/main_file.py:40-46,50-52 and the Results/ plots): for N filters over T steps of the same stream
  * layout as posekf_replay_f32,
  *   out_gyro  [T][N][4]  gyro-only attitude: RK4 without correction from gyro_state (X=[1,0,0,0] when
  *             gyro_state is NULL)   -- SRV/KalmanFilter.cpp:149 `Quarternion_Gyro_pure`

@@ -4,6 +4,8 @@ import ctypes
 import os
 import re
 
+import pytest
+
 from poseestimationkf_b200 import _lib, build
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -83,3 +85,48 @@ def test_product_has_no_cpu_path():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in src.replace("oracle consumes", "").replace("the oracle", "") or f == "synth.py", f
+
+
+def _build_c_example(tmp_path):
+    """examples/replay_capi.c: plain C (gcc, no CUDA headers) against include/posekf.h and the shared library."""
+    import subprocess
+    lib_dir = os.path.dirname(build.build())
+    exe = os.path.join(str(tmp_path), "replay_capi")
+    subprocess.check_call(["gcc", "-O2", "-Wall", "-Werror", "-I" + os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "examples", "replay_capi.c"), "-o", exe, "-L" + lib_dir, "-lposekf_b200",
+                           "-Wl,-rpath," + lib_dir])
+    return exe
+
+
+def test_c_example_compiles_and_links_against_the_header(tmp_path):
+    exe = _build_c_example(tmp_path)
+    import subprocess
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 2 and "usage" in out.stderr          # no compute call without a GPU
+
+
+@pytest.mark.gpu
+def test_c_example_replays_from_host_memory(tmp_path):
+    """The C program (pageable host buffers, no torch anywhere) against the float64 oracle."""
+    import subprocess
+    import numpy as np
+    import torch
+    from oracle import ekf_oracle as O
+    from poseestimationkf_b200.synth import make_imu
+    exe = _build_c_example(tmp_path)
+    N, T = 1000, 150
+    imu = make_imu(N, T, seed=4, sigma=0.01, device=torch.device("cpu"))
+    S, ar, mr = imu.streams.numpy(), imu.acc_ref.numpy(), imu.mag_ref.numpy()
+    fin, fout = os.path.join(str(tmp_path), "in.bin"), os.path.join(str(tmp_path), "out.bin")
+    with open(fin, "wb") as fh:
+        for a in (S, ar, mr):
+            fh.write(np.ascontiguousarray(a, dtype=np.float32).tobytes())
+    subprocess.check_call([exe, str(N), str(T), fin, fout])
+    out = np.fromfile(fout, dtype=np.float32)
+    x = out[:4 * N].reshape(4, N)
+    traj = out[14 * N:].reshape(T, N, 4).astype(np.float64)
+    ref = O.replay_batched(np.full(T, 0.01 * 1e9), S[:, 0:3], S[:, 3:6], S[:, 6:9], ar.T, mr.T, 1.0, float(np.float32(0.1)))
+    ang = O.quat_angle(traj, ref["X"])
+    assert ang.max() < 1e-5, ang.max()
+    assert (np.sum(traj * ref["X"], axis=-1) > 0).all()
+    np.testing.assert_array_equal(x.T, traj[-1].astype(np.float32))
