@@ -103,23 +103,35 @@ template <int ALGO> __global__ void __launch_bounds__(128) tracks_kernel(const T
   float4* og = p.out_gyro ? reinterpret_cast<float4*>(p.out_gyro) + n : nullptr;
   float4* ow = p.out_wahba ? reinterpret_cast<float4*>(p.out_wahba) + n : nullptr;
   const float dt0 = p.dt[0];
+  // the next step's channels are requested before the current step is computed and stored (one thread walks one
+  // filter through time, so without this every step would expose a full memory latency)
+  const bool need_gyro = og || p.gyro_state;
+  float cur[kChannels], nxt[kChannels];
+  auto load_step = [&](float (&v)[kChannels], const float* q) {
+#pragma unroll
+    for (int c = 0; c < kChannels; ++c) v[c] = ((c < 3) ? need_gyro : (ow != nullptr)) ? ldg_stream(q + c * Ns) : 0.f;
+  };
+  if (p.T > 0) load_step(cur, s);
   for (int64_t t = 0; t < p.T; ++t, s += kChannels * Ns) {
+    if (t + 1 < p.T) load_step(nxt, s + kChannels * Ns);
     const float h = p.dt_per_step ? __ldg(p.dt + t) : dt0;
-    if (og || p.gyro_state) {
-      Vec3<float> hw = {0.5f * ldg_stream(s), 0.5f * ldg_stream(s + Ns), 0.5f * ldg_stream(s + 2 * Ns)};
+    if (need_gyro) {
+      Vec3<float> hw = {0.5f * cur[0], 0.5f * cur[1], 0.5f * cur[2]};
       g = rk4_step<float>(g, hw, h);
-      if (og) { *og = make_float4(g.w, g.x, g.y, g.z); og += N; }
+      if (og) { stg_stream4(og, g.w, g.x, g.y, g.z); og += N; }
     }
     if (ow) {
-      Vec3<float> a = {ldg_stream(s + 3 * Ns), ldg_stream(s + 4 * Ns), ldg_stream(s + 5 * Ns)};
-      Vec3<float> m = {ldg_stream(s + 6 * Ns), ldg_stream(s + 7 * Ns), ldg_stream(s + 8 * Ns)};
+      Vec3<float> a = {cur[3], cur[4], cur[5]};
+      Vec3<float> m = {cur[6], cur[7], cur[8]};
       float ka = p.k_acc, km = p.k_mag;
       if (p.weights_from_acc) { ka = fabsf(a.z); km = 1.f - ka; }
       Mat3<float> R = (ALGO == WAHBA_QR2) ? wahba_qr2<float>(E, a, m, ka, km) : wahba_jacobi<float>(ra, rm, a, m, ka, km, 6);
       Quat<float> q = rotation_to_quat_ref<float>(R);
-      *ow = make_float4(q.w, q.x, q.y, q.z);
+      stg_stream4(ow, q.w, q.x, q.y, q.z);
       ow += N;
     }
+#pragma unroll
+    for (int c = 0; c < kChannels; ++c) cur[c] = nxt[c];
   }
   if (p.gyro_state) { p.gyro_state[n] = g.w; p.gyro_state[N + n] = g.x; p.gyro_state[2 * N + n] = g.y; p.gyro_state[3 * N + n] = g.z; }
 }
@@ -152,20 +164,34 @@ __global__ void __launch_bounds__(256) preprocess_kernel(const PreprocessParams 
     la = {p.lpf_state[n], p.lpf_state[N + n], p.lpf_state[2 * N + n]};
     lm = {p.lpf_state[3 * N + n], p.lpf_state[4 * N + n], p.lpf_state[5 * N + n]};
   }
-  for (int64_t t = 0; t < p.T; ++t) {
+  // one step's inputs: 3 gyro + 6 + 6 bracketing samples + 4 time spans; the next step's are requested before the
+  // current step is computed and stored (see tracks_kernel)
+  struct Step { float g[3], y1[6], y2[6], ts[4]; };
+  auto load_step = [&](Step& v, int64_t t) {
     const float* y1 = p.raw_prev + t * 6 * N + n;
     const float* y2 = p.raw_next + t * 6 * N + n;
     const float* ts = p.tspan + t * 4 * N + n;
-    float* o = p.out_streams + t * 9 * N + n;
     const float* g = p.gyro + t * 3 * N + n;
-    o[0] = ldg_stream(g); o[N] = ldg_stream(g + N); o[2 * N] = ldg_stream(g + 2 * N);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) v.g[c] = ldg_stream(g + c * N);
+#pragma unroll
+    for (int c = 0; c < 6; ++c) { v.y1[c] = ldg_stream(y1 + c * N); v.y2[c] = ldg_stream(y2 + c * N); }
+#pragma unroll
+    for (int c = 0; c < 4; ++c) v.ts[c] = ldg_stream(ts + c * N);
+  };
+  Step cur, nxt;
+  if (p.T > 0) load_step(cur, 0);
+  for (int64_t t = 0; t < p.T; ++t) {
+    if (t + 1 < p.T) load_step(nxt, t + 1);
+    float* o = p.out_streams + t * 9 * N + n;
+    o[0] = cur.g[0]; o[N] = cur.g[1]; o[2 * N] = cur.g[2];
 #pragma unroll
     for (int s = 0; s < 2; ++s) {                      // s = 0 accel, 1 mag
-      const float t21 = ldg_stream(ts + (2 * s) * N), t31 = ldg_stream(ts + (2 * s + 1) * N);
+      const float t21 = cur.ts[2 * s], t31 = cur.ts[2 * s + 1];
       float v[3];
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
-        const float a = ldg_stream(y1 + (3 * s + c) * N), b = ldg_stream(y2 + (3 * s + c) * N);
+        const float a = cur.y1[3 * s + c], b = cur.y2[3 * s + c];
         v[c] = (b - a) / t21 * t31 + a;                // Parser.cpp:264, same operation order
       }
       const float den = sqrtf(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);     // Parser.cpp:223-227
@@ -174,6 +200,7 @@ __global__ void __launch_bounds__(256) preprocess_kernel(const PreprocessParams 
       if (s == 1 && lpm) { lowpass<float>(lm, u, p.alpha_mag, 1.f - p.alpha_mag); u = lm; }
       o[(3 + 3 * s) * N] = u.x; o[(4 + 3 * s) * N] = u.y; o[(5 + 3 * s) * N] = u.z;
     }
+    cur = nxt;
   }
   if (p.lpf_state) {
     p.lpf_state[n] = la.x; p.lpf_state[N + n] = la.y; p.lpf_state[2 * N + n] = la.z;
@@ -238,20 +265,34 @@ template <int ALGO> __global__ void __launch_bounds__(128) measurement_stream_ke
     la = {p.lpf_state[n], p.lpf_state[Ns + n], p.lpf_state[2 * Ns + n]};
     lm = {p.lpf_state[3 * Ns + n], p.lpf_state[4 * Ns + n], p.lpf_state[5 * Ns + n]};
   }
-  for (int64_t t = 0; t < p.T; ++t) {
+  // Without the low-pass a sample's solution does not depend on its predecessors, so time is split over blockIdx.y
+  // (thread (n, y) solves t = y, y + gridDim.y, ...): a sweep has few streams (256) and many steps (5000), and one
+  // thread per stream walking all of them would leave the GPU empty.  With the low-pass gridDim.y is 1.
+  // The next step's channels are requested before the current step is solved and stored (see tracks_kernel).
+  const int64_t t0 = blockIdx.y, dt_ = gridDim.y;
+  float cur[kChannels], nxt[kChannels];
+  auto load_step = [&](float (&v)[kChannels], int64_t t) {
     const float* s = p.streams + t * kChannels * Ns + n;
+#pragma unroll
+    for (int c = 0; c < kChannels; ++c) v[c] = ldg_stream(s + c * Ns);
+  };
+  if (t0 < p.T) load_step(cur, t0);
+  for (int64_t t = t0; t < p.T; t += dt_) {
+    if (t + dt_ < p.T) load_step(nxt, t + dt_);
     float* o = p.out + t * kChannels * Ns + n;
-    o[0] = ldg_stream(s); o[Ns] = ldg_stream(s + Ns); o[2 * Ns] = ldg_stream(s + 2 * Ns);
-    Vec3<float> a = {ldg_stream(s + 3 * Ns), ldg_stream(s + 4 * Ns), ldg_stream(s + 5 * Ns)};
-    Vec3<float> m = {ldg_stream(s + 6 * Ns), ldg_stream(s + 7 * Ns), ldg_stream(s + 8 * Ns)};
+    o[0] = cur[0]; o[Ns] = cur[1]; o[2 * Ns] = cur[2];      // plain stores: a sweep re-reads this stream from L2
+    Vec3<float> a = {cur[3], cur[4], cur[5]};
+    Vec3<float> m = {cur[6], cur[7], cur[8]};
     if (p.alpha_acc >= 0.f) { lowpass<float>(la, a, p.alpha_acc, 1.f - p.alpha_acc); a = la; }
     if (p.alpha_mag >= 0.f) { lowpass<float>(lm, m, p.alpha_mag, 1.f - p.alpha_mag); m = lm; }
     const float ka = fabsf(a.z), km = 1.f - ka;                                // PKF/ExtendedKalmanFilter.py:71
     Mat3<float> R = (ALGO == WAHBA_QR2) ? wahba_qr2<float>(E, a, m, ka, km) : wahba_jacobi<float>(ra, rm, a, m, ka, km, 6);
     const Quat<float> q = rotation_to_quat_ref<float>(R);
     o[3 * Ns] = q.w; o[4 * Ns] = q.x; o[5 * Ns] = q.y; o[6 * Ns] = q.z; o[7 * Ns] = 0.f; o[8 * Ns] = 0.f;
+#pragma unroll
+    for (int c = 0; c < kChannels; ++c) cur[c] = nxt[c];
   }
-  if (p.lpf_state) {
+  if (p.lpf_state && blockIdx.y == 0) {
     p.lpf_state[n] = la.x; p.lpf_state[Ns + n] = la.y; p.lpf_state[2 * Ns + n] = la.z;
     p.lpf_state[3 * Ns + n] = lm.x; p.lpf_state[4 * Ns + n] = lm.y; p.lpf_state[5 * Ns + n] = lm.z;
   }

@@ -459,8 +459,13 @@ int posekf_measurement_stream_f32(int64_t n_streams, int64_t n_steps, const floa
   if ((lpf_alpha_acc >= 0.f || lpf_alpha_mag >= 0.f) && !lpf_state) return POSEKF_EINVAL;
   MeasStreamParams p{n_streams, n_steps, streams, acc_ref, mag_ref, lpf_alpha_acc, lpf_alpha_mag, lpf_state, out_streams};
   cudaStream_t st = (cudaStream_t)stream;
-  if (wahba_algo == POSEKF_WAHBA_QR2) measurement_stream_kernel<WAHBA_QR2><<<blocks_for(n_streams, 128), 128, 0, st>>>(p);
-  else if (wahba_algo == POSEKF_WAHBA_JACOBI) measurement_stream_kernel<WAHBA_JACOBI><<<blocks_for(n_streams, 128), 128, 0, st>>>(p);
+  // time is split over gridDim.y when the samples are independent (no low-pass): aim at ~2 Mi threads
+  const bool sequential = lpf_alpha_acc >= 0.f || lpf_alpha_mag >= 0.f;
+  int64_t ty = sequential ? 1 : ((int64_t)2 << 20) / (blocks_for(n_streams, 128) * (int64_t)128);
+  ty = ty < 1 ? 1 : (ty > n_steps ? n_steps : (ty > 65535 ? 65535 : ty));
+  const dim3 grid(blocks_for(n_streams, 128), (unsigned)ty);
+  if (wahba_algo == POSEKF_WAHBA_QR2) measurement_stream_kernel<WAHBA_QR2><<<grid, 128, 0, st>>>(p);
+  else if (wahba_algo == POSEKF_WAHBA_JACOBI) measurement_stream_kernel<WAHBA_JACOBI><<<grid, 128, 0, st>>>(p);
   else return POSEKF_EINVAL;
   return launch_status();
 }
