@@ -207,9 +207,11 @@ def replay(streams: torch.Tensor, acc_ref: torch.Tensor, mag_ref: torch.Tensor, 
     tuning objective: `loss` [N] (created zeroed when None; pass it back in for chunked replays) is
     incremented by sum_t 1-(X_t.truth_t)^2 and is available as `state.loss`.
     `precise_state` selects the precise variant for extreme Q/R ratios (two-float state so that gains
-    ~1e-7 are not lost when R >> Q; Sherman-Morrison gain when Q >> R; +17 % time); None = automatic:
-    on when q or r are per-filter tensors (a tuning sweep), when r/q >= 100 or q/r >= 1e4, off otherwise
-    (the default Q=1, R=0.1 does not need it).
+    ~1e-7 are not lost when R >> Q; Sherman-Morrison gain when Q >> R; +25 % time); None = automatic:
+    on when r/q >= 100 or q/r >= 1e4, off otherwise (the default Q=1, R=0.1 does not need it).  With per-filter
+    q / r tensors the rule is applied per cell of a sweep (blocks of Ns filters that share one tuning; two
+    launches over a permutation of the cells) when no per-step output is requested, and to the whole batch
+    (precise everywhere) otherwise.
     `share_measurements`: in the sweep layout (N > Ns) the Wahba solution of a sample is the same for every
     filter that shares its trajectory, so it is solved once per (trajectory, step) (`measurement_stream`) and
     the replay runs with `wahba="precomputed"`; None = automatic for N >= 4 Ns without a low-pass stage.
@@ -246,6 +248,13 @@ def replay(streams: torch.Tensor, acc_ref: torch.Tensor, mag_ref: torch.Tensor, 
         state.p.mul_(old / new)
     state.r = r
     if precise_state is None:
+        if (isinstance(q, torch.Tensor) or isinstance(r, torch.Tensor)) and N > Ns and N % Ns == 0 \
+                and out_traj is None and not store_trajectory and not store_flips and not use_lpf and T > 0:
+            # a (Q,R) sweep: only the cells with r/q >= 100 or q/r >= 1e4 need the precise variant (+25 % time)
+            mixed = _replay_sweep_mixed(streams, acc_ref, mag_ref, dt=dt, q=q, r=r, state=state, N=N, Ns=Ns, truth=truth,
+                                        loss=loss, wahba=wahba, staging=staging, keep_filter_frame=keep_filter_frame)
+            if mixed is not None:
+                return mixed
         precise_state = (state.x_lo is not None or isinstance(q, torch.Tensor) or isinstance(r, torch.Tensor)
                          or float(r) >= 100.0 * float(q) or float(q) >= 1.0e4 * float(r))
     if precise_state and state.x_lo is None:
@@ -294,6 +303,45 @@ def replay(streams: torch.Tensor, acc_ref: torch.Tensor, mag_ref: torch.Tensor, 
     if wahba != "precomputed":
         state.frame = "filter" if keep_filter_frame else "reference"
     return state, out_traj, flips
+
+
+def _replay_sweep_mixed(streams, acc_ref, mag_ref, *, dt, q, r, state, N, Ns, truth, loss, wahba, staging, keep_filter_frame):
+    """Sweep layout with automatic precision: the cells (blocks of Ns filters sharing one (q, r)) whose tuning is
+    extreme run the precise variant, the others the plain one -- two launches over a cell permutation that keeps
+    every filter on its own stream column (n % Ns).  Returns None when one launch serves all cells."""
+    dev = streams.device
+    q_t, r_t = _per_filter(q, N, dev), _per_filter(r, N, dev)
+    need = ((r_t >= 100.0 * q_t) | (q_t >= 1.0e4 * r_t)).view(N // Ns, Ns).any(dim=1)
+    cells_p, cells_n = need.nonzero().flatten(), (~need).nonzero().flatten()
+    if cells_p.numel() == 0 or cells_n.numel() == 0:
+        return None
+    lane = torch.arange(Ns, device=dev)
+    parts = []
+    if truth is not None and loss is None:
+        loss = torch.zeros((N,), dtype=torch.float32, device=dev)
+    for cells, precise in ((cells_n, False), (cells_p, True)):
+        idx = (cells[:, None] * Ns + lane[None, :]).flatten()
+        sub = ReplayState(state.x[:, idx].contiguous(), state.p[:, idx].contiguous(), r_t[idx].contiguous(), None, None,
+                          state.x_lo[:, idx].contiguous() if (precise and state.x_lo is not None) else None, state.frame)
+        sub_loss = loss[idx].contiguous() if truth is not None else None
+        replay(streams, acc_ref, mag_ref, dt=dt, q=q_t[idx].contiguous(), r=sub.r, state=sub, n_filters=idx.numel(), truth=truth,
+               loss=sub_loss, precise_state=precise, share_measurements=False, wahba=wahba, staging=staging,
+               keep_filter_frame=keep_filter_frame)
+        parts.append((idx, sub, sub_loss, precise))
+    if state.x_lo is None:
+        state.x_lo = torch.zeros((4, N), dtype=torch.float32, device=dev)
+    for idx, sub, sub_loss, precise in parts:
+        state.x[:, idx] = sub.x
+        state.p[:, idx] = sub.p
+        if precise:
+            state.x_lo[:, idx] = sub.x_lo
+        if truth is not None:
+            loss[idx] = sub_loss
+        state.frame = sub.frame
+    if truth is not None:
+        state.loss = loss
+    state.r = r
+    return state, None, None
 
 
 class HostWorkspace:

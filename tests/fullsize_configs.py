@@ -48,7 +48,7 @@ if "c3" in which:
     N = G1 * G1 * Ns
     truth = imu.q_true.permute(0, 2, 1).to(torch.float32).contiguous()
     out = {}
-    for precise, share in ((True, True), (True, False), (False, True), (False, False)):
+    for precise, share in ((None, True), (True, True), (True, False), (False, True), (False, False)):
         def run():
             st = B.ReplayState.initial(N, dev, r=r_t)
             B.replay(imu.streams, imu.acc_ref, imu.mag_ref, dt=imu.dt, q=q_t, r=r_t, n_filters=N, state=st, truth=truth,

@@ -204,7 +204,7 @@ def test_comparison_tracks_and_tuning_objective(cuda):
     loss = None
     for t0, t1 in ((0, 90), (90, T)):
         B.replay(imu.streams[t0:t1].contiguous(), imu.acc_ref, imu.mag_ref, dt=imu.dt, q=q_t, r=r_t, n_filters=G * Ns,
-                 state=st2, truth=truth[t0:t1].contiguous(), loss=loss)
+                 state=st2, truth=truth[t0:t1].contiguous(), loss=loss, precise_state=True)
         loss = st2.loss
     torch.testing.assert_close(loss, st.loss, rtol=1e-5, atol=1e-9)
     surface = loss.reshape(G, Ns).mean(1)

@@ -294,19 +294,25 @@ def test_compensated_state_long_replay_extreme_tunings(cuda):
     S = imu.streams.cpu().numpy()
     refs = [CO.replay(S, imu.dt * 1e9, imu.acc_ref.cpu().numpy(), imu.mag_ref.cpu().numpy(), float(np.float32(q)),
                       float(np.float32(r))) for q, r in grid]
-    worst = {}
+    worst, by_variant = {}, {}
     for precise in (True, False):
         st, traj, _ = B.replay(imu.streams, imu.acc_ref, imu.mag_ref, dt=imu.dt, q=q_t, r=r_t, n_filters=G * Ns,
                                store_trajectory=True, precise_state=precise)
         got = traj.cpu().numpy().reshape(T, G, Ns, 4)
         worst[precise] = [O.quat_angle(got[:, gi], refs[gi]["X"]).max() for gi in range(G)]
         assert (st.x_lo is not None) == precise
+        by_variant[precise] = st
     assert max(worst[True]) < 1e-6, worst[True]                     # every tuning, incl. both corners, far inside the 1e-5 bar
     assert worst[True][0] < 1e-6 and worst[False][0] > TOL          # the corner needs the compensation ...
     assert worst[False][2] < 1e-6                                   # ... the default tuning does not
-    # automatic selection: per-filter tensors (a sweep) switch it on, the default scalars do not
+    # automatic selection: in a sweep (per-filter tensors) the cells with an extreme tuning run the precise variant,
+    # the others the plain one; the default scalars do not switch it on
     st_auto, _, _ = B.replay(imu.streams, imu.acc_ref, imu.mag_ref, dt=imu.dt, q=q_t, r=r_t, n_filters=G * Ns)
     assert st_auto.x_lo is not None
+    for gi, (q, r) in enumerate(grid):
+        sl = slice(gi * Ns, (gi + 1) * Ns)
+        want = by_variant[bool(r >= 100 * q or q >= 1e4 * r)]
+        assert torch.equal(st_auto.x[:, sl], want.x[:, sl]) and torch.equal(st_auto.p[:, sl], want.p[:, sl]), (q, r)
     st_def, _, _ = B.replay(imu.streams, imu.acc_ref, imu.mag_ref, dt=imu.dt, q=1.0, r=0.1)
     assert st_def.x_lo is None
     # chunked == unchunked also for the two-float state
@@ -314,7 +320,8 @@ def test_compensated_state_long_replay_extreme_tunings(cuda):
     for t0, t1 in ((0, 1777), (1777, T)):
         B.replay(imu.streams[t0:t1].contiguous(), imu.acc_ref, imu.mag_ref, dt=imu.dt, q=q_t, r=r_t, n_filters=G * Ns,
                  state=st_c, precise_state=True, keep_filter_frame=t1 < T)
-    assert torch.equal(st_c.x, st_auto.x) and torch.equal(st_c.x_lo, st_auto.x_lo) and torch.equal(st_c.p, st_auto.p)
+    st_p = by_variant[True]
+    assert torch.equal(st_c.x, st_p.x) and torch.equal(st_c.x_lo, st_p.x_lo) and torch.equal(st_c.p, st_p.p)
 
 
 def test_no_out_of_bounds_writes(cuda):
@@ -431,7 +438,7 @@ def test_precomputed_measurement_stream_sweep(cuda):
         outs.append((st, traj, fl))
     assert torch.equal(outs[0][1], outs[1][1]) and torch.equal(outs[1][1], outs[2][1]) and torch.equal(outs[1][2], outs[2][2])
     # automatic sharing in replay(): N >= 4 Ns
-    auto, _, _ = B.replay(imu.streams, imu.acc_ref, imu.mag_ref, dt=imu.dt, q=q_t, r=r_t, n_filters=G * Ns)
+    auto, _, _ = B.replay(imu.streams, imu.acc_ref, imu.mag_ref, dt=imu.dt, q=q_t, r=r_t, n_filters=G * Ns, precise_state=True)
     assert torch.equal(auto.x, outs[2][0].x)
     plain, _, _ = B.replay(imu.streams, imu.acc_ref, imu.mag_ref, dt=imu.dt, q=q_t, r=r_t, n_filters=G * Ns, share_measurements=False)
     assert O.quat_angle(auto.x.t().cpu().numpy(), plain.x.t().cpu().numpy()).max() < 1e-6
@@ -479,3 +486,45 @@ def test_unnormalised_sensors_and_caller_supplied_initial_state(cuda, staging):
     ang = O.quat_angle(got[:, ok], ref["X"][:, ok])
     assert ang.max() < TOL, ang.max()
     assert (np.sum(got[:, ok] * ref["X"][:, ok], axis=-1) > 0).all()
+
+
+def test_sweep_with_automatic_precision_per_cell(cuda):
+    """A (Q,R) sweep with precise_state=None runs the precise variant only for the cells that need it (r/q >= 100 or
+    q/r >= 1e4): same results as two explicit replays of the two groups, every cell within tolerance of the oracle,
+    loss surface accumulated, and a chunked sweep bit-identical to the unchunked one."""
+    Ns, T = 64, 160
+    imu = make_imu(Ns, T, seed=23, sigma=0.01, device=cuda, keep_truth=True)
+    truth = imu.q_true.permute(0, 2, 1).to(torch.float32).contiguous()
+    grid = [(1e-3, 1e3), (1.0, 0.1), (1e3, 1e-3), (1.0, 1.0), (1e-2, 10.0), (10.0, 1e-2)]
+    G = len(grid)
+    N = G * Ns
+    q_t = _dev(np.repeat([q for q, _ in grid], Ns), cuda)
+    r_t = _dev(np.repeat([r for _, r in grid], Ns), cuda)
+    st, _, _ = B.replay(imu.streams, imu.acc_ref, imu.mag_ref, dt=imu.dt, q=q_t, r=r_t, n_filters=N, truth=truth)
+    assert st.loss is not None and st.loss.shape == (N,) and bool((st.loss > 0).all())
+    x = st.x.cpu().numpy().T.reshape(G, Ns, 4)
+    # what each group must equal bit for bit: the whole sweep replayed with one variant (filters are independent)
+    ref_variant = {}
+    for precise in (False, True):
+        ref_variant[precise], _, _ = B.replay(imu.streams, imu.acc_ref, imu.mag_ref, dt=imu.dt, q=q_t, r=r_t, n_filters=N, truth=truth,
+                                              precise_state=precise)
+    n_precise = 0
+    for gi, (q, r) in enumerate(grid):
+        ref = _oracle(imu.streams, imu.acc_ref, imu.mag_ref, imu.dt, float(np.float32(q)), float(np.float32(r)), store=False)
+        assert O.quat_angle(x[gi], ref["X_final"]).max() < TOL, (q, r)
+        need = r >= 100 * q or q >= 1e4 * r
+        n_precise += need
+        sl = slice(gi * Ns, (gi + 1) * Ns)
+        one = ref_variant[bool(need)]
+        assert torch.equal(one.x[:, sl], st.x[:, sl]) and torch.equal(one.p[:, sl], st.p[:, sl]), (q, r)
+        assert torch.equal(one.loss[sl], st.loss[sl])
+    assert 0 < n_precise < G
+    # chunked == unchunked
+    st2 = None
+    loss = None
+    for t0 in range(0, T, 50):
+        st2, _, _ = B.replay(imu.streams[t0:t0 + 50], imu.acc_ref, imu.mag_ref, dt=imu.dt, q=q_t, r=r_t, n_filters=N,
+                             state=st2, truth=truth[t0:t0 + 50].contiguous(), loss=loss, keep_filter_frame=t0 + 50 < T)
+        loss = st2.loss
+    assert torch.equal(st2.x, st.x) and torch.equal(st2.p, st.p)
+    torch.testing.assert_close(st2.loss, st.loss, rtol=1e-5, atol=1e-7)
