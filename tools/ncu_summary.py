@@ -13,6 +13,7 @@ ap.add_argument("rep")
 ap.add_argument("out_prefix")
 ap.add_argument("--filters", type=int, default=1 << 20)
 ap.add_argument("--timesteps", type=int, default=200)
+ap.add_argument("--bytes-per-step", type=int, default=36, help="algorithmic bytes per filter-step (36 in; +16 with the trajectory stored)")
 a = ap.parse_args()
 
 raw = subprocess.run(["ncu", "-i", a.rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
@@ -62,8 +63,8 @@ summary = {
     "warps_active_pct_of_peak": get("sm__warps_active.avg.pct_of_peak_sustained_active"),
     "dram_bytes_read": rd, "dram_bytes_write": wr,
     "dram_bytes_per_launch": None if rd is None else rd + wr,
-    "algorithmic_bytes_per_launch": steps * 36,
-    "dram_traffic_over_algorithmic": None if rd is None else (rd + wr) / (steps * 36),
+    "algorithmic_bytes_per_launch": steps * a.bytes_per_step,
+    "dram_traffic_over_algorithmic": None if rd is None else (rd + wr) / (steps * a.bytes_per_step),
     "dram_throughput_pct_of_peak": get("dram__throughput.avg.pct_of_peak_sustained_elapsed"),
     "achieved_dram_gbs": None if rd is None else (rd + wr) / (dur_ms * 1e-3) / 1e9,
     "warp_inst_executed": inst,
