@@ -279,3 +279,24 @@ def test_caller_supplied_non_unit_initial_state_and_covariance():
         ang = O.quat_angle(traj.transpose(0, 2, 1), ref["X"])
         # (float64: p0/r was rounded to float32 on the way in, hence 1e-6 rather than 1e-9)
         assert ang.max() < tol, (prec, comp, ang.max(), np.unravel_index(ang.argmax(), ang.shape))
+
+
+def test_closed_form_measurement_with_arbitrary_unnormalised_vectors_and_weights():
+    """Reference vectors and measurements of any length (the reference treats lengths as weights) and any positive
+    weights: the closed form equals the SVD solution (float64 to 2e-12), float32 stays below 1e-6 rad."""
+    rng = np.random.default_rng(3)
+    M = 3000
+    ar = rng.normal(size=(M, 3)) * rng.uniform(0.1, 30, (M, 1)); mr = rng.normal(size=(M, 3)) * rng.uniform(0.1, 60, (M, 1))
+    a = rng.normal(size=(M, 3)) * rng.uniform(0.1, 30, (M, 1)); m = rng.normal(size=(M, 3)) * rng.uniform(0.1, 60, (M, 1))
+    ka, km = rng.uniform(1e-3, 3, M), rng.uniform(1e-3, 3, M)
+    f32 = lambda v: v.astype(np.float32)
+    qref = O.wahba_batched(*[f32(v).astype(np.float64) for v in (ar, mr, a, m, ka, km)])
+
+    def sin_angle(u, v):
+        return np.linalg.norm(np.cross(u, v), axis=1) / np.linalg.norm(u, axis=1) / np.linalg.norm(v, axis=1)
+    ok = (sin_angle(a, m) > 0.1) & (sin_angle(ar, mr) > 0.1) & np.isfinite(qref).all(axis=1)      # away from rank 1
+    assert ok.sum() > 2500
+    for prec, tol in (("f64", 1e-10), ("f32", 1e-6)):
+        q = H.wahba(f32(ar).T, f32(mr).T, f32(a).T, f32(m).T, f32(ka), f32(km), precision=prec, algo="quat2")
+        ang = O.quat_angle(q.T[ok], qref[ok])
+        assert ang.max() < tol, (prec, ang.max())
