@@ -21,6 +21,11 @@ def golden_traj():
 
 
 @pytest.fixture(scope="session")
+def golden_edge():
+    return np.load(os.path.join(GOLDEN, "edge_cases.npz"))
+
+
+@pytest.fixture(scope="session")
 def golden_wahba():
     return np.load(os.path.join(GOLDEN, "wahba_cases.npz"))
 

@@ -30,13 +30,14 @@ from UtilityFunctions import norm, Quart2RPY, DimensionalSplit   # noqa: E402
 from poseestimationkf_b200.synth import make_imu   # noqa: E402
 
 
-def drive(t_ns, gyro, acc, mag, acc0, mag0, q, r):
-    """The loop of Python Kalman Filter/main_file.py:19-47 around the reference classes."""
+def drive(t_ns, gyro, acc, mag, acc0, mag0, q, r, X0=None, P0=None):
+    """The loop of Python Kalman Filter/main_file.py:19-47 around the reference classes (X0 / P0: a caller's own
+    initial state instead of main_file.py:23,26)."""
     k = KalmanFilter(t_ns[0], mag0, acc0, 0.5)
     k.setQ(q)
     k.setR(r)
-    P = np.identity(4)
-    X = np.asarray([1., 0., 0., 0.])
+    P = np.identity(4) if P0 is None else np.array(P0, dtype=np.float64)
+    X = np.asarray([1., 0., 0., 0.]) if X0 is None else np.array(X0, dtype=np.float64)
     Xs, ys, flips = [], [], []
     for i in range(len(gyro)):
         z, P, K = k.Prediction(gyro[i], t_ns[i + 1], X, P)
@@ -69,6 +70,36 @@ def trajectories():
                     f"{tag}_r": np.array([r for _, r in qr])})
     out["dt"] = np.float64(0.01)
     np.savez_compressed(os.path.join(HERE, "ekf_trajectories.npz"), **out)
+
+
+def edge_cases():
+    """What the reference accepts beyond main_file.py's own use: a caller-supplied initial state that is not
+    normalised with a full covariance, and sensors that are not normalised (accelerometer in units of 1.6 g, so that
+    the weight 1 - |a_z| of ExtendedKalmanFilter.py:71 changes sign along the trajectory; magnetometer x 47)."""
+    N, T = 8, 150
+    imu = make_imu(N, T, seed=202, sigma=0.01)
+    S = imu.streams.numpy().copy()
+    a0, m0 = imu.acc_ref.numpy(), imu.mag_ref.numpy()
+    t_ns = np.arange(T + 1, dtype=np.int64) * 10 ** 7
+    rng = np.random.default_rng(9)
+    x0 = (rng.normal(size=(N, 4)) * rng.uniform(0.5, 2.0, (N, 1))).astype(np.float32)
+    M = rng.normal(size=(N, 4, 4)) * 0.3
+    P0 = (M @ M.transpose(0, 2, 1) + 0.5 * np.eye(4)).astype(np.float32)
+    P0 = ((P0 + P0.transpose(0, 2, 1)) / 2).astype(np.float32)
+    out = {"acc_ref": a0, "mag_ref": m0, "x0": x0, "P0": P0, "dt": np.float64(0.01), "q": np.float64(1.0),
+           "r": np.float64(np.float32(0.1))}
+    for tag, scale_a, scale_m, use_x0 in (("state", 1.0, 1.0, True), ("sensors", 1.6, 47.0, False), ("both", 1.6, 47.0, True)):
+        Sx = S.copy()
+        Sx[:, 3:6] *= np.float32(scale_a)
+        Sx[:, 6:9] *= np.float32(scale_m)
+        X = np.empty((T, N, 4)); Pf = np.empty((N, 4, 4)); F = np.empty((T, N), dtype=bool)
+        for n in range(N):
+            X[:, n], Pf[n], _, F[:, n] = drive(
+                t_ns, Sx[:, 0:3, n].astype(np.float64), Sx[:, 3:6, n].astype(np.float64), Sx[:, 6:9, n].astype(np.float64),
+                a0[:, n].astype(np.float64), m0[:, n].astype(np.float64), float(out["q"]), float(out["r"]),
+                X0=x0[n].astype(np.float64) if use_x0 else None, P0=P0[n].astype(np.float64) if use_x0 else None)
+        out.update({f"{tag}_streams": Sx, f"{tag}_X": X, f"{tag}_P": Pf, f"{tag}_flips": F})
+    np.savez_compressed(os.path.join(HERE, "edge_cases.npz"), **out)
 
 
 def wahba_cases():
@@ -198,6 +229,10 @@ def log_format():
 
 
 if __name__ == "__main__":
+    if sys.argv[1:] == ["edge"]:          # only the fixture added later; the others stay byte-identical
+        edge_cases()
+        sys.exit(0)
+    edge_cases()
     log_format()
     trajectories()
     wahba_cases()

@@ -528,3 +528,24 @@ def test_sweep_with_automatic_precision_per_cell(cuda):
         loss = st2.loss
     assert torch.equal(st2.x, st.x) and torch.equal(st2.p, st.p)
     torch.testing.assert_close(st2.loss, st.loss, rtol=1e-5, atol=1e-7)
+
+
+@pytest.mark.parametrize("tag", ["state", "sensors", "both"])
+def test_replay_vs_reference_edge_case_goldens(golden_edge, cuda, tag):
+    """The reference's own outputs (tests/golden/edge_cases.npz) for a non-unit initial state with a full covariance
+    and for un-normalised sensors, every staging."""
+    g = golden_edge
+    S = g[f"{tag}_streams"]
+    T, _, N = S.shape
+    az = np.abs(S[:, 5])
+    ok = (np.abs(1 - az) > 1e-3).all(axis=0)        # 1 - |a_z| ~ 0: rank-1 Wahba problem, parity undefined there
+    for staging in ("ldg", "tma", "tma_packed"):
+        st = B.ReplayState.initial(N, cuda, r=0.1, P0=torch.from_numpy(g["P0"].copy()) if tag != "sensors" else None)
+        if tag != "sensors":
+            st.x.copy_(torch.from_numpy(np.ascontiguousarray(g["x0"].T)))
+        _, traj, _ = B.replay(_dev(S, cuda), _dev(g["acc_ref"], cuda), _dev(g["mag_ref"], cuda), dt=float(g["dt"]), q=float(g["q"]),
+                              r=0.1, state=st, store_trajectory=True, staging=staging, precise_state=False)
+        got = traj.cpu().numpy().astype(np.float64)
+        ang = O.quat_angle(got[:, ok], g[f"{tag}_X"][:, ok])
+        assert ang.max() < TOL, (staging, ang.max())
+        assert (np.sum(got[:, ok] * g[f"{tag}_X"][:, ok], axis=-1) > 0).all()

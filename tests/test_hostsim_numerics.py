@@ -300,3 +300,27 @@ def test_closed_form_measurement_with_arbitrary_unnormalised_vectors_and_weights
         q = H.wahba(f32(ar).T, f32(mr).T, f32(a).T, f32(m).T, f32(ka), f32(km), precision=prec, algo="quat2")
         ang = O.quat_angle(q.T[ok], qref[ok])
         assert ang.max() < tol, (prec, ang.max())
+
+
+@pytest.mark.parametrize("tag", ["state", "sensors", "both"])
+def test_device_math_on_reference_edge_cases(golden_edge, tag):
+    """The device math header (float32 and float64 host builds) against the reference's own outputs for a non-unit
+    initial state with a full covariance and for un-normalised sensors."""
+    g = golden_edge
+    S = g[f"{tag}_streams"]
+    T, _, N = S.shape
+    r = np.float32(g["r"])
+    tri = [(0, 0), (0, 1), (0, 2), (0, 3), (1, 1), (1, 2), (1, 3), (2, 2), (2, 3), (3, 3)]
+    kw = {}
+    if tag != "sensors":
+        kw = dict(x0=g["x0"].T.copy(), p0_over_r=np.stack([g["P0"][:, i, j] for i, j in tri]) / r)
+    az = np.abs(S[:, 5])
+    ok = (np.abs(1 - az) > 1e-3).all(axis=0)        # a sample with 1 - |a_z| ~ 0 is a rank-1 Wahba problem (undefined parity)
+    assert ok.sum() >= N - 2
+    for prec, tol in (("f64", 1e-6), ("f32", TOL)):
+        traj, flips, _ = H.replay(S, float(g["dt"]), g["acc_ref"], g["mag_ref"], np.full(N, float(g["q"]), np.float32),
+                                  np.full(N, r, np.float32), precision=prec, algo="qr2", **kw)
+        got = traj.transpose(0, 2, 1)
+        ang = O.quat_angle(got[:, ok], g[f"{tag}_X"][:, ok])
+        assert ang.max() < tol, (prec, ang.max())
+        assert (np.sum(got[:, ok] * g[f"{tag}_X"][:, ok], axis=-1) > 0).all()

@@ -114,3 +114,24 @@ def test_lowpass_closed_form():
     y = O.lowpass_scalar(x, 0.1)
     t = np.arange(1, 51)[:, None]
     np.testing.assert_allclose(y, x * (1 - 0.9 ** t), rtol=1e-12)
+
+
+def test_oracle_equals_reference_on_edge_cases(golden_edge):
+    """Caller-supplied non-unit X0 with a full P0, and un-normalised sensors (|a_z| > 1: negative magnetometer
+    weight), frozen from the unmodified reference (tests/golden/make_golden.py edge_cases): bit-for-bit."""
+    g = golden_edge
+    T = g["state_streams"].shape[0]
+    t_ns = np.arange(T + 1, dtype=np.int64) * 10 ** 7
+    for tag, use_x0 in (("state", True), ("sensors", False), ("both", True)):
+        S = g[f"{tag}_streams"].astype(np.float64)
+        if tag != "state":
+            az = np.abs(S[:, 5])
+            assert (az > 1).mean() > 0.1 and (az < 1).mean() > 0.1
+        for n in range(S.shape[2]):
+            X, P, flips, _ = O.replay_scalar(t_ns, S[:, 0:3, n], S[:, 3:6, n], S[:, 6:9, n], g["acc_ref"][:, n].astype(np.float64),
+                                             g["mag_ref"][:, n].astype(np.float64), float(g["q"]), float(g["r"]),
+                                             x0=g["x0"][n].astype(np.float64) if use_x0 else None,
+                                             P0=g["P0"][n].astype(np.float64) if use_x0 else None, return_aux=True)
+            np.testing.assert_array_equal(X, g[f"{tag}_X"][:, n])
+            np.testing.assert_array_equal(P, g[f"{tag}_P"][n])
+            np.testing.assert_array_equal(flips, g[f"{tag}_flips"][:, n])
