@@ -141,3 +141,24 @@ def test_cpulist_parsing_and_numa_binding_without_gpu():
     import torch
     if not torch.cuda.is_available():
         assert SH.bind_host_to_gpu(0) is None
+
+
+def test_reference_arm_contract_under_torchrun_world2():
+    """`bench.py --impl reference` launched like our arm (torchrun, N = 2): rank 0 alone times the reference's CPU
+    path and prints ONE JSON line with the contract's keys; the other rank exits 0 without output."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29533", os.path.join(root, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1",
+           "--warmup", "1", "--cpu-seconds", "1"]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [ln for ln in out.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "ekf_filter_steps_per_s" and d["unit"] == "filter-steps/s"
+    assert d["n_gpus"] == 2 and d["higher_is_better"] is True and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
