@@ -130,3 +130,14 @@ def test_c_example_replays_from_host_memory(tmp_path):
     assert ang.max() < 1e-5, ang.max()
     assert (np.sum(traj * ref["X"], axis=-1) > 0).all()
     np.testing.assert_array_equal(x.T, traj[-1].astype(np.float32))
+
+
+def test_header_is_plain_c_and_cxx(tmp_path):
+    """include/posekf.h stands alone: C99 and C++17 translation units that include nothing else compile cleanly."""
+    import subprocess
+    inc = os.path.join(ROOT, "include")
+    for compiler, std, ext in (("gcc", "-std=c99", "c"), ("g++", "-std=c++17", "cpp")):
+        src = os.path.join(str(tmp_path), "tu." + ext)
+        with open(src, "w") as fh:
+            fh.write('#include "posekf.h"\nint main(void) { const char* (*f)(void) = posekf_version; return f ? 0 : 1; }\n')
+        subprocess.check_call([compiler, std, "-Wall", "-Wextra", "-Werror", "-pedantic", "-fsyntax-only", "-I" + inc, src])
