@@ -305,22 +305,33 @@ def replay(streams: torch.Tensor, acc_ref: torch.Tensor, mag_ref: torch.Tensor, 
     return state, out_traj, flips
 
 
+def sweep_partition(q_t: torch.Tensor, r_t: torch.Tensor, n_streams: int):
+    """Filter indices of a sweep split by the precision its cells need.  A cell is a block of `n_streams` consecutive
+    filters (one per trajectory); it needs the precise variant when any of its filters has r/q >= 100 or q/r >= 1e4.
+    Returns (plain, precise) index tensors; both keep whole cells in their original order, so filter k of either group
+    still reads stream column k % n_streams."""
+    n = q_t.numel()
+    if n % n_streams:
+        raise ValueError("a sweep has a whole number of cells")
+    need = ((r_t >= 100.0 * q_t) | (q_t >= 1.0e4 * r_t)).view(n // n_streams, n_streams).any(dim=1)
+    lane = torch.arange(n_streams, device=q_t.device)
+    expand = lambda cells: (cells[:, None] * n_streams + lane[None, :]).flatten()
+    return expand((~need).nonzero().flatten()), expand(need.nonzero().flatten())
+
+
 def _replay_sweep_mixed(streams, acc_ref, mag_ref, *, dt, q, r, state, N, Ns, truth, loss, wahba, staging, keep_filter_frame):
     """Sweep layout with automatic precision: the cells (blocks of Ns filters sharing one (q, r)) whose tuning is
     extreme run the precise variant, the others the plain one -- two launches over a cell permutation that keeps
     every filter on its own stream column (n % Ns).  Returns None when one launch serves all cells."""
     dev = streams.device
     q_t, r_t = _per_filter(q, N, dev), _per_filter(r, N, dev)
-    need = ((r_t >= 100.0 * q_t) | (q_t >= 1.0e4 * r_t)).view(N // Ns, Ns).any(dim=1)
-    cells_p, cells_n = need.nonzero().flatten(), (~need).nonzero().flatten()
-    if cells_p.numel() == 0 or cells_n.numel() == 0:
+    idx_plain, idx_precise = sweep_partition(q_t, r_t, Ns)
+    if idx_plain.numel() == 0 or idx_precise.numel() == 0:
         return None
-    lane = torch.arange(Ns, device=dev)
     parts = []
     if truth is not None and loss is None:
         loss = torch.zeros((N,), dtype=torch.float32, device=dev)
-    for cells, precise in ((cells_n, False), (cells_p, True)):
-        idx = (cells[:, None] * Ns + lane[None, :]).flatten()
+    for idx, precise in ((idx_plain, False), (idx_precise, True)):
         sub = ReplayState(state.x[:, idx].contiguous(), state.p[:, idx].contiguous(), r_t[idx].contiguous(), None, None,
                           state.x_lo[:, idx].contiguous() if (precise and state.x_lo is not None) else None, state.frame)
         sub_loss = loss[idx].contiguous() if truth is not None else None

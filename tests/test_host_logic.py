@@ -5,6 +5,7 @@ import socket
 import sys
 
 import numpy as np
+import pytest
 import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
@@ -162,3 +163,26 @@ def test_reference_arm_contract_under_torchrun_world2():
     assert d["n_gpus"] == 2 and d["higher_is_better"] is True and d["value"] > 0
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+
+
+def test_sweep_partition_keeps_cells_and_stream_columns():
+    """The per-cell precision split of a (Q,R) sweep: a partition of all filters into whole cells, original order kept,
+    so that filter k of either group still reads stream column k % Ns."""
+    Ns = 8
+    grid = [(1e-3, 1e3), (1.0, 0.1), (1e3, 1e-3), (1.0, 1.0), (1e-2, 10.0), (10.0, 1e-2), (1.0, 99.0), (1.0, 100.0)]
+    q = torch.tensor([q for q, _ in grid], dtype=torch.float32).repeat_interleave(Ns)
+    r = torch.tensor([r for _, r in grid], dtype=torch.float32).repeat_interleave(Ns)
+    plain, precise = B.sweep_partition(q, r, Ns)
+    want = [bool(rr >= 100 * qq or qq >= 1e4 * rr) for qq, rr in grid]
+    assert precise.numel() == Ns * sum(want) and plain.numel() == Ns * (len(grid) - sum(want))
+    assert sorted(torch.cat([plain, precise]).tolist()) == list(range(len(grid) * Ns))
+    for idx, flag in ((plain, False), (precise, True)):
+        assert torch.equal(idx % Ns, torch.arange(idx.numel()) % Ns)              # stream column preserved
+        assert (idx[1:] > idx[:-1]).all()                                         # original order
+        assert all(want[c] == flag for c in (idx // Ns).unique().tolist())
+    # a single odd filter inside a cell drags the whole cell along
+    q2 = q.clone(); q2[Ns + 3] = 1e-4
+    _, precise2 = B.sweep_partition(q2, r, Ns)
+    assert set(range(Ns, 2 * Ns)) <= set(precise2.tolist())
+    with pytest.raises(ValueError):
+        B.sweep_partition(q[:-1], r[:-1], Ns)
