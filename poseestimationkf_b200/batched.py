@@ -162,6 +162,36 @@ def _same_scale(a, b) -> bool:
     return float(a) == float(b)
 
 
+_checked_scales: dict = {}
+
+
+def _scales_need_precise(q, r) -> bool:
+    """One pass over the (Q,R) values: validates them (r > 0, q >= 0: R = rI must be positive definite because the
+    kernels carry P/r) and answers whether any filter sits where the plain float32 step leaves the 1e-5 rad tolerance
+    (r/q >= 100: gains below half an ulp of the state; q/r >= 1e4: the process noise swamps A K A^T).  For tensors the
+    answer costs one reduction and one host read-back, cached per (q, r) tensor pair and version so that the chunks of
+    a time-chunked replay (same tensor objects) pay for it once."""
+    if not isinstance(q, torch.Tensor) and not isinstance(r, torch.Tensor):
+        qf, rf = float(q), float(r)
+        if not rf > 0.0 or not qf >= 0.0:
+            raise ValueError("r must be > 0 and q >= 0 (the kernel carries the covariance in units of r)")
+        return rf >= 100.0 * qf or qf >= 1.0e4 * rf
+    key = tuple((id(t), t._version, t.data_ptr()) if isinstance(t, torch.Tensor) else float(t) for t in (q, r))
+    hit = _checked_scales.get(key)
+    if hit is None:
+        qt = q if isinstance(q, torch.Tensor) else torch.full((1,), float(q), dtype=torch.float32, device=r.device)
+        rt = r if isinstance(r, torch.Tensor) else torch.full((1,), float(r), dtype=torch.float32, device=q.device)
+        bad = ~(rt > 0) | ~(qt >= 0)
+        need = (rt >= 100.0 * qt) | (qt >= 1.0e4 * rt)
+        flags = torch.stack((bad.any(), need.any())).tolist()
+        if flags[0]:
+            raise ValueError("every r must be > 0 and every q >= 0 (the kernel carries the covariance in units of r)")
+        if len(_checked_scales) > 64:
+            _checked_scales.clear()
+        hit = _checked_scales[key] = bool(flags[1])
+    return hit
+
+
 def _per_filter(v, n, device):
     if isinstance(v, torch.Tensor):
         _require_cuda(v)
@@ -197,7 +227,7 @@ def replay(streams: torch.Tensor, acc_ref: torch.Tensor, mag_ref: torch.Tensor, 
            lpf_alpha_mag: float | None = None, out_traj: torch.Tensor | None = None, store_trajectory: bool = False,
            store_flips: bool = False, truth: torch.Tensor | None = None, loss: torch.Tensor | None = None,
            precise_state: bool | None = None, share_measurements: bool | None = None, wahba: str = "qr2",
-           staging: str = "auto", keep_filter_frame: bool = False):
+           staging: str = "auto", keep_filter_frame: bool = False, allow_imprecise: bool = False):
     """Run T Prediction+Correction steps for N filters in one kernel launch.
 
     streams [T,9,Ns]; acc_ref, mag_ref [3,Ns]; dt: float seconds or [T] float32 CUDA tensor;
@@ -211,7 +241,11 @@ def replay(streams: torch.Tensor, acc_ref: torch.Tensor, mag_ref: torch.Tensor, 
     on when r/q >= 100 or q/r >= 1e4, off otherwise (the default Q=1, R=0.1 does not need it).  With per-filter
     q / r tensors the rule is applied per cell of a sweep (blocks of Ns filters that share one tuning; two
     launches over a permutation of the cells) when no per-step output is requested, and to the whole batch
-    (precise everywhere) otherwise.
+    (precise when ANY filter needs it, decided from the values with one cached reduction) otherwise.
+    `precise_state=False` with such a tuning raises unless `allow_imprecise=True` (the plain step is then 1.4e-5 to
+    3e-5 rad off the float64 reference after 5000 steps, outside the 1e-5 rad tolerance).
+    q, r: pass the SAME tensor objects to every chunk of a time-chunked replay (their validation and the precision
+    rule are cached per tensor; `state.r is r` also skips the rescaling check).
     `share_measurements`: in the sweep layout (N > Ns) the Wahba solution of a sample is the same for every
     filter that shares its trajectory, so it is solved once per (trajectory, step) (`measurement_stream`) and
     the replay runs with `wahba="precomputed"`; None = automatic for N >= 4 Ns without a low-pass stage.
@@ -237,8 +271,11 @@ def replay(streams: torch.Tensor, acc_ref: torch.Tensor, mag_ref: torch.Tensor, 
             raise ValueError("share_measurements needs raw streams, N > Ns and no low-pass stage")
         streams, _ = measurement_stream(streams, acc_ref, mag_ref, algo=wahba)
         wahba = "precomputed"
-    if not isinstance(r, torch.Tensor) and not float(r) > 0.0:
-        raise ValueError("r must be > 0 (the kernel carries the covariance in units of r)")
+    if isinstance(q, torch.Tensor):
+        _require_cuda(q)
+    if isinstance(r, torch.Tensor):
+        _require_cuda(r)
+    needs_precise = _scales_need_precise(q, r)      # also validates r > 0, q >= 0
     if state is None:
         state = ReplayState.initial(N, dev, r=r, with_lpf=use_lpf)
     elif not _same_scale(state.r, r):
@@ -255,8 +292,10 @@ def replay(streams: torch.Tensor, acc_ref: torch.Tensor, mag_ref: torch.Tensor, 
                                         loss=loss, wahba=wahba, staging=staging, keep_filter_frame=keep_filter_frame)
             if mixed is not None:
                 return mixed
-        precise_state = (state.x_lo is not None or isinstance(q, torch.Tensor) or isinstance(r, torch.Tensor)
-                         or float(r) >= 100.0 * float(q) or float(q) >= 1.0e4 * float(r))
+        precise_state = state.x_lo is not None or needs_precise
+    elif not precise_state and needs_precise and not allow_imprecise:
+        raise ValueError("precise_state=False with r/q >= 100 or q/r >= 1e4 leaves the 1e-5 rad tolerance of the float64 "
+                         "reference (the plain float32 step absorbs gains ~1e-7); pass allow_imprecise=True to run it anyway")
     if precise_state and state.x_lo is None:
         state.x_lo = torch.zeros((4, N), dtype=torch.float32, device=dev)
     _require_cuda(state.x_lo)
@@ -337,7 +376,7 @@ def _replay_sweep_mixed(streams, acc_ref, mag_ref, *, dt, q, r, state, N, Ns, tr
         sub_loss = loss[idx].contiguous() if truth is not None else None
         replay(streams, acc_ref, mag_ref, dt=dt, q=q_t[idx].contiguous(), r=sub.r, state=sub, n_filters=idx.numel(), truth=truth,
                loss=sub_loss, precise_state=precise, share_measurements=False, wahba=wahba, staging=staging,
-               keep_filter_frame=keep_filter_frame)
+               keep_filter_frame=keep_filter_frame)      # (the plain group holds no extreme cell by construction)
         parts.append((idx, sub, sub_loss, precise))
     if state.x_lo is None:
         state.x_lo = torch.zeros((4, N), dtype=torch.float32, device=dev)

@@ -41,6 +41,10 @@ constexpr int kThreads2 = PKF_THREADS2;        // threads per CTA of the packed 
 constexpr int kTile2 = 2 * kThreads2;          // filters per CTA (two per thread); TMA box width, <= 256
 constexpr int kTma2Steps = PKF_TMA2_STEPS;
 constexpr int kTma2Stages = PKF_TMA2_STAGES;
+// PKF_FAST_TILE: the packed kernel runs complete tiles without a reflected-Wahba sample as one basic block
+#ifndef PKF_FAST_TILE
+#define PKF_FAST_TILE 1
+#endif
 #ifndef PKF_AUTO_PACKED
 #define PKF_AUTO_PACKED 1
 #endif

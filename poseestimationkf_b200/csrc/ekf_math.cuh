@@ -35,8 +35,10 @@
 
 #if defined(__CUDACC__)
 #define PKF_HD __host__ __device__ __forceinline__
+#define PKF_HD_RARE __host__ __device__ __noinline__      // rare paths: kept out of line so they cost the hot code no registers
 #else
 #define PKF_HD inline
+#define PKF_HD_RARE inline
 #endif
 
 namespace pkf {
@@ -84,10 +86,19 @@ PKF_HD bool any_(bool m) { return m; }
 #ifndef PKF_SEL_MODE
 #define PKF_SEL_MODE 0
 #endif
+// PKF_FUSE: the plain (non-precise) step accumulates z = x + inc and X = z + K e through their FMAs and factors
+// S = P + I with its "+ 1" folded into a constant (see rk4_predict_fused, kalman_gain_from_s): 12 FP32 operations fewer.
+#ifndef PKF_FUSE
+#define PKF_FUSE 2
+#endif
 #if defined(__CUDA_ARCH__)
 __device__ __forceinline__ float flipsign_(float v, float s) {
 #if PKF_SEL_MODE == 0
   return __float_as_int(s) < 0 ? -v : v;
+#elif PKF_SEL_MODE == 2
+  int r;      // v ^ (s & 0x80000000): one LOP3 with two register operands (integer pipe)
+  asm("lop3.b32 %0, %1, %2, 0x80000000, 0x6A;" : "=r"(r) : "r"(__float_as_int(v)), "r"(__float_as_int(s)));
+  return __int_as_float(r);
 #else
   return __uint_as_float(__float_as_uint(v) ^ (__float_as_uint(s) & 0x80000000u));
 #endif
@@ -102,14 +113,27 @@ __device__ __forceinline__ float selsign_(float s, float a, float b) {
 #endif
 }
 __device__ __forceinline__ bool signbit_(float s) { return (__float_as_uint(s) >> 31) != 0u; }
+// |v| with the sign bit of s: one LOP3 ((v & 0x7fffffff) | (s & 0x80000000)) on the integer pipe
+__device__ __forceinline__ float copysign_(float v, float s) {
+  int r;
+  asm("lop3.b32 %0, %1, %2, 0x80000000, 0xCA;" : "=r"(r) : "r"(__float_as_int(s)), "r"(__float_as_int(v)));   // c ? s : v
+  return __int_as_float(r);
+}
 __device__ __forceinline__ float one_with_sign_(float s) {
   return __uint_as_float((__float_as_uint(s) & 0x80000000u) | 0x3f800000u);
 }
+__device__ __forceinline__ double flipsign_(double v, double s) { return __double2hiint(s) < 0 ? -v : v; }   // rare exact path only
+__device__ __forceinline__ double selsign_(double s, double a, double b) { return __double2hiint(s) < 0 ? a : b; }
+__device__ __forceinline__ bool signbit_(double s) { return __double2hiint(s) < 0; }
+__device__ __forceinline__ double one_with_sign_(double s) { return __double2hiint(s) < 0 ? -1.0 : 1.0; }
+__device__ __forceinline__ double copysign_(double v, double s) { return copysign(v, s); }
 #else
 inline float flipsign_(float v, float s) { return __builtin_signbit(s) ? -v : v; }
 inline float selsign_(float s, float a, float b) { return __builtin_signbit(s) ? a : b; }
 inline bool signbit_(float s) { return __builtin_signbit(s); }
 inline float one_with_sign_(float s) { return __builtin_signbit(s) ? -1.0f : 1.0f; }
+inline float copysign_(float v, float s) { return __builtin_copysignf(v, s); }
+inline double copysign_(double v, double s) { return __builtin_copysign(v, s); }
 inline double flipsign_(double v, double s) { return __builtin_signbit(s) ? -v : v; }
 inline double selsign_(double s, double a, double b) { return __builtin_signbit(s) ? a : b; }
 inline bool signbit_(double s) { return __builtin_signbit(s); }
@@ -158,6 +182,7 @@ PKF_HD f32x2 selsign_(const f32x2& s, const f32x2& a, const f32x2& b) { return f
 PKF_HD f32x2 flipsign_(const f32x2& v, const f32x2& s) { return f32x2(flipsign_(v.x, s.x), flipsign_(v.y, s.y)); }
 PKF_HD mask2 signbit_(const f32x2& s) { return mask2{signbit_(s.x), signbit_(s.y)}; }
 PKF_HD f32x2 one_with_sign_(const f32x2& s) { return f32x2(one_with_sign_(s.x), one_with_sign_(s.y)); }
+PKF_HD f32x2 copysign_(const f32x2& v, const f32x2& s) { return f32x2(copysign_(v.x, s.x), copysign_(v.y, s.y)); }
 template <> PKF_HD f32x2 fma_<f32x2>(f32x2 a, f32x2 b, f32x2 c) {
 #if defined(__CUDA_ARCH__)
   float2 r = __ffma2_rn(f2_(a), f2_(b), f2_(c));
@@ -283,6 +308,26 @@ template <typename F> PKF_HD Quat<F> rk4_increment(const Quat<F>& q, const Vec3<
   return inc;
 }
 
+// Plain-variant form: the predicted state z = x + (c0 - 1) x + c1 (A x) accumulated by FMAs onto x (8 operations
+// instead of 4 MUL + 4 FMA + 4 ADD); the state is rounded twice per component instead of once (~1 ulp per step,
+// contracted by the filter's own gain; the precise variant keeps the increment apart, see ekf_update).
+template <typename F> PKF_HD Quat<F> rk4_predict_fused(const Quat<F>& q, const Vec3<F>& hw, F h) {
+  Quat<F> u;   // u = A q
+  u.w = fma_(-hw.z, q.z, fma_(-hw.y, q.y, -(hw.x * q.x)));
+  u.x = fma_(-hw.y, q.z, fma_(hw.z, q.y, hw.x * q.w));
+  u.y = fma_(hw.x, q.z, fma_(-hw.z, q.x, hw.y * q.w));
+  u.z = fma_(-hw.x, q.y, fma_(hw.y, q.x, hw.z * q.w));
+  F a2 = (h * h) * dot3(hw, hw);
+  F cm = a2 * fma_(a2, F(1.0 / 24.0), F(-0.5));            // c0 - 1
+  F c1 = h * fma_(a2, F(-1.0 / 6.0), F(1));
+  Quat<F> z;
+  z.w = fma_(cm, q.w, fma_(c1, u.w, q.w));
+  z.x = fma_(cm, q.x, fma_(c1, u.x, q.x));
+  z.y = fma_(cm, q.y, fma_(c1, u.y, q.y));
+  z.z = fma_(cm, q.z, fma_(c1, u.z, q.z));
+  return z;
+}
+
 // Knuth two-sum: hi + lo == a + b exactly (no magnitude ordering assumed).
 template <typename F> PKF_HD void two_sum(F a, F b, F& hi, F& lo) {
   F s = a + b;
@@ -310,7 +355,7 @@ template <typename F> PKF_HD void two_sum(F a, F b, F& hi, F& lo) {
 // 74 operations including the process noise, against 88 for the two sparse products (A P) A^T.
 // ------------------------------------------------------------------------------------------
 template <typename F, bool NOISE = true>
-PKF_HD Sym4<F> propagate_cov(const Sym4<F>& P, const Vec3<F>& hw, const Quat<F>& x, F qq, F s) {
+PKF_HD Sym4<F> propagate_cov(const Sym4<F>& P, const Vec3<F>& hw, const Quat<F>& x, F qq, F s, F sd) {
   const F X = hw.x, Y = hw.y, Z = hw.z;
   const F p00 = P.a00, p01 = P.a01, p02 = P.a02, p03 = P.a03, p11 = P.a11, p12 = P.a12, p13 = P.a13,
           p22 = P.a22, p23 = P.a23, p33 = P.a33;
@@ -331,7 +376,7 @@ PKF_HD Sym4<F> propagate_cov(const Sym4<F>& P, const Vec3<F>& hw, const Quat<F>&
   const F t1 = T11 + T22, t2 = T22 - T11;
   Sym4<F> N;
   if constexpr (NOISE) {
-    const F al = fma_(c4, A4, s);                      // alpha' + qq |x|^2
+    const F al = fma_(c4, A4, sd);                     // alpha' + qq |x|^2; sd = s, or s + 1 when the caller wants S = P + I
     const F am = al - T00, ap = al + T00;
     const F yw = s * x.w, yx = s * x.x, yy = s * x.y, yz = s * x.z;     // |x| = 1 inside a launch (adopt_state)
     N.a00 = fma_(-yw, x.w, am - t1);
@@ -358,6 +403,11 @@ PKF_HD Sym4<F> propagate_cov(const Sym4<F>& P, const Vec3<F>& hw, const Quat<F>&
     N.a23 = fma_(-Z, U1, fma_(-Y, U2, -(w2 * p23)));
   }
   return N;
+}
+
+template <typename F, bool NOISE = true>
+PKF_HD Sym4<F> propagate_cov(const Sym4<F>& P, const Vec3<F>& hw, const Quat<F>& x, F qq, F s) {
+  return propagate_cov<F, NOISE>(P, hw, x, qq, s, s);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -424,6 +474,45 @@ template <typename F> PKF_HD Sym4<F> gain_from_ldl(const Ldl4<F>& f) {
 }
 
 template <typename F> PKF_HD Sym4<F> kalman_gain_unit(const Sym4<F>& P) { return gain_from_ldl(ldl_unit(P)); }
+
+// Plain-variant form: the caller hands over S = P + I itself (propagate_cov folds the "+ 1" into the constant of its
+// diagonal), the pivots d_k come straight out of the elimination and the diagonal of the gain is formed as
+// kappa_k = 1 - 1/d_k.  Four additions fewer than the split-pivot form; kappa loses eps/kappa of relative accuracy,
+// i.e. 2.4e-5 at the edge of the plain variant's range (r/q = 100, kappa = 2.5e-3), which moves the state by 1e-9 --
+// beyond that range the precise variant (split pivots, kalman_gain_sm) is selected.
+template <typename F> PKF_HD Sym4<F> kalman_gain_from_s(const Sym4<F>& S) {
+  const F p01 = S.a01, p02 = S.a02, p03 = S.a03, p12 = S.a12, p13 = S.a13, p23 = S.a23;
+  const F i0 = rcp_(S.a00);
+  const F l10 = p01 * i0, l20 = p02 * i0, l30 = p03 * i0;
+  const F i1 = rcp_(fma_(-l10, p01, S.a11));
+  const F t21 = fma_(-l10, p02, p12);
+  const F t31 = fma_(-l10, p03, p13);
+  const F l21 = t21 * i1, l31 = t31 * i1;
+  const F i2 = rcp_(fma_(-l21, t21, fma_(-l20, p02, S.a22)));
+  const F t32 = fma_(-l21, t31, fma_(-l20, p03, p23));
+  const F l32 = t32 * i2;
+  const F i3 = rcp_(fma_(-l32, t32, fma_(-l31, t31, fma_(-l30, p03, S.a33))));
+  // N = L^-1 - I
+  const F n10 = -l10, n21 = -l21, n32 = -l32;
+  const F n20 = fma_(-l21, n10, -l20);
+  const F n31 = fma_(-l32, n21, -l31);
+  const F n30 = fma_(-l32, n20, fma_(-l31, n10, -l30));
+  const F v30 = -(i3 * n30), v31 = -(i3 * n31), v32 = -(i3 * n32);
+  const F v20 = -(i2 * n20), v21 = -(i2 * n21);
+  const F v10 = -(i1 * n10);
+  Sym4<F> K;
+  K.a00 = fma_(n30, v30, fma_(n20, v20, fma_(n10, v10, F(1) - i0)));
+  K.a01 = fma_(n30, v31, fma_(n20, v21, v10));
+  K.a02 = fma_(n30, v32, v20);
+  K.a03 = v30;
+  K.a11 = fma_(n31, v31, fma_(n21, v21, F(1) - i1));
+  K.a12 = fma_(n31, v32, v21);
+  K.a13 = v31;
+  K.a22 = fma_(n32, v32, F(1) - i2);
+  K.a23 = v32;
+  K.a33 = F(1) - i3;
+  return K;
+}
 
 // Gain for Q >> R (used by the compensated variant).  The predicted covariance in units of r is
 //   P = M + g (|x|^2 I - x x^T),   M = A K A^T = O(1),   g = q/4r up to ~1e6,
@@ -858,17 +947,94 @@ PKF_HD auto reference_flip_local(const FC& fc, const Mat3<F>& Ml, const Quat<F>&
   return sel_(b1, y.x, sel_(b2, y.y, y.z)) < F(0);
 }
 
+// ------------------------------------------------------------------------------------------
+// EXACT form of the reference's sign rule, for the rare samples where float32 cannot decide it.
+// RotationMatrix2Quart (PKF/Wahba.py:20-47) returns the quaternion whose component i is >= 0, i being the strict
+// maximum of tr1, tr2, tr3 = 4x^2, 4y^2, 4z^2 (else the third).  When two of the squares agree to ~1e-5 the float32
+// quaternion (error ~1e-7) may order them differently from the float64 reference, and the q/-q flip mask -- which
+// north_star requires to be IDENTICAL -- would differ.  Those samples (a few per 1e5) redo the measurement in
+// float64 from the raw float32 sensor and reference vectors, exactly the values the reference consumes, and decide
+// there.  Returns the reference's branch: 0, 1, 2 for the x, y, z component.
+// ------------------------------------------------------------------------------------------
+PKF_HD_RARE int reference_branch_exact(float rax, float ray, float raz, float rmx, float rmy, float rmz,
+                                       float ax, float ay, float az, float mx, float my, float mz, float ka_f, float km_f) {
+  const Vec3<double> ra = {(double)rax, (double)ray, (double)raz}, rm = {(double)rmx, (double)rmy, (double)rmz};
+  const Vec3<double> a = {(double)ax, (double)ay, (double)az}, m = {(double)mx, (double)my, (double)mz};
+  const double ka = (double)ka_f, km = (double)km_f;
+  const RefFrame<double> E = frame_from_pair<double>(ra, rm);
+  Quat<double> yl;
+  if (ka * km < 0.0 || ka < 0.0) {                    // reflected Wahba problem: the rank-2 SVD form
+    yl = rotation_to_quat_best<double>(wahba_qr2_local<double>(E, a, m, ka, km));
+  } else {
+    double inv_norm;
+    yl = wahba_quat2_local<double>(E, a, m, ka, km, inv_norm);
+  }
+  Mat3<double> Em;
+  Em.m[0][0] = E.e1.x; Em.m[1][0] = E.e1.y; Em.m[2][0] = E.e1.z;
+  Em.m[0][1] = E.e2.x; Em.m[1][1] = E.e2.y; Em.m[2][1] = E.e2.z;
+  Em.m[0][2] = E.e3.x; Em.m[1][2] = E.e3.y; Em.m[2][2] = E.e3.z;
+  const Quat<double> y = qmul(rotation_to_quat_best<double>(Em), yl);
+  const double sx = y.x * y.x, sy = y.y * y.y, sz = y.z * y.z;
+  return (sx > sy && sx > sz) ? 0 : ((sy > sx && sy > sz) ? 1 : 2);       // PKF/Wahba.py:26,33: strict maximum, else the third
+}
+
+// |gap| between two of the squared vector components below kTieTol * |y|^2: hand the sign rule to the exact form
+// (cheap over-approximation of "the two LARGEST are close"; a few samples per 1e5).
+constexpr float kTieTol = 1e-5f;
+PKF_HD bool near_tie_(float sx, float sy, float sz, float n2) {
+  const float t = kTieTol * n2;
+  return abs_(sx - sy) < t || abs_(sx - sz) < t || abs_(sy - sz) < t;
+}
+PKF_HD bool near_tie_(double, double, double, double) { return false; }     // the float64 build is its own exact form
+PKF_HD mask2 near_tie_(const f32x2& sx, const f32x2& sy, const f32x2& sz, const f32x2& n2) {
+  return mask2{near_tie_(sx.x, sy.x, sz.x, n2.x), near_tie_(sx.y, sy.y, sz.y, n2.y)};
+}
+// component of lane `lane`
+PKF_HD float lane_(float v, int) { return v; }
+PKF_HD double lane_(double v, int) { return v; }
+PKF_HD float lane_(const f32x2& v, int lane) { return lane ? v.y : v.x; }
+PKF_HD bool lane_(bool v, int) { return v; }
+PKF_HD bool lane_(const mask2& v, int lane) { return lane ? v.y : v.x; }
+PKF_HD void set_lane_(bool& m, int, bool v) { m = v; }
+PKF_HD void set_lane_(mask2& m, int lane, bool v) { if (lane) m.y = v; else m.x = v; }
+PKF_HD void negate_lane_(Quat<float>& q, int) { q.w = -q.w; q.x = -q.x; q.y = -q.y; q.z = -q.z; }
+PKF_HD void negate_lane_(Quat<double>& q, int) { q.w = -q.w; q.x = -q.x; q.y = -q.y; q.z = -q.z; }
+PKF_HD void negate_lane_(Quat<f32x2>& q, int lane) {
+  if (lane) { q.w.y = -q.w.y; q.x.y = -q.x.y; q.y.y = -q.y.y; q.z.y = -q.z.y; }
+  else { q.w.x = -q.w.x; q.x.x = -q.x.x; q.y.x = -q.y.x; q.z.x = -q.z.x; }
+}
+template <typename F> struct Lanes { static constexpr int n = 1; };
+template <> struct Lanes<f32x2> { static constexpr int n = 2; };
+
 // The same decision from the quaternion alone: for a rotation matrix the three traces of
 // RotationMatrix2Quart are 4x^2, 4y^2, 4z^2 of its quaternion, so the reference's branch is the largest of
 // |x|, |y|, |z| (strictly; else the third), its raw quaternion has that component >= 0, and it negated iff the
 // comparator-aligned quaternion (sg * y, expressed in the reference frame) has it negative.
+// Near a tie of two squares float32 cannot reproduce the float64 reference's choice; the flip-mask byte then carries,
+// beside the float32 decision (bit 0), what the decision would be for each of the three branches (bits 1-3: x, y, z)
+// and a tie marker (bit 7), and flip_fixup_kernel (ops_kernels.cuh) settles those few bytes in float64 after the
+// launch (reference_branch_exact).  The hot kernels never call the float64 path.
+struct FlipCode2 { unsigned x, y; };
+PKF_HD unsigned flip_code_(bool flip, bool tie, bool fx, bool fy, bool fz) {
+  return (flip ? 1u : 0u) | (tie ? (0x80u | (fx ? 2u : 0u) | (fy ? 4u : 0u) | (fz ? 8u : 0u)) : 0u);
+}
+PKF_HD FlipCode2 flip_code_(const mask2& flip, const mask2& tie, const mask2& fx, const mask2& fy, const mask2& fz) {
+  return FlipCode2{flip_code_(flip.x, tie.x, fx.x, fy.x, fz.x), flip_code_(flip.y, tie.y, fx.y, fy.y, fz.y)};
+}
+template <typename F> struct FlipCodeOf { typedef unsigned type; };
+template <> struct FlipCodeOf<f32x2> { typedef FlipCode2 type; };
+
 template <typename F, typename FC>
-PKF_HD auto reference_flip_quat(const FC& fc, const Quat<F>& yl, F sg) -> decltype(yl.w < yl.w) {
+PKF_HD auto reference_flip_quat(const FC& fc, const Quat<F>& yl, F sg, typename FlipCodeOf<F>::type* code = nullptr)
+    -> decltype(yl.w < yl.w) {
   const Quat<F> y = qmul(fc.qE, yl);
   const F ax = y.x * y.x, ay = y.y * y.y, az = y.z * y.z;
   auto b1 = (ax > ay) && (ax > az);
   auto b2 = !b1 && ((ay > ax) && (ay > az));
-  return (sg * sel_(b1, y.x, sel_(b2, y.y, y.z))) < F(0);
+  const F sx = sg * y.x, sy = sg * y.y, sz = sg * y.z;
+  auto flip = sel_(b1, sx, sel_(b2, sy, sz)) < F(0);
+  if (code) *code = flip_code_(flip, near_tie_(ax, ay, az, fma_(y.w, y.w, ax + ay + az)), sx < F(0), sy < F(0), sz < F(0));
+  return flip;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -889,6 +1055,7 @@ template <typename F> struct FilterConst {
   Vec3<F> ra, rm;         // raw reference vectors (used by the Jacobi variant only)
   F g;                    // Q/(4R): process noise in units of r
   F gs;                   // g |x|^2 of the CURRENT state: g after any step of the filter (it normalises), see adopt_state
+  F g1, gs1;              // g + 1, gs + 1: the constant of S's diagonal (plain variant, see kalman_gain_from_s)
   Quat<F> qE;             // unit quaternion of the rotation [e1 e2 e3]: filter frame -> reference frame
 };
 
@@ -934,8 +1101,16 @@ PKF_HD void ekf_predict(const Quat<F>& x, const Sym4<F>& P, const FilterConst<F>
     Sym4<F> M = propagate_cov<F, false>(P, hw, x, fc.g, fc.gs);               // :59-61, noise kept apart
     K = kalman_gain_sm(M, x, fc.gs);                                          // :63-66
   } else {
+#if PKF_FUSE
+    Sym4<F> S = propagate_cov<F, true>(P, hw, x, fc.g, fc.gs, fc.gs1);        // :59-61 and S = P + R :63 (in units of r)
+    K = kalman_gain_from_s(S);                                                // :64-66
+    z = rk4_predict_fused(x, hw, h);                                          // :62
+    inc = z;                                                                  // (unused by the plain update)
+    return;
+#else
     Sym4<F> Pp = propagate_cov<F, true>(P, hw, x, fc.g, fc.gs);               // :59-61 (in units of r)
     K = kalman_gain_unit(Pp);                                                 // :63-66
+#endif
   }
   inc = rk4_increment(x, hw, h);                                              // :62
   z.w = x.w + inc.w; z.x = x.x + inc.x; z.y = x.y + inc.y; z.z = x.z + inc.z;   // |z| = 1 to rounding
@@ -946,6 +1121,29 @@ template <typename F, bool COMP>
 PKF_HD void ekf_update(Quat<F>& x, Quat<F>& xlo, Sym4<F>& P, FilterConst<F>& fc, const Sym4<F>& K, const Quat<F>& z,
                        const Quat<F>& inc, F e0, F e1, F e2, F e3) {
   // X = z + K e                                                              :77
+#if PKF_FUSE
+  if (!COMP) {    // the sum is accumulated onto z by the FMAs themselves (no separate products, no final additions)
+    Quat<F> xn;
+#if PKF_FUSE >= 2
+    // column by column: four consecutive FMAs share e_j in the same operand slot (register reuse cache)
+    xn.w = fma_(K.a00, e0, z.w); xn.x = fma_(K.a01, e0, z.x); xn.y = fma_(K.a02, e0, z.y); xn.z = fma_(K.a03, e0, z.z);
+    xn.w = fma_(K.a01, e1, xn.w); xn.x = fma_(K.a11, e1, xn.x); xn.y = fma_(K.a12, e1, xn.y); xn.z = fma_(K.a13, e1, xn.z);
+    xn.w = fma_(K.a02, e2, xn.w); xn.x = fma_(K.a12, e2, xn.x); xn.y = fma_(K.a22, e2, xn.y); xn.z = fma_(K.a23, e2, xn.z);
+    xn.w = fma_(K.a03, e3, xn.w); xn.x = fma_(K.a13, e3, xn.x); xn.y = fma_(K.a23, e3, xn.y); xn.z = fma_(K.a33, e3, xn.z);
+#else
+    xn.w = fma_(K.a03, e3, fma_(K.a02, e2, fma_(K.a01, e1, fma_(K.a00, e0, z.w))));
+    xn.x = fma_(K.a13, e3, fma_(K.a12, e2, fma_(K.a11, e1, fma_(K.a01, e0, z.x))));
+    xn.y = fma_(K.a23, e3, fma_(K.a22, e2, fma_(K.a12, e1, fma_(K.a02, e0, z.y))));
+    xn.z = fma_(K.a33, e3, fma_(K.a23, e2, fma_(K.a13, e1, fma_(K.a03, e0, z.z))));
+#endif
+    F d = rsqrt_(dot4(xn, xn)) - F(1);
+    x.w = fma_(xn.w, d, xn.w); x.x = fma_(xn.x, d, xn.x); x.y = fma_(xn.y, d, xn.y); x.z = fma_(xn.z, d, xn.z);
+    P = K;
+    fc.gs = fc.g;
+    fc.gs1 = fc.g1;
+    return;
+  }
+#endif
   Quat<F> ke;
   ke.w = fma_(K.a03, e3, fma_(K.a02, e2, fma_(K.a01, e1, K.a00 * e0)));
   ke.x = fma_(K.a13, e3, fma_(K.a12, e2, fma_(K.a11, e1, K.a01 * e0)));
@@ -970,6 +1168,7 @@ PKF_HD void ekf_update(Quat<F>& x, Quat<F>& xlo, Sym4<F>& P, FilterConst<F>& fc,
   // P = P - K P = r K  (R = r I): in units of r the new covariance IS the gain     :78
   P = K;
   fc.gs = fc.g;        // the state leaves every step normalised: |x|^2 = 1 for the next step's B Q B^T
+  fc.gs1 = fc.g1;
 }
 
 // The measurement of one sample: getQuarternion(acc, mag, |a_z|, 1 - |a_z|) (PKF/ExtendedKalmanFilter.py:71) as a
@@ -992,27 +1191,42 @@ PKF_HD Quat<F> measure_quat(const FilterConst<F>& fc, const Vec3<F>& acc, const 
 // Prediction + Correction with the measurement quaternion y (filter frame, any sign, norm 1/inv_norm) already computed.
 template <typename F, bool WANT_FLIP, bool COMP, typename FlagT>
 PKF_HD void ekf_step_measured(Quat<F>& x, Quat<F>& xlo, Sym4<F>& P, FilterConst<F>& fc, const Vec3<F>& gyro,
-                              const Quat<F>& y, F inv_norm, F h, FlagT& flip, bool flip_wanted = true) {
+                              const Quat<F>& y, F inv_norm, F h, FlagT& flip, bool flip_wanted = true,
+                              typename FlipCodeOf<F>::type* code = nullptr) {
   Sym4<F> K;
   Quat<F> inc, z;
   ekf_predict<F, COMP>(x, P, fc, gyro, h, K, inc, z);
-  const F sg = one_with_sign_(dot4(y, z));        // the comparator, literally: -1 when dot(y, z) < 0      :73-75
+  const F dyz = dot4(y, z);                       // the comparator, literally: negate when dot(y, z) < 0  :73-75
   flip = FlagT();
-  if (WANT_FLIP && flip_wanted) flip = reference_flip_quat(fc, y, sg);
-  const F sn = sg * inv_norm;                     // e = sg y/|y| - z                                      :76
+  if (WANT_FLIP && flip_wanted) flip = reference_flip_quat(fc, y, one_with_sign_(dyz), code);
+  const F sn = copysign_(inv_norm, dyz);          // e = sg y/|y| - z, sg = sign(dot): the sign bit moves onto 1/|y| > 0  :76
   const F e0 = fma_(sn, y.w, -z.w), e1 = fma_(sn, y.x, -z.x), e2 = fma_(sn, y.y, -z.y), e3 = fma_(sn, y.z, -z.z);
   ekf_update<F, COMP>(x, xlo, P, fc, K, z, inc, e0, e1, e2, e3);
 }
 
+// The common case of ekf_step<WAHBA_QR2>: both Wahba weights are non-negative (|a_z| <= 1, i.e. a normalised
+// accelerometer), so the closed-form measurement applies and the step has no data-dependent branch.  The caller
+// guarantees the precondition (the packed kernel checks a whole tile of samples before taking this path).
+template <typename F, bool WANT_FLIP, bool COMP, typename FlagT>
+PKF_HD void ekf_step_plain_measured(Quat<F>& x, Quat<F>& xlo, Sym4<F>& P, FilterConst<F>& fc, const Vec3<F>& gyro,
+                                    const Vec3<F>& acc, const Vec3<F>& mag, F h, FlagT& flip, bool flip_wanted = true,
+                                    typename FlipCodeOf<F>::type* code = nullptr) {
+  const F ka = abs_(acc.z), km = F(1) - ka;
+  F inv_norm;
+  const Quat<F> y = wahba_quat2_local(fc.E, acc, mag, ka, km, inv_norm);
+  ekf_step_measured<F, WANT_FLIP, COMP>(x, xlo, P, fc, gyro, y, inv_norm, h, flip, flip_wanted, code);
+}
+
 template <typename F, int ALGO, bool WANT_FLIP, bool COMP, typename FlagT>
 PKF_HD void ekf_step(Quat<F>& x, Quat<F>& xlo, Sym4<F>& P, FilterConst<F>& fc, const Vec3<F>& gyro,
-                     const Vec3<F>& acc, const Vec3<F>& mag, F h, FlagT& flip, bool flip_wanted = true) {
+                     const Vec3<F>& acc, const Vec3<F>& mag, F h, FlagT& flip, bool flip_wanted = true,
+                     typename FlipCodeOf<F>::type* code = nullptr) {
   // flip_wanted: launch-uniform run-time switch under WANT_FLIP -- a launch that stores the trajectory but
   // not the flip mask skips the reference's branch rule altogether
   if constexpr (ALGO == WAHBA_QR2) {
     F inv_norm;
     const Quat<F> y = measure_quat(fc, acc, mag, inv_norm);
-    ekf_step_measured<F, WANT_FLIP, COMP>(x, xlo, P, fc, gyro, y, inv_norm, h, flip, flip_wanted);
+    ekf_step_measured<F, WANT_FLIP, COMP>(x, xlo, P, fc, gyro, y, inv_norm, h, flip, flip_wanted, code);
   } else {
     Sym4<F> K;
     Quat<F> inc, z;
@@ -1064,6 +1278,7 @@ template <typename F> PKF_HD void adopt_state(FilterConst<F>& fc, Quat<F>& x, Qu
   const F n2 = dot4(x, x);
   const auto unit = abs_(n2 - F(1)) < F(1e-5);
   fc.gs = sel_(unit, fc.g, fc.g * n2);
+  fc.gs1 = fc.gs + F(1);
   const F sc = sel_(unit, F(1), rsqrt_(n2));
   x.w *= sc; x.x *= sc; x.y *= sc; x.z *= sc;
   xlo.w *= sc; xlo.x *= sc; xlo.y *= sc; xlo.z *= sc;
@@ -1076,6 +1291,7 @@ PKF_HD FilterConst<F> make_filter_const(const Vec3<F>& acc_ref, const Vec3<F>& m
   fc.ra = acc_ref; fc.rm = mag_ref;
   fc.g = (F(0.25) * q) / r;
   fc.gs = fc.g;
+  fc.g1 = fc.g + F(1); fc.gs1 = fc.g1;
   Mat3<F> Em;
   Em.m[0][0] = fc.E.e1.x; Em.m[1][0] = fc.E.e1.y; Em.m[2][0] = fc.E.e1.z;
   Em.m[0][1] = fc.E.e2.x; Em.m[1][1] = fc.E.e2.y; Em.m[2][1] = fc.E.e2.z;

@@ -42,6 +42,8 @@ namespace {
     if (_e != cudaSuccess) return (int)_e;           \
   } while (0)
 
+inline unsigned blocks_for(int64_t n, int threads) { return (unsigned)((n + threads - 1) / threads); }
+
 inline int launch_status() {
   cudaError_t e = cudaPeekAtLastError();
   return e == cudaSuccess ? 0 : (int)e;
@@ -153,15 +155,34 @@ int replay_dispatch(const ReplayParams& p, int algo, int staging, cudaStream_t s
     use_tma = tma_eligible(p);
     packed = use_tma && kAutoPrefersPacked && algo != POSEKF_WAHBA_JACOBI && packed_eligible(p);
   } else return POSEKF_EINVAL;
+  int rc;
   if (packed)
-    return algo == POSEKF_WAHBA_QR2 ? launch_packed_variant<WAHBA_QR2>(p, lpf, st) : launch_packed_variant<WAHBA_PRECOMPUTED>(p, lpf, st);
-  if (algo == POSEKF_WAHBA_PRECOMPUTED) return lpf ? launch_replay_aux<WAHBA_PRECOMPUTED, true>(p, use_tma, st) : launch_replay_aux<WAHBA_PRECOMPUTED, false>(p, use_tma, st);
-  if (algo == POSEKF_WAHBA_QR2) return lpf ? launch_replay_aux<WAHBA_QR2, true>(p, use_tma, st) : launch_replay_aux<WAHBA_QR2, false>(p, use_tma, st);
-  if (algo == POSEKF_WAHBA_JACOBI) return lpf ? launch_replay_aux<WAHBA_JACOBI, true>(p, use_tma, st) : launch_replay_aux<WAHBA_JACOBI, false>(p, use_tma, st);
-  return POSEKF_EINVAL;
+    rc = algo == POSEKF_WAHBA_QR2 ? launch_packed_variant<WAHBA_QR2>(p, lpf, st) : launch_packed_variant<WAHBA_PRECOMPUTED>(p, lpf, st);
+  else if (algo == POSEKF_WAHBA_PRECOMPUTED) rc = lpf ? launch_replay_aux<WAHBA_PRECOMPUTED, true>(p, use_tma, st) : launch_replay_aux<WAHBA_PRECOMPUTED, false>(p, use_tma, st);
+  else if (algo == POSEKF_WAHBA_QR2) rc = lpf ? launch_replay_aux<WAHBA_QR2, true>(p, use_tma, st) : launch_replay_aux<WAHBA_QR2, false>(p, use_tma, st);
+  else if (algo == POSEKF_WAHBA_JACOBI) rc = lpf ? launch_replay_aux<WAHBA_JACOBI, true>(p, use_tma, st) : launch_replay_aux<WAHBA_JACOBI, false>(p, use_tma, st);
+  else return POSEKF_EINVAL;
+  if (rc == 0 && p.out_flip && p.T > 0 && algo == POSEKF_WAHBA_QR2 && !lpf) {
+    // the flip-mask bytes the kernel marked as float32 ties of the reference's sign rule are settled in float64
+    const FlipFixupParams fp{p.N, p.T, p.Ns, p.streams, p.acc_ref, p.mag_ref, p.out_flip};
+    const int64_t words = (p.N * p.T + 3) / 4;
+    flip_fixup_kernel<<<blocks_for(words, 256), 256, 0, st>>>(fp);
+    rc = launch_status();
+  }
+  return rc;
 }
 
-inline unsigned blocks_for(int64_t n, int threads) { return (unsigned)((n + threads - 1) / threads); }
+// Entry points that take a device ordinal switch to it for their own work and put the caller's current device back on
+// every exit path (the caller may be a torch process whose notion of "current device" must not change behind its back).
+struct DeviceGuard {
+  int prev = -1;
+  cudaError_t status;
+  explicit DeviceGuard(int device) {
+    status = cudaGetDevice(&prev);
+    if (status == cudaSuccess && prev != device) status = cudaSetDevice(device);
+  }
+  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
 
 }  // namespace
 
@@ -221,7 +242,7 @@ struct HostWorkspace {
 
 static void host_ws_free(HostWorkspace* w) {
   if (!w) return;
-  cudaSetDevice(w->device);
+  DeviceGuard guard(w->device);
   for (int i = 0; i < 2; ++i) {
     if (w->d_in[i]) cudaFree(w->d_in[i]);
     if (w->d_traj[i]) cudaFree(w->d_traj[i]);
@@ -241,7 +262,8 @@ static void host_ws_free(HostWorkspace* w) {
 int posekf_host_workspace_create(int device, int64_t n_filters, int64_t chunk_steps, int with_trajectory, void** out_ws) {
   if (!out_ws || n_filters <= 0) return POSEKF_EINVAL;
   *out_ws = nullptr;
-  PKF_CUDA_TRY(cudaSetDevice(device));
+  DeviceGuard guard(device);
+  PKF_CUDA_TRY(guard.status);
   const int64_t N = n_filters;
   if (chunk_steps <= 0) {   // ~256 MiB per staging buffer: small enough that the first kernel starts after ~5 ms
     const int64_t bytes_per_step = (int64_t)kChannels * N * sizeof(float);
@@ -289,6 +311,9 @@ int posekf_replay_host_f32(int64_t N, int64_t T, const float* streams_host, floa
                            int wahba_algo, int precise, int device, void* workspace) {
   if (N <= 0 || T < 0 || !streams_host || !acc_ref_host || !mag_ref_host || !q_scale_host || !r_scale_host || !out_x_host)
     return POSEKF_EINVAL;
+  // R = r I must be positive definite (the device state is P/r) and Q = q I positive semi-definite; NaN fails both tests
+  for (int64_t n = 0; n < N; ++n)
+    if (!(r_scale_host[n] > 0.f) || !(q_scale_host[n] >= 0.f)) return POSEKF_EINVAL;
   const bool traj = out_traj_host != nullptr;
   HostWorkspace* w = static_cast<HostWorkspace*>(workspace);
   bool own = false;
@@ -301,16 +326,23 @@ int posekf_replay_host_f32(int64_t N, int64_t T, const float* streams_host, floa
     w = static_cast<HostWorkspace*>(tmp);
     own = true;
   }
-  PKF_CUDA_TRY(cudaSetDevice(device));
+  DeviceGuard guard(device);
+  if (guard.status != cudaSuccess) { if (own) host_ws_free(w); return (int)guard.status; }
   chunk_steps = w->chunk_steps;
   const bool lpf = lpf_alpha_acc >= 0.f || lpf_alpha_mag >= 0.f;
   int rc = 0;
-#define TRY(expr)                                                                  \
-  do {                                                                             \
-    cudaError_t _e = (expr);                                                       \
-    if (_e != cudaSuccess) { rc = (int)_e; if (own) host_ws_free(w); return rc; }  \
-  } while (0)
   cudaStream_t s_copy = w->s_copy, s_comp = w->s_comp, s_out = w->s_out;
+  // on failure: nothing issued so far may still be reading the caller's host buffers when the call returns
+  auto fail = [&](int code) {
+    cudaStreamSynchronize(s_copy); cudaStreamSynchronize(s_comp); cudaStreamSynchronize(s_out);
+    if (own) host_ws_free(w);
+    return code;
+  };
+#define TRY(expr)                                          \
+  do {                                                     \
+    cudaError_t _e = (expr);                               \
+    if (_e != cudaSuccess) return fail((int)_e);           \
+  } while (0)
   float* d_ref = w->d_ref; float* d_qr = w->d_qr; float* d_x = w->d_x; float* d_p = w->d_p; float* d_dt = w->d_dt;
   float* d_lpf = lpf ? w->d_lpf : nullptr;
   float* d_xlo = precise ? w->d_xlo : nullptr;
@@ -320,7 +352,6 @@ int posekf_replay_host_f32(int64_t N, int64_t T, const float* streams_host, floa
   TRY(cudaMemcpyAsync(d_ref + 3 * N, mag_ref_host, (size_t)3 * N * sizeof(float), cudaMemcpyHostToDevice, s_comp));
   TRY(cudaMemcpyAsync(d_qr, q_scale_host, (size_t)N * sizeof(float), cudaMemcpyHostToDevice, s_comp));
   TRY(cudaMemcpyAsync(d_qr + N, r_scale_host, (size_t)N * sizeof(float), cudaMemcpyHostToDevice, s_comp));
-  TRY(cudaMemcpyAsync(d_dt, &dt, sizeof(float), cudaMemcpyHostToDevice, s_comp));
   // the first stream chunk is independent of the state set-up: start it right away
   const int64_t n_chunks = (T + chunk_steps - 1) / chunk_steps;
   auto issue_copy = [&](int64_t c) -> cudaError_t {
@@ -336,7 +367,8 @@ int posekf_replay_host_f32(int64_t N, int64_t T, const float* streams_host, floa
   // initial state: X = [1,0,0,0], P = I4 (PKF/main_file.py:23,26) unless given; the device state holds P/r
   if (x0_host) TRY(cudaMemcpyAsync(d_x, x0_host, (size_t)4 * N * sizeof(float), cudaMemcpyHostToDevice, s_comp));
   if (p0_host) TRY(cudaMemcpyAsync(d_p, p0_host, (size_t)10 * N * sizeof(float), cudaMemcpyHostToDevice, s_comp));
-  host_init_state_kernel<<<blocks_for(N, 256), 256, 0, s_comp>>>(N, x0_host != nullptr, p0_host != nullptr, d_qr + N, d_x, d_p);
+  // (dt travels as a kernel argument: no asynchronous copy out of this function's stack frame)
+  host_init_state_kernel<<<blocks_for(N, 256), 256, 0, s_comp>>>(N, x0_host != nullptr, p0_host != nullptr, d_qr + N, d_x, d_p, dt, d_dt);
   TRY(cudaPeekAtLastError());
   for (int64_t c = 0; c < n_chunks; ++c) {
     const int b = (int)(c & 1);
@@ -349,7 +381,7 @@ int posekf_replay_host_f32(int64_t N, int64_t T, const float* streams_host, floa
     rc = posekf_replay_f32(N, tc, w->d_in[b], N, d_dt, 0, d_ref, d_ref + 3 * N, d_qr, d_qr + N, lpf_alpha_acc,
                            lpf_alpha_mag, d_x, d_xlo, d_p, d_lpf, traj ? w->d_traj[b] : nullptr, nullptr, nullptr, nullptr,
                            wahba_algo, POSEKF_STAGE_AUTO, frames, s_comp);
-    if (rc != 0) { if (own) host_ws_free(w); return rc; }
+    if (rc != 0) return fail(rc);
     TRY(cudaEventRecord(w->ev_free[b], s_comp));
     if (traj) {
       TRY(cudaEventRecord(w->ev_traj[b], s_comp));
@@ -575,7 +607,8 @@ int posekf_stream_sync(void* stream) {
 
 int posekf_fp32_peak_tflops(int device, double* out_tflops, double* out_ms) {
   if (!out_tflops) return POSEKF_EINVAL;
-  PKF_CUDA_TRY(cudaSetDevice(device));
+  DeviceGuard guard(device);
+  PKF_CUDA_TRY(guard.status);
   cudaDeviceProp prop;
   PKF_CUDA_TRY(cudaGetDeviceProperties(&prop, device));
   const int blocks = prop.multiProcessorCount * 8;

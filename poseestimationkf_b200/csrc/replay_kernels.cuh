@@ -4,6 +4,7 @@
 //   replay_tma2_kernel  TWO filters per thread in packed f32x2 lanes (FFMA2), same ring  -- the default
 // Replaces the loop body of "Python Kalman Filter/main_file.py":38-47 (see include/posekf.h).
 #pragma once
+#include <type_traits>
 #include "device_util.cuh"
 
 namespace pkf_dev {
@@ -103,7 +104,12 @@ __device__ __forceinline__ void filter_step(const ReplayParams& p, FilterRegs& f
     if (p.alpha_mag >= 0.f) { lowpass<float>(f.lm, m, p.alpha_mag, 1.f - p.alpha_mag); m = f.lm; }
   }
   bool flip;
-  ekf_step<float, ALGO, AUX, COMP>(f.x, f.xlo, f.P, f.fc, w, a, m, h, flip, aux.flips != nullptr);
+  // flip-mask byte: the float32 decision, plus the tie marker and per-branch alternatives that flip_fixup_kernel settles
+  // in float64 after the launch (raw samples only: a low-passed sample is not in the stream any more)
+  unsigned code = 0;
+  ekf_step<float, ALGO, AUX, COMP>(f.x, f.xlo, f.P, f.fc, w, a, m, h, flip, aux.flips != nullptr,
+                                   (AUX && !LPF && ALGO == WAHBA_QR2) ? &code : nullptr);
+  if (!(AUX && !LPF && ALGO == WAHBA_QR2)) code = flip ? 1u : 0u;
   if (AUX) {
     // per-step outputs are in the reference frame (the reference's X_k)
     Quat<float> xr = f.x;
@@ -114,7 +120,7 @@ __device__ __forceinline__ void filter_step(const ReplayParams& p, FilterRegs& f
                    : "memory");
       aux.traj += p.N;
     }
-    if (aux.flips) { *aux.flips = flip ? 1 : 0; aux.flips += p.N; }
+    if (aux.flips) { *aux.flips = (uint8_t)code; aux.flips += p.N; }
     if (aux.truth) {  // tuning objective: sin^2 of the angle between the estimate and the reference track
       const float4 qt = __ldg(aux.truth);
       aux.truth += p.Ns;
@@ -265,7 +271,7 @@ struct FilterRegs2 {
 };
 
 template <int ALGO, bool LPF, bool AUX, bool COMP>
-__global__ void __launch_bounds__(kThreads2, (LPF && COMP) ? (PKF_MIN_CTAS2 > 6 ? 6 : PKF_MIN_CTAS2) : PKF_MIN_CTAS2)
+__global__ void __launch_bounds__(kThreads2, (AUX && COMP) ? (PKF_MIN_CTAS2 > 4 ? 4 : PKF_MIN_CTAS2) : ((LPF && COMP) ? (PKF_MIN_CTAS2 > 6 ? 6 : PKF_MIN_CTAS2) : PKF_MIN_CTAS2))
     replay_tma2_kernel(const ReplayParams p, const __grid_constant__ CUtensorMap tmap) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   Tma2Smem& sm = *reinterpret_cast<Tma2Smem*>(smem_raw);
@@ -340,41 +346,69 @@ __global__ void __launch_bounds__(kThreads2, (LPF && COMP) ? (PKF_MIN_CTAS2 > 6 
     mbar_wait(&sm.full[stage], parity);
     if (valid) {
       const int steps = min(kTma2Steps, T - k * kTma2Steps);
+      // One packed step on the samples of slot tt of the current tile.  FAST: the tile is complete and none of its
+      // samples takes the rare reflected-Wahba path (|a_z| > 1), so the whole tile is ONE basic block for the
+      // scheduler (the measurement of step t+1 does not depend on the state and overlaps the update of step t).
+      auto one_step = [&](int tt, auto fast_tag) {
+        constexpr bool FAST = decltype(fast_tag)::value;
+        f32x2 s[kChannels];
 #pragma unroll
-      for (int tt = 0; tt < kTma2Steps; ++tt) {
-        if (tt < steps) {
-          f32x2 s[kChannels];
+        for (int c = 0; c < kChannels; ++c) s[c] = ld2(&sm.tile[stage][tt][c][2 * tid]);
+        const float h = p.dt_per_step ? __ldg(p.dt + k * kTma2Steps + tt) : dt0;
+        Vec3<f32x2> w = {s[0], s[1], s[2]}, a = {s[3], s[4], s[5]}, m = {s[6], s[7], s[8]};
+        if (LPF) {
+          if (p.alpha_acc >= 0.f) { lowpass<f32x2>(f.la, a, f32x2(p.alpha_acc), f32x2(1.f - p.alpha_acc)); a = f.la; }
+          if (p.alpha_mag >= 0.f) { lowpass<f32x2>(f.lm, m, f32x2(p.alpha_mag), f32x2(1.f - p.alpha_mag)); m = f.lm; }
+        }
+        mask2 flip;
+        constexpr bool kTieCode = AUX && !LPF && ALGO == WAHBA_QR2;     // see filter_step
+        FlipCode2 code = {0u, 0u};
+        if constexpr (FAST) ekf_step_plain_measured<f32x2, AUX, COMP>(f.x, f.xlo, f.P, f.fc, w, a, m, f32x2(h), flip, flips != nullptr,
+                                                                      kTieCode ? &code : nullptr);
+        else ekf_step<f32x2, ALGO, AUX, COMP>(f.x, f.xlo, f.P, f.fc, w, a, m, f32x2(h), flip, flips != nullptr, kTieCode ? &code : nullptr);
+        if (!kTieCode) code = FlipCode2{flip.x ? 1u : 0u, flip.y ? 1u : 0u};
+        if (AUX) {
+          Quat<f32x2> xr = f.x;     // per-step outputs are in the reference frame
+          if (uses_filter_frame<ALGO>() && (traj || truth)) xr = state_in_reference_frame(f.fc, f.x);
+          if (traj) {   // [T][N][4]: two adjacent 16-byte quaternions
+            asm volatile("st.global.cs.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(traj), "f"(xr.w.x), "f"(xr.x.x), "f"(xr.y.x),
+                         "f"(xr.z.x) : "memory");
+            asm volatile("st.global.cs.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(traj + 1), "f"(xr.w.y), "f"(xr.x.y),
+                         "f"(xr.y.y), "f"(xr.z.y) : "memory");
+            traj += N;
+          }
+          if (flips) { *reinterpret_cast<uchar2*>(flips) = make_uchar2((unsigned char)code.x, (unsigned char)code.y); flips += N; }
+          if (truth) {  // squared wedge product |X ^ q_ref|^2 per lane (see the scalar kernel)
+            const float4 t0 = __ldg(truth), t1 = __ldg(truth + 1);
+            truth += Ns;
+            const f32x2 qw(t0.x, t1.x), qx(t0.y, t1.y), qy(t0.z, t1.z), qz(t0.w, t1.w);
+            const f32x2 xw = xr.w, xx = xr.x, xy = xr.y, xz = xr.z;
+            const f32x2 m01 = fma_(xw, qx, -(xx * qw)), m02 = fma_(xw, qy, -(xy * qw)), m03 = fma_(xw, qz, -(xz * qw));
+            const f32x2 m12 = fma_(xx, qy, -(xy * qx)), m13 = fma_(xx, qz, -(xz * qx)), m23 = fma_(xy, qz, -(xz * qy));
+            loss = loss + fma_(m23, m23, fma_(m13, m13, fma_(m12, m12, fma_(m03, m03, fma_(m02, m02, m01 * m01)))));
+          }
+        }
+      };
+      bool fast = false;
+      if constexpr (ALGO == WAHBA_QR2 && !LPF && PKF_FAST_TILE) {
+        if (steps == kTma2Steps) {
+          // |a_z| <= 1 for every sample of the tile (both lanes): the accelerometer weight 1 - |a_z| is non-negative
+          float az = 0.f;
 #pragma unroll
-          for (int c = 0; c < kChannels; ++c) s[c] = ld2(&sm.tile[stage][tt][c][2 * tid]);
-          const float h = p.dt_per_step ? __ldg(p.dt + k * kTma2Steps + tt) : dt0;
-          Vec3<f32x2> w = {s[0], s[1], s[2]}, a = {s[3], s[4], s[5]}, m = {s[6], s[7], s[8]};
-          if (LPF) {
-            if (p.alpha_acc >= 0.f) { lowpass<f32x2>(f.la, a, f32x2(p.alpha_acc), f32x2(1.f - p.alpha_acc)); a = f.la; }
-            if (p.alpha_mag >= 0.f) { lowpass<f32x2>(f.lm, m, f32x2(p.alpha_mag), f32x2(1.f - p.alpha_mag)); m = f.lm; }
+          for (int tt = 0; tt < kTma2Steps; ++tt) {
+            const float2 v = *reinterpret_cast<const float2*>(&sm.tile[stage][tt][5][2 * tid]);
+            az = fmaxf(az, fmaxf(fabsf(v.x), fabsf(v.y)));
           }
-          mask2 flip;
-          ekf_step<f32x2, ALGO, AUX, COMP>(f.x, f.xlo, f.P, f.fc, w, a, m, f32x2(h), flip, flips != nullptr);
-          if (AUX) {
-            Quat<f32x2> xr = f.x;     // per-step outputs are in the reference frame
-            if (uses_filter_frame<ALGO>() && (traj || truth)) xr = state_in_reference_frame(f.fc, f.x);
-            if (traj) {   // [T][N][4]: two adjacent 16-byte quaternions
-              asm volatile("st.global.cs.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(traj), "f"(xr.w.x), "f"(xr.x.x), "f"(xr.y.x),
-                           "f"(xr.z.x) : "memory");
-              asm volatile("st.global.cs.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(traj + 1), "f"(xr.w.y), "f"(xr.x.y),
-                           "f"(xr.y.y), "f"(xr.z.y) : "memory");
-              traj += N;
-            }
-            if (flips) { *reinterpret_cast<uchar2*>(flips) = make_uchar2(flip.x ? 1 : 0, flip.y ? 1 : 0); flips += N; }
-            if (truth) {  // squared wedge product |X ^ q_ref|^2 per lane (see the scalar kernel)
-              const float4 t0 = __ldg(truth), t1 = __ldg(truth + 1);
-              truth += Ns;
-              const f32x2 qw(t0.x, t1.x), qx(t0.y, t1.y), qy(t0.z, t1.z), qz(t0.w, t1.w);
-              const f32x2 xw = xr.w, xx = xr.x, xy = xr.y, xz = xr.z;
-              const f32x2 m01 = fma_(xw, qx, -(xx * qw)), m02 = fma_(xw, qy, -(xy * qw)), m03 = fma_(xw, qz, -(xz * qw));
-              const f32x2 m12 = fma_(xx, qy, -(xy * qx)), m13 = fma_(xx, qz, -(xz * qx)), m23 = fma_(xy, qz, -(xz * qy));
-              loss = loss + fma_(m23, m23, fma_(m13, m13, fma_(m12, m12, fma_(m03, m03, fma_(m02, m02, m01 * m01)))));
-            }
-          }
+          fast = az <= 1.f;
+        }
+      }
+      if (fast) {
+#pragma unroll
+        for (int tt = 0; tt < kTma2Steps; ++tt) one_step(tt, std::true_type{});
+      } else {
+#pragma unroll
+        for (int tt = 0; tt < kTma2Steps; ++tt) {
+          if (tt < steps) one_step(tt, std::false_type{});
         }
       }
     }

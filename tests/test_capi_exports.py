@@ -43,8 +43,9 @@ def test_zero_spills_reported_by_ptxas():
     spills = re.findall(r"(\d+) bytes spill stores, (\d+) bytes spill loads", log)
     assert spills and all(a == "0" and b == "0" for a, b in spills)
     regs = [int(r) for r in re.findall(r"Used (\d+) registers", log)]
-    # scalar kernels: 128 threads x >= 4 CTAs/SM (<= 128 regs); packed kernels: 64 threads x 6 CTAs/SM (<= 168 regs)
-    assert max(regs) <= 168
+    # scalar kernels: 128 threads x >= 4 CTAs/SM (<= 128 regs); packed kernels: 64 threads x 6 CTAs/SM (<= 168 regs),
+    # except the precise variant with per-step outputs, which is built for 4 CTAs/SM (<= 255)
+    assert max(regs) <= 200 and sorted(regs)[-2] <= 168
 
 
 def test_argument_validation_without_gpu():

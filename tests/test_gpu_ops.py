@@ -36,7 +36,7 @@ def test_wahba_vs_reference_golden(golden_wahba, cuda, tag, algo):
         np.testing.assert_allclose(R.cpu().numpy().T.reshape(-1, 3, 3), g[f"{tag}_R"], atol=5e-6)
     else:
         assert (ang < 1e-6 + 4 * 6e-8 * _cond(g, tag)).all()
-    assert (np.sum(q.cpu().numpy().T * g[f"{tag}_q"], axis=1) < 0).sum() <= 2
+    assert (np.sum(q.cpu().numpy().T * g[f"{tag}_q"], axis=1) < 0).sum() == 0       # the reference's sign convention, every case
     if tag == "half":       # scalar weights and the reference-weights shortcut go through the same kernel
         _, q2 = B.wahba(*args, k_acc=0.5, k_mag=0.5, algo=algo)
         assert torch.equal(q2, q)
@@ -89,7 +89,7 @@ def test_stepwise_operators_vs_reference_golden(golden_step, cuda):
     np.testing.assert_allclose(B.jacobian_b(x).cpu().numpy().T.reshape(M, 4, 3), g["JB"], rtol=1e-7)
     np.testing.assert_allclose(B.comparator(x, _dev(g["z"].T, cuda)).cpu().numpy().T, g["comparator"], atol=1e-6)
     assert O.quat_angle(B.rk4(x, dt, gyro).cpu().numpy().T, g["rk4"]).max() < 1e-6
-    np.testing.assert_allclose(B.quat2rpy(x).cpu().numpy().T, g["rpy"], atol=2e-3)      # degrees
+    np.testing.assert_allclose(B.quat2rpy(x).cpu().numpy().T, g["rpy"], atol=1e-4)      # degrees (float32 output: 1.5e-5 at 180)
     np.testing.assert_allclose(B.norm(_dev(g["P"][:, 0, :].T, cuda)).cpu().numpy(), g["norm"], rtol=1e-6)
 
 
@@ -147,7 +147,7 @@ def test_compat_modules_run_the_reference_loop(golden_traj, cuda):
         assert k.Q[0, 0] == 1.0 and abs(k.R[0, 0] - 0.1) < 1e-15 and k.previousT == t_ns[T]
         k.setQ(2); k.setQ(3)
         assert k.Q[1, 1] == 6.0                                     # cumulative, like the reference
-        np.testing.assert_allclose(Quart2RPY(X), O.quat_to_rpy_deg(X), atol=2e-3)
+        np.testing.assert_allclose(Quart2RPY(X), O.quat_to_rpy_deg(X), atol=1e-4)
         R = w.getRotation(S[5, 3:6, n], S[5, 6:9, n], 0.5, 0.5)
         np.testing.assert_allclose(R @ R.T, np.identity(3), atol=1e-5)
         np.testing.assert_allclose(Wahba.RotationMatrix2Quart(R), w.getQuarternion(S[5, 3:6, n], S[5, 6:9, n], 0.5, 0.5), atol=1e-6)
@@ -186,7 +186,10 @@ def test_comparison_tracks_and_tuning_objective(cuda):
     # RPY of a stored trajectory
     rpy = B.traj2rpy(wah)
     ref = np.stack([O.quat_to_rpy_deg(wah[5, n].cpu().numpy().astype(np.float64)) for n in range(8)])
-    np.testing.assert_allclose(rpy[5, :8].cpu().numpy(), ref, atol=5e-3)
+    # float32 streaming form: asin amplifies the float32 rounding of its argument by 1/cos(pitch)
+    sp = np.abs(np.sin(np.radians(ref[:, 1])))
+    tol = 1e-4 * np.maximum(1.0, 0.25 / np.sqrt(np.maximum(1.0 - sp * sp, 1e-12)))
+    assert (np.abs(rpy[5, :8].cpu().numpy() - ref) <= tol[:, None]).all()
     # tuning objective of a small (Q,R) grid against ground truth, no trajectory stored
     truth = imu.q_true.permute(0, 2, 1).to(torch.float32).contiguous()           # [T, Ns, 4]
     grid = [(q, r) for q in (0.01, 1.0, 100.0) for r in (0.01, 0.1, 10.0)]

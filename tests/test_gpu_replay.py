@@ -26,7 +26,7 @@ def _oracle(imu_streams, acc_ref, mag_ref, dt, q, r, **kw):
                             mag_ref.cpu().numpy().T.astype(np.float64), q, r, **kw)
 
 
-@pytest.mark.parametrize("staging", ["ldg", "tma"])
+@pytest.mark.parametrize("staging", ["ldg", "tma", "tma_packed"])
 @pytest.mark.parametrize("tag", ["clean", "noisy"])
 def test_replay_vs_reference_golden(golden_traj, cuda, tag, staging):
     g = golden_traj
@@ -57,9 +57,11 @@ def test_replay_vs_oracle_seeded(cuda, algo):
     if algo == "qr2":
         assert ang.max() < TOL, ang.max()
         assert (np.sum(got * ref["X"], axis=-1) > 0).all()
-        mism = flips.cpu().numpy().astype(bool) != ref["flips"]
-        # a flip decision can only differ where the 3-branch sign rule is at a near-tie (measure zero)
-        assert mism.sum() <= 3, mism.sum()
+        # identical q/-q choices (north_star): float32 ties of the reference's 3-branch sign rule are settled in float64
+        # by flip_fixup_kernel, so the mask is the reference's, bit for bit
+        fl = flips.cpu().numpy()
+        assert fl.max() <= 1                              # no tie marker survives the fix-up pass
+        assert (fl.astype(bool) != ref["flips"]).sum() == 0
     else:
         # B formed in float32: fine where the reference's weights keep B well conditioned, degraded
         # where |a_z| -> 0 or 1 (documented in DESIGN.md; this is why QR2 is the default)
@@ -262,19 +264,12 @@ def test_full_length_parity_against_c_oracle(cuda):
         ang = O.quat_angle(got, ref["X"])
         assert ang.max() < TOL, ang.max()
         assert (np.sum(got * ref["X"], axis=-1) > 0).all()
-        mism = flips.cpu().numpy().astype(bool) != ref["flips"]
-        # The q/-q decision may differ only where the reference's 3-branch sign rule (PKF/Wahba.py:28,35,41)
-        # sits on a numerical tie of its two largest traces tr_i = 4 q_i^2: verify that for every mismatch.
-        assert mism.sum() <= 40, mism.sum()         # ~1e-6 of 8.2 M steps
-        tt, nn = np.nonzero(mism)
-        if len(tt):
-            S = imu.streams.cpu().numpy()
-            ar, mr = imu.acc_ref.cpu().numpy()[:, nn], imu.mag_ref.cpu().numpy()[:, nn]
-            acc, mag = S[tt, 3:6, nn].T, S[tt, 6:9, nn].T
-            ka = np.abs(acc[2]).astype(np.float64)
-            _, qw = CO.wahba(ar, mr, acc, mag, ka, 1 - ka)
-            tr = np.sort(4 * qw[:, 1:] ** 2, axis=1)
-            assert ((tr[:, 2] - tr[:, 1]) < 2e-6).all(), (tr[:, 2] - tr[:, 1]).max()
+        fl = flips.cpu().numpy()
+        assert fl.max() <= 1
+        mism = fl.astype(bool) != ref["flips"]
+        # identical q/-q choices over all 8.2 M filter-steps: where the reference's 3-branch sign rule (PKF/Wahba.py:28,35,41)
+        # sits on a float32 tie of its traces tr_i = 4 q_i^2 the kernel's marker byte is settled in float64 (flip_fixup_kernel)
+        assert mism.sum() == 0, mism.sum()
         az = np.abs(imu.streams[:, 5].cpu().numpy())
         inside = (az >= 0.02) & (az <= 0.98)
         print(f"sigma={sigma}: max {ang.max():.2e} rad, inside 0.02<=|a_z|<=0.98: {ang[inside].max():.2e}, "
@@ -434,7 +429,7 @@ def test_precomputed_measurement_stream_sweep(cuda):
         for gi in range(G):
             assert O.quat_angle(got[:, gi], refs[gi]["X"]).max() < 1e-6, (staging, grid[gi])
             assert (np.sum(got[:, gi] * refs[gi]["X"], axis=-1) > 0).all()
-            assert (flips[:, gi] != refs[gi]["flips"]).sum() <= 2
+            assert (flips[:, gi] != refs[gi]["flips"]).sum() == 0
         outs.append((st, traj, fl))
     assert torch.equal(outs[0][1], outs[1][1]) and torch.equal(outs[1][1], outs[2][1]) and torch.equal(outs[1][2], outs[2][2])
     # automatic sharing in replay(): N >= 4 Ns

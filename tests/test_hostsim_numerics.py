@@ -143,10 +143,15 @@ def test_kalman_gain_against_numpy_inverse():
     # P/r = g (|x|^2 I - x x^T) + ... in float32 and loses the unit eigenvalue of S along x at eps*q/4r, so
     # it is held to the bound for q/r <= 100 (the host API switches to the precise variant from q/r = 1e4,
     # where the plain error reaches 1e-4); the precise variant (Sherman-Morrison) holds it over all 12 decades.
-    for compensated, sel in ((False, q <= 100.0), (True, q > 0)):
+    # The plain variant also forms the gain's diagonal as 1 - 1/d_k (kalman_gain_from_s): relative accuracy eps*4r/q, so
+    # inside ITS range (0.01 < q/r, the host API's rule r/q >= 100 -> precise) the covariance is good to 3e-5 of its own
+    # scale and the state to 5e-7 rad everywhere; the precise variant keeps split pivots and holds 5e-6 over 12 decades.
+    for compensated, sel, bound in ((False, (q <= 100.0) & (q > 0.01), 3e-5), (True, q > 0, 5e-6)):
         traj, _, P = H.replay(streams, 0.01, acc_ref, mag_ref, q, r, precision="f32", algo="qr2", compensated=compensated)
         assert O.quat_angle(traj[0].T, ref["X"][0]).max() < 5e-7
-        assert ((np.abs(P - Pref) / scale)[:, sel]).max() < 5e-6      # relative to each filter's own covariance scale
+        assert ((np.abs(P - Pref) / scale)[:, sel]).max() < bound     # relative to each filter's own covariance scale
+        if not compensated:      # ... and at the default tuning's neighbourhood (0.1 <= q/r <= 100) the plain variant holds 5e-6 too
+            assert ((np.abs(P - Pref) / scale)[:, (q <= 100.0) & (q >= 0.1)]).max() < 5e-6
 
 
 def test_packed_lanes_equal_scalar(golden_traj):
