@@ -245,19 +245,46 @@ def lowpass_scalar(x, alpha, y0=None):
     return out
 
 
-def interpolate_normalise(y1, y2, t1, t2, t3):
-    """Linear interpolation of a sensor sample pair to the gyro timestamp, then normalisation.
-    (`Kalman Filter Server/PoseEstimator/Parser.cpp:259-267` LinearInterpolationSensor and :221-228
-    NormalizeValues, as sequenced by ExecuteKalmanFilter :229-242.)  The C++ server cannot be compiled
-    here (Eigen + Windows headers), so this restatement is NOT pinned by executing the reference:
-    parity for this pre-processing row is "unpinned" (formula restatement only).
+def interpolate_sensor(y1, y2, t1, t2, t3):
+    """Linear interpolation of a sensor sample pair to the gyro timestamp, float64, in the reference's order of
+    operations: (y2 - y1) / (t2 - t1) * (t3 - t1) + y1 with the int64 nanosecond stamps converted to double first.
+    (`Kalman Filter Server/PoseEstimator/Parser.cpp:259-267` LinearInterpolationSensor.)
     y1, y2: [...,3]; t1, t2, t3: integer ns (broadcastable)."""
     y1 = np.asarray(y1, dtype=np.float64)
     y2 = np.asarray(y2, dtype=np.float64)
     t1, t2, t3 = (np.asarray(t, dtype=np.float64)[..., None] for t in (t1, t2, t3))
-    v = (y2 - y1) / (t2 - t1) * (t3 - t1) + y1
-    den = np.sqrt(v[..., 0] * v[..., 0] + v[..., 1] * v[..., 1] + v[..., 2] * v[..., 2])
+    return (y2 - y1) / (t2 - t1) * (t3 - t1) + y1
+
+
+def normalize_values(v):
+    """`Parser::NormalizeValues` (`Parser.cpp:221-228`): divide by sqrt(x*x + y*y + z*z), summed left to right."""
+    v = np.asarray(v, dtype=np.float64)
+    den = np.sqrt((v[..., 0] * v[..., 0]) + (v[..., 1] * v[..., 1]) + (v[..., 2] * v[..., 2]))
     return v / den[..., None]
+
+
+def interpolate_normalise(y1, y2, t1, t2, t3):
+    """ExecuteKalmanFilter's sequence for one sensor (`Parser.cpp:232-242`): interpolate to the gyro timestamp, then
+    normalise.  PINNED: tests/test_oracle.py holds it bit for bit to tests/golden/preprocess_ref.npz, which
+    tests/golden/make_golden_cpp.py produced by executing the reference's own C++ text (oracle/_ref)."""
+    return normalize_values(interpolate_sensor(y1, y2, t1, t2, t3))
+
+
+def initial_values(samples):
+    """`InitialValues` (`Kalman Filter Server/PoseEstimator/InitialValues.cpp:19-66`): running sum of the K samples
+    in arrival order, mean = sum / K, unbiased variance = sum_i (x_i - mean)^2 / (K - 1), accumulated in order.
+    samples [..., K, 3] -> (mean [...,3], var [...,3]).  PINNED bit for bit to tests/golden/initial_values_ref.npz
+    (the unmodified InitialValues.cpp compiled into oracle/_ref)."""
+    x = np.asarray(samples, dtype=np.float64)
+    K = x.shape[-2]
+    acc = np.zeros(x.shape[:-2] + (3,))
+    for i in range(K):
+        acc = acc + x[..., i, :]
+    mean = acc / K
+    var = np.zeros_like(mean)
+    for i in range(K):
+        var = var + (x[..., i, :] - mean) * (x[..., i, :] - mean)
+    return mean, var / float(K - 1)
 
 
 # --------------------------------------------------------------------------------------------

@@ -97,7 +97,8 @@ __device__ __forceinline__ float flipsign_(float v, float s) {
   return __float_as_int(s) < 0 ? -v : v;
 #elif PKF_SEL_MODE == 2
   int r;      // v ^ (s & 0x80000000): one LOP3 with two register operands (integer pipe)
-  asm("lop3.b32 %0, %1, %2, 0x80000000, 0x6A;" : "=r"(r) : "r"(__float_as_int(v)), "r"(__float_as_int(s)));
+  // (a, b, c) = (v, s, mask); LUT = a ^ (b & c) = 0xF0 ^ (0xCC & 0xAA) = 0x78
+  asm("lop3.b32 %0, %1, %2, 0x80000000, 0x78;" : "=r"(r) : "r"(__float_as_int(v)), "r"(__float_as_int(s)));
   return __int_as_float(r);
 #else
   return __uint_as_float(__float_as_uint(v) ^ (__float_as_uint(s) & 0x80000000u));
@@ -116,7 +117,8 @@ __device__ __forceinline__ bool signbit_(float s) { return (__float_as_uint(s) >
 // |v| with the sign bit of s: one LOP3 ((v & 0x7fffffff) | (s & 0x80000000)) on the integer pipe
 __device__ __forceinline__ float copysign_(float v, float s) {
   int r;
-  asm("lop3.b32 %0, %1, %2, 0x80000000, 0xCA;" : "=r"(r) : "r"(__float_as_int(s)), "r"(__float_as_int(v)));   // c ? s : v
+  // operands (a, b, c) = (s, v, mask); LUT = (c & a) | (~c & b) = (0xAA & 0xF0) | (0x55 & 0xCC) = 0xE4
+  asm("lop3.b32 %0, %1, %2, 0x80000000, 0xE4;" : "=r"(r) : "r"(__float_as_int(s)), "r"(__float_as_int(v)));
   return __int_as_float(r);
 }
 __device__ __forceinline__ float one_with_sign_(float s) {

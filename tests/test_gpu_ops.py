@@ -248,6 +248,36 @@ def test_preprocess_and_log_replay(cuda):
     # inputs were themselves rounded to 6 decimals by the writer, hence the looser bound
 
 
+def test_preprocess_and_initial_values_vs_reference_cpp_golden(cuda):
+    """SURVEY 8f-2 / f-2b pinned: the pre-processing and initial-value kernels against fixtures frozen from the
+    reference's OWN C++ (Parser.cpp:221-228,259-267 and InitialValues.cpp, executed through oracle/_ref by
+    tests/golden/make_golden_cpp.py)."""
+    import os
+    from tests.conftest import GOLDEN
+    g = np.load(os.path.join(GOLDEN, "preprocess_ref.npz"))
+    M = g["y1"].shape[0]
+    H = M // 2                                          # first half accelerometer-like, second half magnetometer-like cases
+    prev = np.concatenate([g["y1"][:H].T, g["y1"][H:].T])[None]          # [1, 6, H]
+    nxt = np.concatenate([g["y2"][:H].T, g["y2"][H:].T])[None]
+    d21, d31 = (g["t2"] - g["t1"]) * 1e-9, (g["t3"] - g["t1"]) * 1e-9    # the kernel takes the two time spans in seconds
+    tspan = np.stack([d21[:H], d31[:H], d21[H:], d31[H:]])[None]
+    gyro = np.zeros((1, 3, H))
+    out, _ = B.preprocess(_dev(gyro, cuda), _dev(prev, cuda), _dev(nxt, cuda), _dev(tspan, cuda))
+    got = out[0].cpu().numpy()
+    np.testing.assert_allclose(got[3:6].T, g["normalised"][:H], atol=2e-6)
+    np.testing.assert_allclose(got[6:9].T, g["normalised"][H:], atol=2e-6)
+    ang = np.arccos(np.clip(np.sum(np.concatenate([got[3:6].T, got[6:9].T]) * g["normalised"], axis=1), -1, 1))
+    assert ang.max() < 1e-5 / 2          # as a direction: far inside the filter's own tolerance
+    h = np.load(os.path.join(GOLDEN, "initial_values_ref.npz"))
+    x = np.ascontiguousarray(h["samples"].transpose(1, 2, 0))             # [K, 3, N]
+    mean, var = B.initial_values(_dev(x, cuda), normalize=False, want_variance=True)
+    scale = np.abs(h["avg"]).max(axis=1)
+    assert (np.abs(mean.cpu().numpy().T - h["avg"]) / scale[:, None]).max() < 3e-7
+    np.testing.assert_allclose(var.cpu().numpy().T, h["var"], rtol=2e-4)
+    unit, _ = B.initial_values(_dev(x, cuda), normalize=True)
+    np.testing.assert_allclose(unit.cpu().numpy().T, h["avg_unit"], atol=2e-6)
+
+
 def test_wahba_negative_weights_on_device(cuda):
     rng = np.random.default_rng(5)
     M = 1000

@@ -1,6 +1,7 @@
 """The oracle (oracle/ekf_oracle.py) against the frozen outputs of the unmodified reference and the
 reference's own known answers.  CPU only."""
 import numpy as np
+import pytest
 
 from oracle import ekf_oracle as O
 
@@ -135,3 +136,36 @@ def test_oracle_equals_reference_on_edge_cases(golden_edge):
             np.testing.assert_array_equal(X, g[f"{tag}_X"][:, n])
             np.testing.assert_array_equal(P, g[f"{tag}_P"][n])
             np.testing.assert_array_equal(flips, g[f"{tag}_flips"][:, n])
+
+
+def test_preprocessing_restatements_equal_the_reference_cpp():
+    """the oracle's interpolate / normalise / initial-values restatements against fixtures frozen
+    from the reference's OWN C++ (oracle/_ref: InitialValues.cpp compiled as is, Parser.cpp:221-228,259-267 extracted at
+    build time; tests/golden/make_golden_cpp.py): bit for bit."""
+    import os
+    from tests.conftest import GOLDEN
+    g = np.load(os.path.join(GOLDEN, "preprocess_ref.npz"))
+    np.testing.assert_array_equal(O.interpolate_sensor(g["y1"], g["y2"], g["t1"], g["t2"], g["t3"]), g["interpolated"])
+    np.testing.assert_array_equal(O.interpolate_normalise(g["y1"], g["y2"], g["t1"], g["t2"], g["t3"]), g["normalised"])
+    assert (g["t3"] == g["t1"]).sum() >= 64 and (g["t3"] > g["t2"]).sum() >= 64        # end points and extrapolation covered
+    h = np.load(os.path.join(GOLDEN, "initial_values_ref.npz"))
+    mean, var = O.initial_values(h["samples"])
+    np.testing.assert_array_equal(mean, h["avg"])
+    np.testing.assert_array_equal(var, h["var"])
+    np.testing.assert_array_equal(O.normalize_values(mean), h["avg_unit"])
+
+
+def test_reference_cpp_fixtures_regenerate_identically(tmp_path):
+    """Where the reference tree is present (the build container), re-running the recipe reproduces the committed fixtures."""
+    import os
+    import subprocess
+    import sys
+    from tests.conftest import GOLDEN, ROOT
+    if not os.path.exists("/root/reference/Kalman Filter Server/PoseEstimator/InitialValues.cpp"):
+        pytest.skip("reference tree not present (GPU box)")
+    subprocess.check_call([sys.executable, os.path.join(GOLDEN, "make_golden_cpp.py"), str(tmp_path)], stdout=subprocess.DEVNULL)
+    for name in ("preprocess_ref.npz", "initial_values_ref.npz"):
+        a, b = np.load(os.path.join(GOLDEN, name)), np.load(os.path.join(str(tmp_path), name))
+        assert sorted(a.files) == sorted(b.files)
+        for k in a.files:
+            np.testing.assert_array_equal(a[k], b[k])
