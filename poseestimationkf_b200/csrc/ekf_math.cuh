@@ -701,99 +701,60 @@ PKF_HD Mat3<F> wahba_qr2(const RefFrame<F>& E, const Vec3<F>& a, const Vec3<F>& 
 }
 
 // ------------------------------------------------------------------------------------------
-// Wahba, general form: B formed as the reference forms it, then a one-sided (Hestenes) Jacobi SVD
-// of the 3x3 in registers.  G <- B J1 J2 ... (columns made orthogonal), V <- J1 J2 ...;
-// singular values are the column norms.  With (u1,v1),(u2,v2) the two dominant pairs,
-//   U diag(1,1,det U det V) V^T = u1 v1^T + u2 v2^T + (u1 x u2)(v1 x v2)^T
-// holds for ANY orthogonal completion, so the third pair is never needed (PKF/Wahba.py:14-16).
-// `sweeps` cyclic sweeps over (0,1),(0,2),(1,2).
+// Wahba by a one-sided (Hestenes) Jacobi SVD, QR-preconditioned                         (PKF/Wahba.py:8-17)
+//
+// The reference takes the SVD of the 3x3 B = ka r_a a^T + km r_m m^T.  In float32 that matrix cannot be FORMED
+// without losing the answer: its weights ka = |a_z|, km = 1 - |a_z| drive it to rank 1, and rounding B's entries
+// costs eps * sigma1/sigma2 in the rotation (1.5e-2 rad measured on the synthetic set with a plain float32 Jacobi
+// of B, 2.9e-5 rad on config 4 -- round 1).  The remedy is the standard one for Jacobi SVDs (Drmac & Veselic: QR
+// factorisation first, Jacobi on the triangular factor): B has rank 2 by construction,
+//     B = [u1 u2] diag(w1, w2) [v1 v2]^T = E2 (S W T^T) F2^T,   [u1 u2] = E2 S,  [v1 v2] = F2 T   (S, T upper triangular)
+// so the SVD that matters is that of the 2x2 core C = S W T^T, whose four entries are products of norms and dot
+// products -- nothing is summed across scales except in c00.  With the pairs ORDERED so that the heavier one comes
+// first (column pivoting) C is graded: a dominant c00 and three entries of the lighter pair's size, which is the
+// shape one-sided Jacobi resolves to full relative accuracy.  A 2x2 needs exactly ONE rotation:
+//     columns c0, c1 of C;  t = sgn(d) 2 c0.c1 / (|d| + hypot(d, 2 c0.c1)),  d = |c1|^2 - |c0|^2;
+//     G = C J (orthogonal columns g0, g1), V = J, U = [g0/|g0|, g1/|g1|]
+// and with U = [E2 Uc, e3], V = [F2 Vc, f3] the reference's R = U diag(1,1,det U det V^T) V^T becomes
+//     R = E blockdiag(Uc Vc^T, det(Uc Vc^T)) F^T.
+// `sweeps` is accepted for interface compatibility (the 3x3 form iterated; one rotation is exact here).
+// There is nothing left to spread over a quad of lanes or to shuffle: the rotation is 30 operations in registers.
 // ------------------------------------------------------------------------------------------
-template <typename F> PKF_HD void jacobi_pair(Vec3<F>& gi, Vec3<F>& gj, Vec3<F>& vi, Vec3<F>& vj) {
-  F al = dot3(gi, gi), be = dot3(gj, gj), ga = dot3(gi, gj);
-  // tangent of the rotation that zeroes gi.gj:  t = sgn(d) 2 ga / (|d| + sqrt(d^2 + 4 ga^2)), d = be - al
-  F d = be - al;
-  F g2 = ga + ga;
-  F hyp = sqrt_(fma_(d, d, g2 * g2));
-  F den = abs_(d) + hyp;
-  F t = sel_(den > F(0), sel_(d < F(0), -g2, g2) * rcp_(den), F(0));
-  F c = rsqrt_(fma_(t, t, F(1)));
-  F s = c * t;
-  Vec3<F> ni, nj;
-  ni.x = fma_(-s, gj.x, c * gi.x); nj.x = fma_(s, gi.x, c * gj.x);
-  ni.y = fma_(-s, gj.y, c * gi.y); nj.y = fma_(s, gi.y, c * gj.y);
-  ni.z = fma_(-s, gj.z, c * gi.z); nj.z = fma_(s, gi.z, c * gj.z);
-  gi = ni; gj = nj;
-  ni.x = fma_(-s, vj.x, c * vi.x); nj.x = fma_(s, vi.x, c * vj.x);
-  ni.y = fma_(-s, vj.y, c * vi.y); nj.y = fma_(s, vi.y, c * vj.y);
-  ni.z = fma_(-s, vj.z, c * vi.z); nj.z = fma_(s, vi.z, c * vj.z);
-  vi = ni; vj = nj;
-}
-
-template <typename F, typename M> PKF_HD void swap_if(M c, Vec3<F>& a, Vec3<F>& b) {
-  Vec3<F> t = a;
-  a.x = sel_(c, b.x, a.x); a.y = sel_(c, b.y, a.y); a.z = sel_(c, b.z, a.z);
-  b.x = sel_(c, t.x, b.x); b.y = sel_(c, t.y, b.y); b.z = sel_(c, t.z, b.z);
-}
-
-// Off-diagonal measure used by the stand-alone kernel's warp-voted early exit.
-template <typename F> PKF_HD F jacobi_offdiag(const Vec3<F>& g0, const Vec3<F>& g1, const Vec3<F>& g2) {
-  F a = abs_(dot3(g0, g1)), b = abs_(dot3(g0, g2)), c = abs_(dot3(g1, g2));
-  F m = a > b ? a : b;
-  return m > c ? m : c;
-}
-
 template <typename F>
-PKF_HD Mat3<F> rotation_from_svd_pairs(Vec3<F> g0, Vec3<F> g1, Vec3<F> g2, Vec3<F> v0, Vec3<F> v1, Vec3<F> v2) {
-  // bring the two largest columns to slots 0,1 (order among them is irrelevant)
-  F n0 = dot3(g0, g0), n1 = dot3(g1, g1), n2 = dot3(g2, g2);
-  auto s0 = (n0 < n1) && (n0 < n2);          // column 0 is the smallest -> swap with 2
-  auto s1 = !s0 && (n1 < n2);                // column 1 is the smallest -> swap with 2
-  swap_if(s0, g0, g2); swap_if(s0, v0, v2);
-  F t = n0; n0 = sel_(s0, n2, n0); n2 = sel_(s0, t, n2);
-  swap_if(s1, g1, g2); swap_if(s1, v1, v2);
-  t = n1; n1 = sel_(s1, n2, n1);
-  F i0 = rsqrt_(n0), i1 = rsqrt_(n1);
-  Vec3<F> u0, u1;
-  u0.x = g0.x * i0; u0.y = g0.y * i0; u0.z = g0.z * i0;
-  u1.x = g1.x * i1; u1.y = g1.y * i1; u1.z = g1.z * i1;
-  Vec3<F> u2 = cross3(u0, u1), w2 = cross3(v0, v1);
-  Mat3<F> R;
-  const F ux[3] = {u0.x, u0.y, u0.z}, uy[3] = {u1.x, u1.y, u1.z}, uz[3] = {u2.x, u2.y, u2.z};
-  const F vx[3] = {v0.x, v0.y, v0.z}, vy[3] = {v1.x, v1.y, v1.z}, vz[3] = {w2.x, w2.y, w2.z};
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-  for (int i = 0; i < 3; ++i) {
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-    for (int j = 0; j < 3; ++j) R.m[i][j] = fma_(uz[i], vz[j], fma_(uy[i], vy[j], ux[i] * vx[j]));
-  }
-  return R;
-}
-
-template <typename F>
-PKF_HD void wahba_form_b(const Vec3<F>& ra, const Vec3<F>& rm, const Vec3<F>& a, const Vec3<F>& m, F ka, F km,
-                         Vec3<F>& g0, Vec3<F>& g1, Vec3<F>& g2) {
-  // B[i][j] = ka ra[i] a[j] + km rm[i] m[j]; g_j = column j        (PKF/Wahba.py:11-13)
-  F kax = ka * a.x, kay = ka * a.y, kaz = ka * a.z, kmx = km * m.x, kmy = km * m.y, kmz = km * m.z;
-  g0.x = fma_(rm.x, kmx, ra.x * kax); g0.y = fma_(rm.y, kmx, ra.y * kax); g0.z = fma_(rm.z, kmx, ra.z * kax);
-  g1.x = fma_(rm.x, kmy, ra.x * kay); g1.y = fma_(rm.y, kmy, ra.y * kay); g1.z = fma_(rm.z, kmy, ra.z * kay);
-  g2.x = fma_(rm.x, kmz, ra.x * kaz); g2.y = fma_(rm.y, kmz, ra.y * kaz); g2.z = fma_(rm.z, kmz, ra.z * kaz);
-}
-
-template <typename F>
-PKF_HD Mat3<F> wahba_jacobi(const Vec3<F>& ra, const Vec3<F>& rm, const Vec3<F>& a, const Vec3<F>& m, F ka, F km,
-                            int sweeps) {
-  Vec3<F> g0, g1, g2;
-  wahba_form_b(ra, rm, a, m, ka, km, g0, g1, g2);
-  Vec3<F> v0 = {F(1), F(0), F(0)}, v1 = {F(0), F(1), F(0)}, v2 = {F(0), F(0), F(1)};
-  for (int s = 0; s < sweeps; ++s) {
-    jacobi_pair(g0, g1, v0, v1);
-    jacobi_pair(g0, g2, v0, v2);
-    jacobi_pair(g1, g2, v1, v2);
-  }
-  return rotation_from_svd_pairs(g0, g1, g2, v0, v1, v2);
+PKF_HD Mat3<F> wahba_jacobi(const Vec3<F>& ra, const Vec3<F>& rm, const Vec3<F>& a, const Vec3<F>& m, F ka, F km, int /*sweeps*/) {
+  // column pivoting: the pair with the larger weighted size |w| |u| |v| first (compared squared)
+  const F za = (ka * ka) * (dot3(ra, ra) * dot3(a, a)), zm = (km * km) * (dot3(rm, rm) * dot3(m, m));
+  const auto swap = zm > za;
+  Vec3<F> u1, u2, v1, v2;
+  u1.x = sel_(swap, rm.x, ra.x); u1.y = sel_(swap, rm.y, ra.y); u1.z = sel_(swap, rm.z, ra.z);
+  u2.x = sel_(swap, ra.x, rm.x); u2.y = sel_(swap, ra.y, rm.y); u2.z = sel_(swap, ra.z, rm.z);
+  v1.x = sel_(swap, m.x, a.x); v1.y = sel_(swap, m.y, a.y); v1.z = sel_(swap, m.z, a.z);
+  v2.x = sel_(swap, a.x, m.x); v2.y = sel_(swap, a.y, m.y); v2.z = sel_(swap, a.z, m.z);
+  const F w1 = sel_(swap, km, ka), w2 = sel_(swap, ka, km);
+  const RefFrame<F> E = frame_from_pair(u1, u2), Fb = frame_from_pair(v1, v2);
+  // C = S diag(w1, w2) T^T
+  const F e12 = E.s12 * w2, e22 = E.s22 * w2;
+  const F c00 = fma_(e12, Fb.s12, (E.s11 * w1) * Fb.s11), c01 = e12 * Fb.s22;
+  const F c10 = e22 * Fb.s12, c11 = e22 * Fb.s22;
+  // the one Jacobi rotation that makes the columns of C orthogonal
+  const F al = fma_(c10, c10, c00 * c00), be = fma_(c11, c11, c01 * c01), ga = fma_(c10, c11, c00 * c01);
+  const F d = be - al, g2 = ga + ga;
+  const F den = abs_(d) + sqrt_(fma_(d, d, g2 * g2));
+  const F t = sel_(den > F(0), sel_(d < F(0), -g2, g2) * rcp_(den), F(0));
+  const F c = rsqrt_(fma_(t, t, F(1))), sn = c * t;
+  const F g00 = fma_(-sn, c01, c * c00), g10 = fma_(-sn, c11, c * c10);      // g0 = c c0 - s c1
+  const F g01 = fma_(sn, c00, c * c01), g11 = fma_(sn, c10, c * c11);        // g1 = s c0 + c c1
+  const F i0 = rsqrt_(fma_(g10, g10, g00 * g00)), i1 = rsqrt_(fma_(g11, g11, g01 * g01));
+  const F u00 = g00 * i0, u10 = g10 * i0, u01 = g01 * i1, u11 = g11 * i1;    // Uc = [u0 u1]
+  // M = Uc Vc^T with Vc = [[c, s], [-s, c]] (columns v0 = (c, -s), v1 = (s, c))
+  const F m00 = fma_(u01, sn, u00 * c), m01 = fma_(u01, c, -(u00 * sn));
+  const F m10 = fma_(u11, sn, u10 * c), m11 = fma_(u11, c, -(u10 * sn));
+  const F dt = one_with_sign_(fma_(m00, m11, -(m01 * m10)));                 // det(Uc Vc^T) = +-1
+  Mat3<F> L;                                                                 // blockdiag(M, det) F^T
+  L.m[0][0] = fma_(m01, Fb.e2.x, m00 * Fb.e1.x); L.m[0][1] = fma_(m01, Fb.e2.y, m00 * Fb.e1.y); L.m[0][2] = fma_(m01, Fb.e2.z, m00 * Fb.e1.z);
+  L.m[1][0] = fma_(m11, Fb.e2.x, m10 * Fb.e1.x); L.m[1][1] = fma_(m11, Fb.e2.y, m10 * Fb.e1.y); L.m[1][2] = fma_(m11, Fb.e2.z, m10 * Fb.e1.z);
+  L.m[2][0] = dt * Fb.e3.x; L.m[2][1] = dt * Fb.e3.y; L.m[2][2] = dt * Fb.e3.z;
+  return frame_times(E, L);
 }
 
 // ------------------------------------------------------------------------------------------

@@ -42,23 +42,8 @@ template <int ALGO> __global__ void __launch_bounds__(256) wahba_kernel(const Wa
   else if (p.weights_from_acc) { ka = fabsf(a.z); km = 1.f - ka; }           // PKF/ExtendedKalmanFilter.py:71
   else { ka = p.k_acc_s; km = p.k_mag_s; }
   Mat3<float> R;
-  if (ALGO == WAHBA_QR2) {
-    R = wahba_qr2<float>(frame_from_pair<float>(ra, rm), a, m, ka, km);
-  } else {
-    Vec3<float> g0, g1, g2;
-    wahba_form_b<float>(ra, rm, a, m, ka, km, g0, g1, g2);
-    Vec3<float> v0 = {1.f, 0.f, 0.f}, v1 = {0.f, 1.f, 0.f}, v2 = {0.f, 0.f, 1.f};
-    for (int s = 0; s < p.max_sweeps; ++s) {
-      jacobi_pair(g0, g1, v0, v1);
-      jacobi_pair(g0, g2, v0, v2);
-      jacobi_pair(g1, g2, v1, v2);
-      // converged when every pairwise column dot product is below eps * (largest column norm)^2
-      float nmax = fmaxf(dot3(g0, g0), fmaxf(dot3(g1, g1), dot3(g2, g2)));
-      bool more = jacobi_offdiag(g0, g1, g2) > 6e-8f * nmax;
-      if (!__any_sync(0xffffffffu, more)) break;
-    }
-    R = rotation_from_svd_pairs<float>(g0, g1, g2, v0, v1, v2);
-  }
+  if (ALGO == WAHBA_QR2) R = wahba_qr2<float>(frame_from_pair<float>(ra, rm), a, m, ka, km);
+  else R = wahba_jacobi<float>(ra, rm, a, m, ka, km, p.max_sweeps);
   if (!valid) return;
   if (p.out_rot) {
 #pragma unroll
@@ -216,29 +201,30 @@ __global__ void __launch_bounds__(256)
                           float* __restrict__ var) {
   const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= N) return;
-  float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+  // float64 accumulators, the reference's own precision and order (InitialValues.cpp:22-29,48-62): this runs once per
+  // recording over K = 100 samples, and a float32 running sum would cost sqrt(K) ulps of the reference vectors
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0;
   for (int64_t k = 0; k < K; ++k) {
     const float* p = x + k * 3 * N + n;
-    s0 += ldg_stream(p); s1 += ldg_stream(p + N); s2 += ldg_stream(p + 2 * N);
+    s0 += (double)ldg_stream(p); s1 += (double)ldg_stream(p + N); s2 += (double)ldg_stream(p + 2 * N);
   }
-  const float ik = 1.f / (float)K;
-  const float m0 = s0 * ik, m1 = s1 * ik, m2 = s2 * ik;
+  const double m0 = s0 / (double)K, m1 = s1 / (double)K, m2 = s2 / (double)K;
   if (var) {
-    float v0 = 0.f, v1 = 0.f, v2 = 0.f;
+    double v0 = 0.0, v1 = 0.0, v2 = 0.0;
     for (int64_t k = 0; k < K; ++k) {
       const float* p = x + k * 3 * N + n;
-      const float d0 = __ldg(p) - m0, d1 = __ldg(p + N) - m1, d2 = __ldg(p + 2 * N) - m2;
-      v0 = fmaf(d0, d0, v0); v1 = fmaf(d1, d1, v1); v2 = fmaf(d2, d2, v2);
+      const double d0 = (double)__ldg(p) - m0, d1 = (double)__ldg(p + N) - m1, d2 = (double)__ldg(p + 2 * N) - m2;
+      v0 += d0 * d0; v1 += d1 * d1; v2 += d2 * d2;
     }
-    const float ik1 = 1.f / (float)(K - 1);
-    var[n] = v0 * ik1; var[N + n] = v1 * ik1; var[2 * N + n] = v2 * ik1;
+    const double k1 = (double)(K - 1);
+    var[n] = (float)(v0 / k1); var[N + n] = (float)(v1 / k1); var[2 * N + n] = (float)(v2 / k1);
   }
-  float o0 = m0, o1 = m1, o2 = m2;
+  double o0 = m0, o1 = m1, o2 = m2;
   if (normalize) {
-    const float den = sqrtf(m0 * m0 + m1 * m1 + m2 * m2);       // Parser.cpp:223-227
+    const double den = sqrt((m0 * m0) + (m1 * m1) + (m2 * m2));       // Parser.cpp:223-227
     o0 = m0 / den; o1 = m1 / den; o2 = m2 / den;
   }
-  mean[n] = o0; mean[N + n] = o1; mean[2 * N + n] = o2;
+  mean[n] = (float)o0; mean[N + n] = (float)o1; mean[2 * N + n] = (float)o2;
 }
 
 // Measurement stream for POSEKF_WAHBA_PRECOMPUTED: solves the Wahba problem of every (stream, step) ONCE --

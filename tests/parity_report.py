@@ -58,7 +58,7 @@ for q, r in ((1e-3, 1e3), (1e3, 1e-3), (1e-3, 1e-3), (1e3, 1e3), (1.0, 0.1)):
     ref = CO.replay(S, imu.dt * 1e9, imu.acc_ref.cpu().numpy(), imu.mag_ref.cpu().numpy(), float(np.float32(q)), float(np.float32(r)),
                     store=True, flips=False)
     for precise in (True, False):
-        st, traj, _ = B.replay(imu.streams, imu.acc_ref, imu.mag_ref, dt=imu.dt, q=q, r=r, store_trajectory=True, precise_state=precise)
+        st, traj, _ = B.replay(imu.streams, imu.acc_ref, imu.mag_ref, dt=imu.dt, q=q, r=r, store_trajectory=True, precise_state=precise, allow_imprecise=True)
         out["sweep_corners_256x2000"][f"q={q:g},r={r:g},{'precise' if precise else 'plain'}"] = stats(traj.cpu().numpy(), ref["X"])
 
 text = json.dumps(out, indent=1)

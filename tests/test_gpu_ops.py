@@ -31,18 +31,17 @@ def test_wahba_vs_reference_golden(golden_wahba, cuda, tag, algo):
     R, q = B.wahba(*args, k_acc=_dev(g[f"{tag}_ka"], cuda), k_mag=_dev(g[f"{tag}_km"], cuda), want_rotation=True,
                    algo=algo)
     ang = O.quat_angle(q.cpu().numpy().T, g[f"{tag}_q"])
-    if algo == "qr2":
-        assert ang.max() < 2e-6, ang.max()
-        np.testing.assert_allclose(R.cpu().numpy().T.reshape(-1, 3, 3), g[f"{tag}_R"], atol=5e-6)
-    else:
-        assert (ang < 1e-6 + 4 * 6e-8 * _cond(g, tag)).all()
+    # both solvers hold the reference's rotation for BOTH weightings (the Jacobi SVD is QR-preconditioned: it works on the
+    # 2x2 core of the rank-2 problem, so the reference's near-rank-1 weights cost it nothing -- wahba_jacobi in ekf_math.cuh)
+    assert ang.max() < (2e-6 if algo == "qr2" else 4e-6), ang.max()
+    np.testing.assert_allclose(R.cpu().numpy().T.reshape(-1, 3, 3), g[f"{tag}_R"], atol=5e-6 if algo == "qr2" else 1e-5)
     assert (np.sum(q.cpu().numpy().T * g[f"{tag}_q"], axis=1) < 0).sum() == 0       # the reference's sign convention, every case
     if tag == "half":       # scalar weights and the reference-weights shortcut go through the same kernel
         _, q2 = B.wahba(*args, k_acc=0.5, k_mag=0.5, algo=algo)
         assert torch.equal(q2, q)
     else:
         _, q3 = B.wahba(*args, weights_from_acc=True, algo=algo)
-        assert O.quat_angle(q3.cpu().numpy().T, g["refw_q"]).max() < (2e-6 if algo == "qr2" else 1.0)
+        assert O.quat_angle(q3.cpu().numpy().T, g["refw_q"]).max() < (2e-6 if algo == "qr2" else 4e-6)
 
 
 def test_wahba_hand_check_and_shared_reference(cuda):
@@ -266,16 +265,16 @@ def test_preprocess_and_initial_values_vs_reference_cpp_golden(cuda):
     got = out[0].cpu().numpy()
     np.testing.assert_allclose(got[3:6].T, g["normalised"][:H], atol=2e-6)
     np.testing.assert_allclose(got[6:9].T, g["normalised"][H:], atol=2e-6)
-    ang = np.arccos(np.clip(np.sum(np.concatenate([got[3:6].T, got[6:9].T]) * g["normalised"], axis=1), -1, 1))
-    assert ang.max() < 1e-5 / 2          # as a direction: far inside the filter's own tolerance
+    chord = np.linalg.norm(np.concatenate([got[3:6].T, got[6:9].T]) - g["normalised"], axis=1)     # = the angle between the
+    assert chord.max() < 3e-6            # unit vectors (arccos of their dot product would amplify the float32 rounding of 1)
     h = np.load(os.path.join(GOLDEN, "initial_values_ref.npz"))
     x = np.ascontiguousarray(h["samples"].transpose(1, 2, 0))             # [K, 3, N]
     mean, var = B.initial_values(_dev(x, cuda), normalize=False, want_variance=True)
     scale = np.abs(h["avg"]).max(axis=1)
-    assert (np.abs(mean.cpu().numpy().T - h["avg"]) / scale[:, None]).max() < 3e-7
-    np.testing.assert_allclose(var.cpu().numpy().T, h["var"], rtol=2e-4)
+    assert (np.abs(mean.cpu().numpy().T - h["avg"]) / scale[:, None]).max() < 1e-7      # float32 rounding of the output
+    np.testing.assert_allclose(var.cpu().numpy().T, h["var"], rtol=2e-7)
     unit, _ = B.initial_values(_dev(x, cuda), normalize=True)
-    np.testing.assert_allclose(unit.cpu().numpy().T, h["avg_unit"], atol=2e-6)
+    np.testing.assert_allclose(unit.cpu().numpy().T, h["avg_unit"], atol=1e-7)
 
 
 def test_wahba_negative_weights_on_device(cuda):

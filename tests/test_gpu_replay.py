@@ -54,21 +54,17 @@ def test_replay_vs_oracle_seeded(cuda, algo):
     ref = _oracle(imu.streams, imu.acc_ref, imu.mag_ref, imu.dt, 1.0, 0.1)
     got = traj.cpu().numpy().astype(np.float64)
     ang = O.quat_angle(got, ref["X"])
-    if algo == "qr2":
+    if True:      # both Wahba solvers hold the tolerance (the Jacobi SVD is QR-preconditioned since round 2)
         assert ang.max() < TOL, ang.max()
         assert (np.sum(got * ref["X"], axis=-1) > 0).all()
+    if algo == "qr2":
         # identical q/-q choices (north_star): float32 ties of the reference's 3-branch sign rule are settled in float64
         # by flip_fixup_kernel, so the mask is the reference's, bit for bit
         fl = flips.cpu().numpy()
         assert fl.max() <= 1                              # no tie marker survives the fix-up pass
         assert (fl.astype(bool) != ref["flips"]).sum() == 0
     else:
-        # B formed in float32: fine where the reference's weights keep B well conditioned, degraded
-        # where |a_z| -> 0 or 1 (documented in DESIGN.md; this is why QR2 is the default)
-        az = np.abs(imu.streams[:, 5].cpu().numpy())
-        assert np.median(ang) < 1e-6
-        assert np.isfinite(got).all()
-        assert ang[(az > 0.2) & (az < 0.8)].max() < 5e-4
+        assert (flips.cpu().numpy().astype(bool) != ref["flips"]).sum() <= 2      # no float64 tie fix-up on this path
 
 
 def test_ragged_and_unaligned_batches(cuda):
@@ -292,7 +288,7 @@ def test_compensated_state_long_replay_extreme_tunings(cuda):
     worst, by_variant = {}, {}
     for precise in (True, False):
         st, traj, _ = B.replay(imu.streams, imu.acc_ref, imu.mag_ref, dt=imu.dt, q=q_t, r=r_t, n_filters=G * Ns,
-                               store_trajectory=True, precise_state=precise)
+                               store_trajectory=True, precise_state=precise, allow_imprecise=True)
         got = traj.cpu().numpy().reshape(T, G, Ns, 4)
         worst[precise] = [O.quat_angle(got[:, gi], refs[gi]["X"]).max() for gi in range(G)]
         assert (st.x_lo is not None) == precise
@@ -310,6 +306,15 @@ def test_compensated_state_long_replay_extreme_tunings(cuda):
         assert torch.equal(st_auto.x[:, sl], want.x[:, sl]) and torch.equal(st_auto.p[:, sl], want.p[:, sl]), (q, r)
     st_def, _, _ = B.replay(imu.streams, imu.acc_ref, imu.mag_ref, dt=imu.dt, q=1.0, r=0.1)
     assert st_def.x_lo is None
+    # the plain variant is refused for a tuning it cannot hold to 1e-5 rad, unless the caller insists; bad scales are refused
+    with pytest.raises(ValueError):
+        B.replay(imu.streams, imu.acc_ref, imu.mag_ref, dt=imu.dt, q=1e-3, r=1e3, precise_state=False)
+    with pytest.raises(ValueError):
+        B.replay(imu.streams, imu.acc_ref, imu.mag_ref, dt=imu.dt, q=q_t, r=r_t, n_filters=G * Ns, precise_state=False, store_flips=True)
+    with pytest.raises(ValueError):
+        B.replay(imu.streams, imu.acc_ref, imu.mag_ref, dt=imu.dt, q=1.0, r=torch.zeros((Ns,), device=cuda))
+    with pytest.raises(ValueError):
+        B.replay(imu.streams, imu.acc_ref, imu.mag_ref, dt=imu.dt, q=-1.0, r=0.1)
     # chunked == unchunked also for the two-float state
     st_c = B.ReplayState.initial(G * Ns, cuda, r=r_t)
     for t0, t1 in ((0, 1777), (1777, T)):
@@ -366,9 +371,9 @@ def test_packed_kernel_bitwise_equals_scalar(cuda):
                         B.replay(imu.streams, imu.acc_ref, imu.mag_ref, dt=imu.dt, q=q, r=r, staging="tma_packed", **kw)
                     continue
                 a, _, _ = B.replay(imu.streams, imu.acc_ref, imu.mag_ref, dt=imu.dt, q=q, r=r, precise_state=precise,
-                                   staging="tma", **kw)
+                                   staging="tma", allow_imprecise=True, **kw)
                 b, _, _ = B.replay(imu.streams, imu.acc_ref, imu.mag_ref, dt=imu.dt, q=q, r=r, precise_state=precise,
-                                   staging="tma_packed", **kw)
+                                   staging="tma_packed", allow_imprecise=True, **kw)
                 assert torch.equal(a.x, b.x) and torch.equal(a.p, b.p)
                 if precise:
                     assert torch.equal(a.x_lo, b.x_lo)
@@ -502,7 +507,7 @@ def test_sweep_with_automatic_precision_per_cell(cuda):
     ref_variant = {}
     for precise in (False, True):
         ref_variant[precise], _, _ = B.replay(imu.streams, imu.acc_ref, imu.mag_ref, dt=imu.dt, q=q_t, r=r_t, n_filters=N, truth=truth,
-                                              precise_state=precise)
+                                              precise_state=precise, allow_imprecise=True)
     n_precise = 0
     for gi, (q, r) in enumerate(grid):
         ref = _oracle(imu.streams, imu.acc_ref, imu.mag_ref, imu.dt, float(np.float32(q)), float(np.float32(r)), store=False)
