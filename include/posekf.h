@@ -35,7 +35,10 @@ extern "C" {
 #define POSEKF_WAHBA_QR2    0   /* rank-2 forms that never build B: stand-alone entry points use the QR of both vector
                                    pairs + closed-form 2x2 polar factor; the fused replay solves for the quaternion
                                    directly (two-observation closed form) and keeps the former for negative weights */
-#define POSEKF_WAHBA_JACOBI 1   /* B formed as in PKF/Wahba.py:11-13, one-sided Jacobi SVD in registers */
+#define POSEKF_WAHBA_JACOBI 1   /* the SVD of PKF/Wahba.py:14 as a one-sided (Hestenes) Jacobi SVD in registers, QR-preconditioned:
+                                   B = ka r_a a^T + km r_m m^T has rank 2, so the rotation is applied to its 2x2 core
+                                   (QR of both vector pairs, heavier pair first); accurate to float32 rounding for any
+                                   weights, including the reference's near-rank-1 (|a_z|, 1-|a_z|).  One thread per problem */
 #define POSEKF_WAHBA_PRECOMPUTED 2 /* posekf_replay_f32 only: stream rows 3-6 already hold the Wahba quaternion
                                       (posekf_measurement_stream_f32) -- for (Q,R) sweeps over shared streams */
 
@@ -98,7 +101,9 @@ const char* posekf_version(void);
  *   out_traj    [T][N][4] state after every step (one 16-byte quaternion per filter-step, i.e. the
  *               reference's X_k list, PKF/main_file.py:44, for every filter), 16-byte aligned, or NULL
  *   out_flip    [T][N] uint8, 1 where the comparator negated the Wahba quaternion
- *               (PKF/ExtendedKalmanFilter.py:73-75), or NULL
+ *               (PKF/ExtendedKalmanFilter.py:73-75), or NULL.  With POSEKF_WAHBA_QR2 on raw samples (no low-pass) the
+ *               mask is the float64 reference's bit for bit: steps where its 3-branch sign rule (PKF/Wahba.py:26-47)
+ *               sits on a float32 tie are re-decided in float64 by a second small kernel launched by this call
  *   truth       [T][Ns][4] reference track (ground truth, a Wahba-only or gyro-only track, another
  *               run's out_traj ...) for the on-device tuning objective, 16-byte aligned, or NULL
  *   loss_acc    [N] in/out, required with truth: loss_acc[n] += sum_t |X_t ^ truth_t|^2 = 1 - (X_t . truth_t)^2
@@ -127,7 +132,9 @@ int posekf_replay_f32(int64_t n_filters, int64_t n_steps, const float* streams, 
  *   workspace   from posekf_host_workspace_create (staging buffers, streams and events are reused across
  *               calls -- allocating and freeing GiB-sized buffers per call costs tens of ms), or NULL
  *               for a temporary one.
- * Host buffers should be page-locked (cudaHostAlloc / cudaHostRegister) for full PCIe rate. */
+ * Host buffers should be page-locked (cudaHostAlloc / cudaHostRegister) for full PCIe rate.
+ * Every r_scale must be > 0 and every q_scale >= 0 (checked on the host: POSEKF_EINVAL otherwise).  The caller's current
+ * CUDA device is restored before returning; on a failure all work issued so far is drained before the call returns. */
 int posekf_replay_host_f32(int64_t n_filters, int64_t n_steps, const float* streams_host, float dt,
                            const float* acc_ref_host, const float* mag_ref_host, const float* q_scale_host,
                            const float* r_scale_host, float lpf_alpha_acc, float lpf_alpha_mag,
@@ -148,8 +155,8 @@ int posekf_host_workspace_destroy(void* workspace);
  *               weights_from_acc != 0, the reference's k_acc=|acc_z|, k_mag=1-|acc_z|
  *               (PKF/ExtendedKalmanFilter.py:71)
  *   out_rot     [9][N] rotation matrix (row-major) or NULL;  out_quat [4][N] or NULL
- *   jacobi_sweeps  maximum cyclic sweeps for POSEKF_WAHBA_JACOBI (<=0: default 6; the loop exits
- *               early when every lane of the warp has converged)
+ *   jacobi_sweeps  accepted for interface compatibility and ignored: the QR-preconditioned Jacobi SVD works on a
+ *               2x2 core, for which ONE rotation is exact
  */
 int posekf_wahba_f32(int64_t n, const float* acc_ref, const float* mag_ref, int ref_shared, const float* acc,
                      const float* mag, const float* k_acc, const float* k_mag, float k_acc_s, float k_mag_s,

@@ -10,7 +10,7 @@ import numpy as np
 
 from poseestimationkf_b200 import _lib
 from Wahba import Wahba
-from _bridge import as_rows, call, from_rows
+from _bridge import FixedCall, as_rows, call, from_rows, is_single, is_single_matrix
 
 
 def _dt_rows(dt_seconds, n):
@@ -60,7 +60,18 @@ class KalmanFilter:
         out, = call([qd], [12], lambda i, o, n, s: lib.posekf_jacobians_f32(n, None, None, i[0], o[0], s))
         return from_rows(out, (4, 3), batched)
 
+    # fixed layouts of the one-filter calls (see _bridge.FixedCall): inputs / outputs per argument
+    _predict1 = FixedCall([(3,), (1,), (4,), (4, 4), (3, 3), (4, 4)], [(4,), (4, 4), (4, 4)])
+    _correct1 = FixedCall([(3,), (3,), (3,), (3,), (4,), (4, 4), (4, 4)], [(4,), (4, 4)])
+
     def Prediction(self, Gyro, T, X_k, P_k):               # :58-68
+        if is_single(Gyro, 3) and is_single(X_k, 4) and is_single_matrix(P_k, 4, 4) and np.ndim(T) == 0:
+            dt = (float(T) - float(self.previousT)) * (10 ** -9)
+            z, pn, k = self._predict1.run(
+                [Gyro, dt, X_k, P_k, self.Q, self.R],
+                lambda lib, i, o, s: lib.posekf_predict_f32(1, i[0], i[1], 0, i[2], i[3], i[4], i[5], None, None, o[0], o[1], o[2], s))
+            self.previousT = T                             # :67
+            return z, pn, k
         g, batched = as_rows(Gyro, (3,))
         x, _ = as_rows(X_k, (4,))
         p, _ = as_rows(P_k, (4, 4))
@@ -76,6 +87,14 @@ class KalmanFilter:
         return from_rows(z, (4,), batched), from_rows(pn, (4, 4), batched), from_rows(k, (4, 4), batched)
 
     def Correction(self, Mag, Acc, z_k, P_k, K_k):         # :70-80 (NB: Mag before Acc)
+        w = self.wahba
+        if (is_single(Mag, 3) and is_single(Acc, 3) and is_single(z_k, 4) and is_single_matrix(P_k, 4, 4)
+                and is_single_matrix(K_k, 4, 4) and is_single(w.w_initial_acc, 3) and is_single(w.w_initial_mag, 3)):
+            algo = _lib.WAHBA[w.algo]
+            x, pn = self._correct1.run(
+                [Mag, Acc, w.w_initial_acc, w.w_initial_mag, z_k, P_k, K_k],
+                lambda lib, i, o, s: lib.posekf_correct_f32(1, i[0], i[1], i[2], i[3], 1, i[4], i[5], i[6], o[0], o[1], None, None, algo, s))
+            return x, pn
         m, batched = as_rows(Mag, (3,))
         a, _ = as_rows(Acc, (3,))
         z, _ = as_rows(z_k, (4,))

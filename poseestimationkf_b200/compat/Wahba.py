@@ -1,12 +1,12 @@
 """`Wahba.Wahba` with the reference's interface (reference: Python Kalman Filter/Wahba.py:3-50),
-backed by the sm_100a kernels.  `algo` selects the device algorithm ("qr2": rank-2 SVD, accurate
-for any weights in float32; "jacobi": B formed as the reference forms it + one-sided Jacobi SVD)."""
+backed by the sm_100a kernels.  `algo` selects the device algorithm ("qr2": rank-2 SVD with a closed-form 2x2 polar
+factor; "jacobi": QR-preconditioned one-sided Jacobi SVD -- both accurate to float32 rounding for any weights)."""
 from __future__ import annotations
 
 import numpy as np
 
 from poseestimationkf_b200 import _lib
-from _bridge import as_rows, call, from_rows
+from _bridge import FixedCall, as_rows, call, from_rows, is_single
 
 
 class Wahba:
@@ -31,7 +31,17 @@ class Wahba:
         k = np.asarray(k, dtype=np.float64)
         return np.broadcast_to(k.astype(np.float32).reshape(-1), (n,)).reshape(1, n).copy()
 
+    _solve1 = FixedCall([(3,), (3,), (3,), (3,)], [(3, 3), (4,)])
+
     def _solve(self, acc, mag, k_acc, k_mag, want_rotation):
+        if (is_single(acc, 3) and is_single(mag, 3) and is_single(self.w_initial_acc, 3) and is_single(self.w_initial_mag, 3)
+                and np.ndim(k_acc) == 0 and np.ndim(k_mag) == 0):
+            algo, ka, km = _lib.WAHBA[self.algo], float(k_acc), float(k_mag)
+            rot, quat = self._solve1.run(
+                [self.w_initial_acc, self.w_initial_mag, acc, mag],
+                lambda lib, i, o, s: lib.posekf_wahba_f32(1, i[0], i[1], 1, i[2], i[3], None, None, ka, km, 0,
+                                                          o[0] if want_rotation else None, None if want_rotation else o[1], algo, 0, s))
+            return rot if want_rotation else quat
         a, batched = as_rows(acc, (3,))
         m, _ = as_rows(mag, (3,))
         n = a.shape[1]

@@ -1,8 +1,13 @@
 """numpy <-> device plumbing shared by the compat modules (batch of 1 like the reference, or a
 leading batch dimension).  Every reference-named call packs all of its inputs into ONE pinned
-staging buffer (one H2D copy), launches the kernel(s) on raw pointers into that buffer, and reads
-all outputs back with ONE D2H copy -- a per-call latency of a few tens of microseconds instead of
-one copy per argument."""
+staging buffer and launches the kernel(s) on raw pointers.
+
+Small calls (the reference's own use: one filter per call, `main_file.py:38-47`) are ZERO-COPY: pinned host memory is
+mapped into the device's address space under unified addressing (same pointer value on both sides), so the kernel
+reads its few dozen inputs from the pinned buffer and writes its outputs to another one directly over the host link --
+one kernel launch and one stream synchronisation per call, no `cudaMemcpyAsync`.  Large batches stage through device
+memory instead (one H2D copy, kernel, one D2H copy): reading megabytes through the link from inside a kernel would be
+slower than a bulk copy."""
 from __future__ import annotations
 
 import numpy as np
@@ -22,13 +27,17 @@ def as_rows(a, per_item_shape):
     arr = np.asarray(a, dtype=np.float64)
     batched = arr.ndim == len(per_item_shape) + 1
     if not batched:
-        arr = arr[None]
+        if arr.shape != tuple(per_item_shape):
+            raise ValueError(f"expected shape {per_item_shape} (optionally with a leading batch dim), got {arr.shape}")
+        return arr.astype(np.float32).reshape(-1, 1), False      # one filter: the [k, 1] column is the flattened item
     if arr.shape[1:] != tuple(per_item_shape):
         raise ValueError(f"expected shape {per_item_shape} (optionally with a leading batch dim), got {arr.shape}")
     return arr.reshape(arr.shape[0], -1).T.astype(np.float32), batched
 
 
 def from_rows(rows, per_item_shape, batched):
+    if not batched:
+        return rows.astype(np.float64).reshape(per_item_shape)
     arr = rows.astype(np.float64).T
     arr = arr.reshape(arr.shape[0], *per_item_shape)
     return arr if batched else arr[0]
@@ -59,6 +68,9 @@ class _Staging:
 _staging = _Staging()
 
 
+ZERO_COPY_MAX_FLOATS = 4096      # in + out floats up to which a call runs on the mapped pinned buffers
+
+
 def call(inputs, out_rows, launch):
     """inputs: list of float32 arrays [k_i, n_i] (n_i = N, or 1-D [k] for data shared by all filters);
     out_rows: list of (k_j) row counts of [k_j, N] outputs; N taken from the first 2-D input.
@@ -84,10 +96,86 @@ def call(inputs, out_rows, launch):
     lib = _lib.load()
     stream = torch.cuda.current_stream().cuda_stream
     h_in, base_in, h_out, base_out = st.ptrs
-    _lib.check(lib.posekf_copy_async(base_in, h_in, 4 * n_in, 1, stream), "posekf_copy_async")
+    zero_copy = n_in + n_out <= ZERO_COPY_MAX_FLOATS
+    if zero_copy:        # the kernel works on the mapped pinned buffers themselves
+        base_in, base_out = h_in, h_out
+    else:
+        _lib.check(lib.posekf_copy_async(base_in, h_in, 4 * n_in, 1, stream), "posekf_copy_async")
     rc = launch([base_in + 4 * o for o in offs], [base_out + 4 * o for o in out_offs], N, stream)
     for code in (rc if isinstance(rc, (list, tuple)) else [rc]):
         _lib.check(code, "posekf compat call")
-    _lib.check(lib.posekf_copy_async(h_out, base_out, 4 * n_out, 0, stream), "posekf_copy_async")
+    if not zero_copy:
+        _lib.check(lib.posekf_copy_async(h_out, base_out, 4 * n_out, 0, stream), "posekf_copy_async")
     _lib.check(lib.posekf_stream_sync(stream), "posekf_stream_sync")
     return [st.np_out[o:o + s].reshape(k, N).copy() for o, s, k in zip(out_offs, out_sizes, out_rows)]
+
+
+# ------------------------------------------------------------------------------------------------
+# One-filter fast path (what the reference's own loop does, main_file.py:38-47): a call with a FIXED argument layout
+# keeps its own small mapped pinned buffers with numpy views bound once, so that a call is a handful of slice
+# assignments (numpy converts float64 -> float32 in C), ONE kernel launch on the mapped buffers, ONE stream
+# synchronisation and a few float32 -> float64 conversions on the way out.
+# ------------------------------------------------------------------------------------------------
+def is_single(a, n) -> bool:
+    """True for ONE item of n scalars (list / tuple / 1-D array), False for a batch with a leading dimension."""
+    if isinstance(a, np.ndarray):
+        return a.ndim == 1 and a.shape[0] == n
+    try:
+        return len(a) == n and not hasattr(a[0], "__len__")
+    except TypeError:
+        return False
+
+
+def is_single_matrix(a, rows, cols) -> bool:
+    if isinstance(a, np.ndarray):
+        return a.shape == (rows, cols)
+    try:
+        return len(a) == rows and len(a[0]) == cols and not hasattr(a[0][0], "__len__")
+    except TypeError:
+        return False
+
+
+class FixedCall:
+    """in_shapes / out_shapes: per-argument shapes of ONE filter, e.g. [(3,), (1,), (4,), (4, 4)]."""
+
+    def __init__(self, in_shapes, out_shapes):
+        self.in_shapes, self.out_shapes = list(in_shapes), list(out_shapes)
+        self.bound = False
+
+    def _bind(self):
+        def layout(shapes):
+            offs, pos = [], 0
+            for sh in shapes:
+                offs.append(pos)
+                pos += (int(np.prod(sh)) + 3) & ~3          # 16-byte aligned segments
+            return offs, max(pos, 4)
+        device()                                            # raises without a CUDA device
+        in_offs, n_in = layout(self.in_shapes)
+        out_offs, n_out = layout(self.out_shapes)
+        self.h_in = torch.zeros(n_in, dtype=torch.float32).pin_memory()
+        self.h_out = torch.zeros(n_out, dtype=torch.float32).pin_memory()
+        np_in, np_out = self.h_in.numpy(), self.h_out.numpy()
+        self.inv = [np_in[o:o + int(np.prod(sh))].reshape(sh) for o, sh in zip(in_offs, self.in_shapes)]
+        self.outv = [np_out[o:o + int(np.prod(sh))].reshape(sh) for o, sh in zip(out_offs, self.out_shapes)]
+        # under unified addressing pinned host memory has the same address on the device
+        self.in_ptrs = [self.h_in.data_ptr() + 4 * o for o in in_offs]
+        self.out_ptrs = [self.h_out.data_ptr() + 4 * o for o in out_offs]
+        self.lib = _lib.load()
+        self.bound = True
+
+    def run(self, args, launch):
+        """args: one array-like per input slot (None = leave the slot as it is); launch(lib, in_ptrs, out_ptrs, stream)
+        returns the C status.  Returns float64 copies of the outputs."""
+        if not self.bound:
+            self._bind()
+        for view, a in zip(self.inv, args):
+            if a is not None:
+                view[...] = a
+        stream = torch.cuda.current_stream().cuda_stream
+        rc = launch(self.lib, self.in_ptrs, self.out_ptrs, stream)
+        if rc != 0:
+            _lib.check(rc, "posekf compat call")
+        rc = self.lib.posekf_stream_sync(stream)
+        if rc != 0:
+            _lib.check(rc, "posekf_stream_sync")
+        return [v.astype(np.float64) for v in self.outv]

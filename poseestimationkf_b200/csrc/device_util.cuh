@@ -45,6 +45,11 @@ constexpr int kTma2Stages = PKF_TMA2_STAGES;
 #ifndef PKF_FAST_TILE
 #define PKF_FAST_TILE 1
 #endif
+// PKF_L2_PREFETCH: tiles of the packed kernel's ring are requested into L2 this many tiles beyond the ring's own depth
+// (the ring holds the tile being processed and the next one; DRAM latency under load is about one tile's compute time)
+#ifndef PKF_L2_PREFETCH
+#define PKF_L2_PREFETCH 0
+#endif
 #ifndef PKF_AUTO_PACKED
 #define PKF_AUTO_PACKED 1
 #endif
@@ -96,6 +101,11 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, u
           smem_u32(dst)),
       "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
+}
+
+// TMA prefetch of a tile into L2 only (no shared memory, no barrier): used one tile further ahead than the ring holds
+__device__ __forceinline__ void tma_prefetch_l2_3d(const CUtensorMap* map, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" ::"l"(map), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
 
 __device__ __forceinline__ f32x2 ld2(const float* p) {

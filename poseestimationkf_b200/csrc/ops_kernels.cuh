@@ -373,8 +373,25 @@ __global__ void __launch_bounds__(256) rot2quat_kernel(int64_t N, const float* _
   for (int r = 0; r < 3; ++r)
 #pragma unroll
     for (int c = 0; c < 3; ++c) R.m[r][c] = rot[(3 * r + c) * N + n];
-  Quat<float> q = rotation_to_quat_ref<float>(R);
-  out[n] = q.w; out[N + n] = q.x; out[2 * N + n] = q.y; out[3 * N + n] = q.z;
+  // The stand-alone operator accepts ANY 3x3 the reference accepts (scaled, not orthogonal, the identity): it
+  // evaluates the reference's three branches literally, in float64 on the float32 inputs (PKF/Wahba.py:20-47), so
+  // the result is the reference's to the rounding of the float32 output -- not normalised, NaN at M == I (0/0).
+  // (The fused paths use rotation_to_quat_ref / the closed-form measurement, which assume a rotation.)
+  const double m00 = R.m[0][0], m01 = R.m[0][1], m02 = R.m[0][2], m10 = R.m[1][0], m11 = R.m[1][1], m12 = R.m[1][2],
+               m20 = R.m[2][0], m21 = R.m[2][1], m22 = R.m[2][2];
+  const double tr1 = 1.0 + m00 - m11 - m22, tr2 = 1.0 - m00 + m11 - m22, tr3 = 1.0 - m00 - m11 + m22;
+  double qw, qx, qy, qz;
+  if (tr1 > tr2 && tr1 > tr3) {
+    const double S = sqrt(tr1) * 2.0;
+    qw = (m21 - m12) / S; qx = 0.25 * S; qy = (m01 + m10) / S; qz = (m02 + m20) / S;
+  } else if (tr2 > tr1 && tr2 > tr3) {
+    const double S = sqrt(tr2) * 2.0;
+    qw = (m02 - m20) / S; qx = (m01 + m10) / S; qy = 0.25 * S; qz = (m12 + m21) / S;
+  } else {
+    const double S = sqrt(tr3) * 2.0;
+    qw = (m10 - m01) / S; qx = (m02 + m20) / S; qy = (m12 + m21) / S; qz = 0.25 * S;
+  }
+  out[n] = (float)qw; out[N + n] = (float)qx; out[2 * N + n] = (float)qy; out[3 * N + n] = (float)qz;
 }
 
 // ---------------------------------------------------------------------------------------------

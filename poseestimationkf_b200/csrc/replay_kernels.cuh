@@ -343,6 +343,10 @@ __global__ void __launch_bounds__(kThreads2, (AUX && COMP) ? (PKF_MIN_CTAS2 > 4 
       mbar_expect_tx(&sm.full[ps], kTile2Bytes);
       tma_load_3d(&sm.tile[ps][0][0][0], &tmap, &sm.full[ps], col0, 0, (k - 1 + kTma2Stages) * kTma2Steps);
     }
+#if PKF_L2_PREFETCH > 0
+    if (tid == 0 && (k + kTma2Stages - 1 + PKF_L2_PREFETCH) < n_chunks)
+      tma_prefetch_l2_3d(&tmap, col0, 0, (k + kTma2Stages - 1 + PKF_L2_PREFETCH) * kTma2Steps);
+#endif
     mbar_wait(&sm.full[stage], parity);
     if (valid) {
       const int steps = min(kTma2Steps, T - k * kTma2Steps);

