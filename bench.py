@@ -622,7 +622,8 @@ def run_c5(ctx, args):
     gather = {"gather_ms": None}
     if ctx.world > 1:
         SH = ctx.SH
-        SH.gather_states(state.x, N_total)          # warm-up (NCCL channel set-up)
+        SH.gather_states(state.x, N_total)          # warm-up (NCCL channel set-up, allocator) for both shapes
+        SH.gather_states(state.p, N_total)
         ctx.barrier()
         g0, g1, g2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
         g0.record()

@@ -373,10 +373,25 @@ __global__ void __launch_bounds__(256) rot2quat_kernel(int64_t N, const float* _
   for (int r = 0; r < 3; ++r)
 #pragma unroll
     for (int c = 0; c < 3; ++c) R.m[r][c] = rot[(3 * r + c) * N + n];
-  // The stand-alone operator accepts ANY 3x3 the reference accepts (scaled, not orthogonal, the identity): it
-  // evaluates the reference's three branches literally, in float64 on the float32 inputs (PKF/Wahba.py:20-47), so
-  // the result is the reference's to the rounding of the float32 output -- not normalised, NaN at M == I (0/0).
-  // (The fused paths use rotation_to_quat_ref / the closed-form measurement, which assume a rotation.)
+  // The stand-alone operator accepts ANY 3x3 the reference accepts.  A rotation (M^T M = I to 1e-3: every matrix the
+  // Wahba stage produces) goes through rotation_to_quat_ref: the best-conditioned Shepperd candidate with the
+  // reference's sign rule -- the reference's own formula divides by S = 2 sqrt(tr_i) -> 0 near the identity, which
+  // float64 survives and a float32 INPUT matrix does not (its 1e-7 rounding would come out as 1e-5).  Anything else
+  // (scaled, sheared) evaluates the reference's three branches literally, in float64 on the float32 inputs
+  // (PKF/Wahba.py:20-47): the reference's un-normalised vector to the rounding of the float32 output.
+  float ortho = 0.f;
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = i; j < 3; ++j) {
+      const float d = R.m[0][i] * R.m[0][j] + R.m[1][i] * R.m[1][j] + R.m[2][i] * R.m[2][j] - (i == j ? 1.f : 0.f);
+      ortho = fmaxf(ortho, fabsf(d));
+    }
+  if (ortho < 1e-3f) {
+    const Quat<float> q = rotation_to_quat_ref<float>(R);
+    out[n] = q.w; out[N + n] = q.x; out[2 * N + n] = q.y; out[3 * N + n] = q.z;
+    return;
+  }
   const double m00 = R.m[0][0], m01 = R.m[0][1], m02 = R.m[0][2], m10 = R.m[1][0], m11 = R.m[1][1], m12 = R.m[1][2],
                m20 = R.m[2][0], m21 = R.m[2][1], m22 = R.m[2][2];
   const double tr1 = 1.0 + m00 - m11 - m22, tr2 = 1.0 - m00 + m11 - m22, tr3 = 1.0 - m00 - m11 + m22;

@@ -199,6 +199,9 @@ class ShardedLongReplay:
         off = self.begin % self.base_n
         reps = (off + self.n_local + self.base_n - 1) // self.base_n
         view = self.buf[: t1 - t0]
+        if off == 0 and self.n_local % self.base_n == 0:      # whole periods: one broadcast copy
+            view.view(t1 - t0, 9, reps, self.base_n).copy_(self.base.streams[t0:t1].unsqueeze(2).expand(-1, -1, reps, -1))
+            return view
         for k in range(reps):       # copy period by period: no [tc, 9, reps*base_n] temporary
             lo = max(k * self.base_n, off) - off
             hi = min((k + 1) * self.base_n, off + self.n_local) - off
