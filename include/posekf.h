@@ -91,8 +91,12 @@ const char* posekf_version(void);
  *               carried as two floats (state_x + state_x_lo) so that corrections below half an ulp of the
  *               state are not lost (R >> Q: 2.4e-5 rad from the reference after 5000 steps at Q=1e-3,
  *               R=1e3 otherwise), and the gain is formed by Sherman-Morrison with the process noise kept
- *               apart from A K A^T (Q >> R: 1.3e-5 rad spikes at Q=1e3, R=1e-3 otherwise).  <= 3e-7 rad over
- *               the whole 1e-3..1e3 grid; costs ~17 % more time.  Start at 0.
+ *               apart from A K A^T (Q >> R: 1.7e-5 rad spikes at Q=1e3, R=1e-3 otherwise).  <= 3.5e-7 rad over
+ *               the whole 1e-3..1e3 grid; costs ~25 % more time.  Start at 0.
+ *               VALIDITY OF THE PLAIN VARIANT (NULL): 1e-2 < q/r < 1e4 for every filter.  Outside that range it
+ *               leaves the 1e-5 rad tolerance -- quickly for r >> q, where the diagonal of its gain, formed as
+ *               1 - 1/d, cancels (3e-3 rad at q/r = 1e-6).  Device pointers cannot be checked here: the Python layer
+ *               selects the variant from the values and refuses the plain one outside its range.
  *   state_p     [10][N] in/out: upper triangle of P / r  (the covariance IN UNITS OF THE FILTER'S r; after
  *               an update this equals the Kalman gain) in the order 00 01 02 03 11 12 13 22 23 33.
  *               The kernel works in this scaled form, so storing it unscaled would make a chunked
