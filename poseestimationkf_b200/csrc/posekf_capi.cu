@@ -499,6 +499,10 @@ int posekf_measurement_stream_f32(int64_t n_streams, int64_t n_steps, const floa
   if (wahba_algo == POSEKF_WAHBA_QR2) measurement_stream_kernel<WAHBA_QR2><<<grid, 128, 0, st>>>(p);
   else if (wahba_algo == POSEKF_WAHBA_JACOBI) measurement_stream_kernel<WAHBA_JACOBI><<<grid, 128, 0, st>>>(p);
   else return POSEKF_EINVAL;
+  if (int rc = launch_status()) return rc;
+  if (!sequential && streams != out_streams) {     // float32 ties of the reference's sign rule, re-decided in float64
+    meas_fixup_kernel<<<blocks_for(n_streams * n_steps, 256), 256, 0, st>>>(p);
+  }
   return launch_status();
 }
 

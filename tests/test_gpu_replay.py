@@ -424,7 +424,11 @@ def test_precomputed_measurement_stream_sweep(cuda):
     meas, _ = B.measurement_stream(imu.streams, imu.acc_ref, imu.mag_ref)
     assert torch.equal(meas[:, 0:3], imu.streams[:, 0:3]) and (meas[:, 7:9] == 0).all()
     _, wah, _ = B.tracks(imu.streams, imu.acc_ref, imu.mag_ref, dt=imu.dt, weights_from_acc=True, want_gyro=False)
-    assert torch.equal(meas[:, 3:7].permute(0, 2, 1), wah)               # rows 3-6 ARE the Wahba-only track
+    # rows 3-6 ARE the Wahba-only track -- except that the stream's sign rule is re-decided in float64 on float32 ties
+    # (meas_fixup_kernel), which may negate a sample or two of the 76 800
+    mq = meas[:, 3:7].permute(0, 2, 1)
+    same, negated = (mq == wah).all(dim=-1), (mq == -wah).all(dim=-1)
+    assert bool((same | negated).all()) and int((~same).sum()) <= 2
     outs = []
     for staging in ("ldg", "tma", "tma_packed"):
         st, traj, fl = B.replay(meas, imu.acc_ref, imu.mag_ref, dt=imu.dt, q=q_t, r=r_t, n_filters=G * Ns, wahba="precomputed",
