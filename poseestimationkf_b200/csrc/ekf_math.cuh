@@ -310,18 +310,27 @@ template <typename F> PKF_HD Quat<F> rk4_increment(const Quat<F>& q, const Vec3<
   return inc;
 }
 
+// The time step of one sample with the two products of it that the RK4 polynomial needs.  They are launch constants
+// when dt is (the usual case), so the kernels form them once, outside the time loop, instead of twice per step.
+template <typename F> struct StepH {
+  F h, hh, mh6;       // h, h^2, -h/6
+  PKF_HD StepH() {}
+  PKF_HD StepH(F h_) : h(h_), hh(h_ * h_), mh6(h_ * F(-1.0 / 6.0)) {}
+  PKF_HD StepH(F h_, F hh_, F mh6_) : h(h_), hh(hh_), mh6(mh6_) {}
+};
+
 // Plain-variant form: the predicted state z = x + (c0 - 1) x + c1 (A x) accumulated by FMAs onto x (8 operations
 // instead of 4 MUL + 4 FMA + 4 ADD); the state is rounded twice per component instead of once (~1 ulp per step,
 // contracted by the filter's own gain; the precise variant keeps the increment apart, see ekf_update).
-template <typename F> PKF_HD Quat<F> rk4_predict_fused(const Quat<F>& q, const Vec3<F>& hw, F h) {
+template <typename F> PKF_HD Quat<F> rk4_predict_fused(const Quat<F>& q, const Vec3<F>& hw, const StepH<F>& st) {
   Quat<F> u;   // u = A q
   u.w = fma_(-hw.z, q.z, fma_(-hw.y, q.y, -(hw.x * q.x)));
   u.x = fma_(-hw.y, q.z, fma_(hw.z, q.y, hw.x * q.w));
   u.y = fma_(hw.x, q.z, fma_(-hw.z, q.x, hw.y * q.w));
   u.z = fma_(-hw.x, q.y, fma_(hw.y, q.x, hw.z * q.w));
-  F a2 = (h * h) * dot3(hw, hw);
+  F a2 = st.hh * dot3(hw, hw);
   F cm = a2 * fma_(a2, F(1.0 / 24.0), F(-0.5));            // c0 - 1
-  F c1 = h * fma_(a2, F(-1.0 / 6.0), F(1));
+  F c1 = fma_(a2, st.mh6, st.h);                            // h (1 - a2/6)
   Quat<F> z;
   z.w = fma_(cm, q.w, fma_(c1, u.w, q.w));
   z.x = fma_(cm, q.x, fma_(c1, u.x, q.x));
@@ -1056,7 +1065,7 @@ PKF_HD void quat_fallback_unaligned(const Mat3<f32x2>& Rm, const Quat<f32x2>& z,
 // Prediction (PKF/ExtendedKalmanFilter.py:58-68): gain K (= the post-update covariance in units of r), RK4
 // increment inc and predicted state z = x + inc.
 template <typename F, bool COMP>
-PKF_HD void ekf_predict(const Quat<F>& x, const Sym4<F>& P, const FilterConst<F>& fc, const Vec3<F>& gyro, F h,
+PKF_HD void ekf_predict(const Quat<F>& x, const Sym4<F>& P, const FilterConst<F>& fc, const Vec3<F>& gyro, const StepH<F>& h,
                         Sym4<F>& K, Quat<F>& inc, Quat<F>& z) {
   Vec3<F> hw;
   hw.x = F(0.5) * gyro.x; hw.y = F(0.5) * gyro.y; hw.z = F(0.5) * gyro.z;
@@ -1075,7 +1084,7 @@ PKF_HD void ekf_predict(const Quat<F>& x, const Sym4<F>& P, const FilterConst<F>
     K = kalman_gain_unit(Pp);                                                 // :63-66
 #endif
   }
-  inc = rk4_increment(x, hw, h);                                              // :62
+  inc = rk4_increment(x, hw, h.h);                                            // :62
   z.w = x.w + inc.w; z.x = x.x + inc.x; z.y = x.y + inc.y; z.z = x.z + inc.z;   // |z| = 1 to rounding
 }
 
@@ -1154,7 +1163,7 @@ PKF_HD Quat<F> measure_quat(const FilterConst<F>& fc, const Vec3<F>& acc, const 
 // Prediction + Correction with the measurement quaternion y (filter frame, any sign, norm 1/inv_norm) already computed.
 template <typename F, bool WANT_FLIP, bool COMP, typename FlagT>
 PKF_HD void ekf_step_measured(Quat<F>& x, Quat<F>& xlo, Sym4<F>& P, FilterConst<F>& fc, const Vec3<F>& gyro,
-                              const Quat<F>& y, F inv_norm, F h, FlagT& flip, bool flip_wanted = true,
+                              const Quat<F>& y, F inv_norm, const StepH<F>& h, FlagT& flip, bool flip_wanted = true,
                               typename FlipCodeOf<F>::type* code = nullptr) {
   Sym4<F> K;
   Quat<F> inc, z;
@@ -1172,7 +1181,7 @@ PKF_HD void ekf_step_measured(Quat<F>& x, Quat<F>& xlo, Sym4<F>& P, FilterConst<
 // guarantees the precondition (the packed kernel checks a whole tile of samples before taking this path).
 template <typename F, bool WANT_FLIP, bool COMP, typename FlagT>
 PKF_HD void ekf_step_plain_measured(Quat<F>& x, Quat<F>& xlo, Sym4<F>& P, FilterConst<F>& fc, const Vec3<F>& gyro,
-                                    const Vec3<F>& acc, const Vec3<F>& mag, F h, FlagT& flip, bool flip_wanted = true,
+                                    const Vec3<F>& acc, const Vec3<F>& mag, const StepH<F>& h, FlagT& flip, bool flip_wanted = true,
                                     typename FlipCodeOf<F>::type* code = nullptr) {
   const F ka = abs_(acc.z), km = F(1) - ka;
   F inv_norm;
@@ -1182,7 +1191,7 @@ PKF_HD void ekf_step_plain_measured(Quat<F>& x, Quat<F>& xlo, Sym4<F>& P, Filter
 
 template <typename F, int ALGO, bool WANT_FLIP, bool COMP, typename FlagT>
 PKF_HD void ekf_step(Quat<F>& x, Quat<F>& xlo, Sym4<F>& P, FilterConst<F>& fc, const Vec3<F>& gyro,
-                     const Vec3<F>& acc, const Vec3<F>& mag, F h, FlagT& flip, bool flip_wanted = true,
+                     const Vec3<F>& acc, const Vec3<F>& mag, const StepH<F>& h, FlagT& flip, bool flip_wanted = true,
                      typename FlipCodeOf<F>::type* code = nullptr) {
   // flip_wanted: launch-uniform run-time switch under WANT_FLIP -- a launch that stores the trajectory but
   // not the flip mask skips the reference's branch rule altogether

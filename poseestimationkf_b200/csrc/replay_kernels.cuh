@@ -107,7 +107,7 @@ __device__ __forceinline__ void filter_step(const ReplayParams& p, FilterRegs& f
   // flip-mask byte: the float32 decision, plus the tie marker and per-branch alternatives that flip_fixup_kernel settles
   // in float64 after the launch (raw samples only: a low-passed sample is not in the stream any more)
   unsigned code = 0;
-  ekf_step<float, ALGO, AUX, COMP>(f.x, f.xlo, f.P, f.fc, w, a, m, h, flip, aux.flips != nullptr,
+  ekf_step<float, ALGO, AUX, COMP>(f.x, f.xlo, f.P, f.fc, w, a, m, StepH<float>(h), flip, aux.flips != nullptr,
                                    (AUX && !LPF && ALGO == WAHBA_QR2) ? &code : nullptr);
   if (!(AUX && !LPF && ALGO == WAHBA_QR2)) code = flip ? 1u : 0u;
   if (AUX) {
@@ -322,6 +322,7 @@ __global__ void __launch_bounds__(kThreads2, (AUX && COMP) ? (PKF_MIN_CTAS2 > 4 
     if (uses_filter_frame<ALGO>() && !(p.state_flags & kStateInFilterFrame)) enter_filter_frame(f.fc, f.x, f.xlo, f.P, COMP);
   }
   const float dt0 = p.dt[0];
+  const StepH<f32x2> sh0{f32x2(dt0), f32x2(dt0 * dt0), f32x2(dt0 * (-1.f / 6.f))};
   // auxiliary outputs: this thread's pair of adjacent slots
   float4* traj = nullptr;
   uint8_t* flips = nullptr;
@@ -358,7 +359,8 @@ __global__ void __launch_bounds__(kThreads2, (AUX && COMP) ? (PKF_MIN_CTAS2 > 4 
         f32x2 s[kChannels];
 #pragma unroll
         for (int c = 0; c < kChannels; ++c) s[c] = ld2(&sm.tile[stage][tt][c][2 * tid]);
-        const float h = p.dt_per_step ? __ldg(p.dt + k * kTma2Steps + tt) : dt0;
+        StepH<f32x2> sh = sh0;                         // launch constant (the fast path runs only then) ...
+        if (!FAST && p.dt_per_step) sh = StepH<f32x2>(f32x2(__ldg(p.dt + k * kTma2Steps + tt)));     // ... unless dt comes per step
         Vec3<f32x2> w = {s[0], s[1], s[2]}, a = {s[3], s[4], s[5]}, m = {s[6], s[7], s[8]};
         if (LPF) {
           if (p.alpha_acc >= 0.f) { lowpass<f32x2>(f.la, a, f32x2(p.alpha_acc), f32x2(1.f - p.alpha_acc)); a = f.la; }
@@ -367,9 +369,9 @@ __global__ void __launch_bounds__(kThreads2, (AUX && COMP) ? (PKF_MIN_CTAS2 > 4 
         mask2 flip;
         constexpr bool kTieCode = AUX && !LPF && ALGO == WAHBA_QR2;     // see filter_step
         FlipCode2 code = {0u, 0u};
-        if constexpr (FAST) ekf_step_plain_measured<f32x2, AUX, COMP>(f.x, f.xlo, f.P, f.fc, w, a, m, f32x2(h), flip, flips != nullptr,
+        if constexpr (FAST) ekf_step_plain_measured<f32x2, AUX, COMP>(f.x, f.xlo, f.P, f.fc, w, a, m, sh, flip, flips != nullptr,
                                                                       kTieCode ? &code : nullptr);
-        else ekf_step<f32x2, ALGO, AUX, COMP>(f.x, f.xlo, f.P, f.fc, w, a, m, f32x2(h), flip, flips != nullptr, kTieCode ? &code : nullptr);
+        else ekf_step<f32x2, ALGO, AUX, COMP>(f.x, f.xlo, f.P, f.fc, w, a, m, sh, flip, flips != nullptr, kTieCode ? &code : nullptr);
         if (!kTieCode) code = FlipCode2{flip.x ? 1u : 0u, flip.y ? 1u : 0u};
         if (AUX) {
           Quat<f32x2> xr = f.x;     // per-step outputs are in the reference frame
@@ -395,7 +397,7 @@ __global__ void __launch_bounds__(kThreads2, (AUX && COMP) ? (PKF_MIN_CTAS2 > 4 
       };
       bool fast = false;
       if constexpr (ALGO == WAHBA_QR2 && !LPF && PKF_FAST_TILE) {
-        if (steps == kTma2Steps) {
+        if (steps == kTma2Steps && !p.dt_per_step) {
           // |a_z| <= 1 for every sample of the tile (both lanes): the accelerometer weight 1 - |a_z| is non-negative
           float az = 0.f;
 #pragma unroll

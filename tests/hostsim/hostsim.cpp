@@ -37,7 +37,7 @@ static void replay_t(int64_t N, int64_t T, const float* streams, const double* d
       if (lpf_mag >= 0.f) { lowpass<F>(lm, m, (F)lpf_mag, F(1) - (F)lpf_mag); m = lm; }
       F h = (F)(dt_per_step ? dt[t] : dt[0]);
       bool flip;
-      ekf_step<F, ALGO, true, COMP>(x, xlo, P, fc, w, a, m, h, flip);
+      ekf_step<F, ALGO, true, COMP>(x, xlo, P, fc, w, a, m, StepH<F>(h), flip);
       if (out_traj) {
         const Quat<F> xr = state_in_reference_frame(fc, x);
         double* o = out_traj + (size_t)t * 4 * N + n;
@@ -78,7 +78,7 @@ static void replay_packed_t(int64_t N, int64_t T, const float* streams, const do
       if (lpf_mag >= 0.f) { lowpass<F>(lm, m, F(lpf_mag), F(1.f - lpf_mag)); m = lm; }
       F h = F((float)(dt_per_step ? dt[t] : dt[0]));
       mask2 flip;
-      ekf_step<F, WAHBA_QR2, true, COMP>(x, xlo, P, fc, w, a, m, h, flip);
+      ekf_step<F, WAHBA_QR2, true, COMP>(x, xlo, P, fc, w, a, m, StepH<F>(h), flip);
       if (out_flip) { out_flip[(size_t)t * N + n] = flip.x; out_flip[(size_t)t * N + n + 1] = flip.y; }
       if (out_traj) {
         const Quat<F> xr = state_in_reference_frame(fc, x);
