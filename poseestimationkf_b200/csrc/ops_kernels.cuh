@@ -369,6 +369,39 @@ __global__ void __launch_bounds__(256, PKF_WAHBA2_MIN_CTAS) wahba2_kernel(const 
   }
 }
 
+// Packed form of the Wahba-only comparison track (tracks_kernel's second output): two filters per thread in f32x2
+// lanes, one thread walks its pair of filters through time with the next step's six 8-byte loads in flight while the
+// current pair of samples is solved and stored as two float4 quaternions.  Same arithmetic per sample as
+// tracks_kernel<WAHBA_QR2> (bit-identical results); needs N even, Ns == N and 8-byte aligned rows.
+__global__ void __launch_bounds__(128) tracks_wahba2_kernel(const TracksParams p) {
+  const int64_t n = 2 * ((int64_t)blockIdx.x * blockDim.x + threadIdx.x);
+  if (n >= p.N) return;
+  const int64_t N = p.N;
+  const Vec3<f32x2> ra = {ld2(p.acc_ref + n), ld2(p.acc_ref + N + n), ld2(p.acc_ref + 2 * N + n)};
+  const Vec3<f32x2> rm = {ld2(p.mag_ref + n), ld2(p.mag_ref + N + n), ld2(p.mag_ref + 2 * N + n)};
+  const RefFrame<f32x2> E = frame_from_pair<f32x2>(ra, rm);
+  float4* ow = reinterpret_cast<float4*>(p.out_wahba) + n;
+  const float* s = p.streams + n;
+  f32x2 cur[6], nxt[6];
+  auto load_step = [&](f32x2 (&v)[6], const float* q) {
+#pragma unroll
+    for (int c = 0; c < 6; ++c) v[c] = ld2_stream(q + (3 + c) * N);
+  };
+  if (p.T > 0) load_step(cur, s);
+  for (int64_t t = 0; t < p.T; ++t, s += kChannels * N) {
+    if (t + 1 < p.T) load_step(nxt, s + kChannels * N);
+    const Vec3<f32x2> a = {cur[0], cur[1], cur[2]}, m = {cur[3], cur[4], cur[5]};
+    f32x2 ka(p.k_acc), km(p.k_mag);
+    if (p.weights_from_acc) { ka = abs_<f32x2>(a.z); km = f32x2(1.f) - ka; }
+    const Quat<f32x2> q = rotation_to_quat_ref<f32x2>(wahba_qr2<f32x2>(E, a, m, ka, km));
+    stg_stream4(ow, q.w.x, q.x.x, q.y.x, q.z.x);
+    stg_stream4(ow + 1, q.w.y, q.x.y, q.y.y, q.z.y);
+    ow += N;
+#pragma unroll
+    for (int c = 0; c < 6; ++c) cur[c] = nxt[c];
+  }
+}
+
 __global__ void __launch_bounds__(256) rot2quat_kernel(int64_t N, const float* __restrict__ rot, float* __restrict__ out) {
   const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= N) return;

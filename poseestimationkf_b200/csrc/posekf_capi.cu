@@ -454,6 +454,17 @@ int posekf_tracks_f32(int64_t n_filters, int64_t n_steps, const float* streams, 
   TracksParams p{n_filters, n_steps, n_streams, streams, dt, dt_per_step, acc_ref ? acc_ref : streams,
                  mag_ref ? mag_ref : streams, k_acc, k_mag, weights_from_acc, gyro_state, out_gyro, out_wahba};
   cudaStream_t st = (cudaStream_t)stream;
+  // the Wahba-only track does not depend on its predecessors: with one stream per filter it runs packed (two filters
+  // per thread), and the sequential kernel keeps the gyro-only track
+  const bool packed_wahba = out_wahba && wahba_algo == POSEKF_WAHBA_QR2 && n_streams == n_filters && (n_filters & 1) == 0 &&
+                            ((reinterpret_cast<uintptr_t>(streams) | reinterpret_cast<uintptr_t>(acc_ref) |
+                              reinterpret_cast<uintptr_t>(mag_ref)) & 7) == 0;
+  if (packed_wahba) {
+    tracks_wahba2_kernel<<<blocks_for(n_filters / 2, 128), 128, 0, st>>>(p);
+    if (int rc = launch_status()) return rc;
+    if (!out_gyro && !gyro_state) return 0;
+    p.out_wahba = nullptr;
+  }
   if (wahba_algo == POSEKF_WAHBA_QR2) tracks_kernel<WAHBA_QR2><<<blocks_for(n_filters, 128), 128, 0, st>>>(p);
   else if (wahba_algo == POSEKF_WAHBA_JACOBI) tracks_kernel<WAHBA_JACOBI><<<blocks_for(n_filters, 128), 128, 0, st>>>(p);
   else return POSEKF_EINVAL;

@@ -189,6 +189,15 @@ def test_comparison_tracks_and_tuning_objective(cuda):
             got = wah[t, n].cpu().numpy()
             assert O.quat_angle(got, yw) < 2e-6 and np.dot(got, yw) > 0       # same raw sign convention
     assert torch.equal(gstate.t().contiguous(), gyro[-1])
+    # the Wahba-only track runs packed (two filters per thread) for even N and scalar otherwise: same bits; weights from the
+    # accelerometer and the Wahba-only call go through the same kernels
+    for kw in (dict(), dict(weights_from_acc=True)):
+        _, w_even, _ = B.tracks(imu.streams, imu.acc_ref, imu.mag_ref, dt=imu.dt, want_gyro=False, **kw)
+        _, w_odd, _ = B.tracks(imu.streams[:, :, :255].contiguous(), imu.acc_ref[:, :255].contiguous(), imu.mag_ref[:, :255].contiguous(),
+                               dt=imu.dt, want_gyro=False, **kw)
+        assert torch.equal(w_even[:, :255], w_odd)
+        if not kw:
+            assert torch.equal(w_even, wah)
     # chunked gyro track carries its state
     g1, _, st = B.tracks(imu.streams[:77].contiguous(), imu.acc_ref, imu.mag_ref, dt=imu.dt, want_wahba=False)
     g2, _, _ = B.tracks(imu.streams[77:].contiguous(), imu.acc_ref, imu.mag_ref, dt=imu.dt, want_wahba=False, gyro_state=st)
