@@ -382,14 +382,18 @@ __global__ void __launch_bounds__(128) tracks_wahba2_kernel(const TracksParams p
   const RefFrame<f32x2> E = frame_from_pair<f32x2>(ra, rm);
   float4* ow = reinterpret_cast<float4*>(p.out_wahba) + n;
   const float* s = p.streams + n;
-  f32x2 cur[6], nxt[6];
+  // TWO steps ahead in flight (96 B per thread): one thread walks its filters through time, so the memory-level
+  // parallelism has to come from the depth of its own prefetch
+  f32x2 cur[6], nx1[6], nx2[6];
   auto load_step = [&](f32x2 (&v)[6], const float* q) {
 #pragma unroll
     for (int c = 0; c < 6; ++c) v[c] = ld2_stream(q + (3 + c) * N);
   };
+  const int64_t step = kChannels * N;
   if (p.T > 0) load_step(cur, s);
-  for (int64_t t = 0; t < p.T; ++t, s += kChannels * N) {
-    if (t + 1 < p.T) load_step(nxt, s + kChannels * N);
+  if (p.T > 1) load_step(nx1, s + step);
+  for (int64_t t = 0; t < p.T; ++t, s += step) {
+    if (t + 2 < p.T) load_step(nx2, s + 2 * step);
     const Vec3<f32x2> a = {cur[0], cur[1], cur[2]}, m = {cur[3], cur[4], cur[5]};
     f32x2 ka(p.k_acc), km(p.k_mag);
     if (p.weights_from_acc) { ka = abs_<f32x2>(a.z); km = f32x2(1.f) - ka; }
@@ -398,7 +402,7 @@ __global__ void __launch_bounds__(128) tracks_wahba2_kernel(const TracksParams p
     stg_stream4(ow + 1, q.w.y, q.x.y, q.y.y, q.z.y);
     ow += N;
 #pragma unroll
-    for (int c = 0; c < 6; ++c) cur[c] = nxt[c];
+    for (int c = 0; c < 6; ++c) { cur[c] = nx1[c]; nx1[c] = nx2[c]; }
   }
 }
 

@@ -369,8 +369,8 @@ __global__ void __launch_bounds__(kThreads2, (AUX && COMP) ? (PKF_MIN_CTAS2 > 4 
         mask2 flip;
         constexpr bool kTieCode = AUX && !LPF && ALGO == WAHBA_QR2;     // see filter_step
         FlipCode2 code = {0u, 0u};
-        if constexpr (FAST) ekf_step_plain_measured<f32x2, AUX, COMP>(f.x, f.xlo, f.P, f.fc, w, a, m, sh, flip, flips != nullptr,
-                                                                      kTieCode ? &code : nullptr);
+        if constexpr (FAST && ALGO == WAHBA_QR2) ekf_step_plain_measured<f32x2, AUX, COMP>(f.x, f.xlo, f.P, f.fc, w, a, m, sh, flip, flips != nullptr,
+                                                                                            kTieCode ? &code : nullptr);
         else ekf_step<f32x2, ALGO, AUX, COMP>(f.x, f.xlo, f.P, f.fc, w, a, m, sh, flip, flips != nullptr, kTieCode ? &code : nullptr);
         if (!kTieCode) code = FlipCode2{flip.x ? 1u : 0u, flip.y ? 1u : 0u};
         if (AUX) {
@@ -396,6 +396,7 @@ __global__ void __launch_bounds__(kThreads2, (AUX && COMP) ? (PKF_MIN_CTAS2 > 4 
         }
       };
       bool fast = false;
+      if constexpr (ALGO == WAHBA_PRECOMPUTED && PKF_FAST_TILE) fast = steps == kTma2Steps && !p.dt_per_step;   // no branch in that step at all
       if constexpr (ALGO == WAHBA_QR2 && !LPF && PKF_FAST_TILE) {
         if (steps == kTma2Steps && !p.dt_per_step) {
           // |a_z| <= 1 for every sample of the tile (both lanes): the accelerometer weight 1 - |a_z| is non-negative
