@@ -485,7 +485,7 @@ def wahba(acc_ref, mag_ref, acc, mag, *, k_acc=None, k_mag=None, weights_from_ac
 def tracks(streams, acc_ref, mag_ref, *, dt, n_filters=None, k_acc=0.5, k_mag=0.5, weights_from_acc=False,
            gyro_state=None, want_gyro=True, want_wahba=True, algo: str = "qr2"):
     """Gyro-only and Wahba-only comparison tracks (the curves main_file.py plots beside the filter).
-    Returns (gyro [T,N,4] or None, wahba [T,N,4] or None, gyro_state [4,N])."""
+    Returns (gyro [T,N,4] or None, wahba [T,N,4] or None, gyro_state [4,N] -- None for a Wahba-only call without a state)."""
     _require_cuda(streams, acc_ref, mag_ref, gyro_state)
     T, _, Ns = streams.shape
     N = Ns if n_filters is None else int(n_filters)
@@ -495,7 +495,7 @@ def tracks(streams, acc_ref, mag_ref, *, dt, n_filters=None, k_acc=0.5, k_mag=0.
         dt_t, per_step = dt, 1
     else:
         dt_t, per_step = _scalar_tensor(dt, dev), 0
-    if gyro_state is None:
+    if gyro_state is None and want_gyro:      # (a Wahba-only call integrates nothing)
         gyro_state = torch.zeros((4, N), dtype=torch.float32, device=dev)
         gyro_state[0] = 1.0
     og = torch.empty((T, N, 4), dtype=torch.float32, device=dev) if want_gyro else None

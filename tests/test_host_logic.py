@@ -211,3 +211,30 @@ def test_sharded_long_replay_tiles_the_right_columns():
             if world == 5:
                 cover.append((job.begin, job.end))
     assert cover[0][0] == 0 and cover[-1][1] == N and all(a[1] == b[0] for a, b in zip(cover, cover[1:]))
+
+
+def test_bench_workload_selection_and_evidence_stamps():
+    """bench.py host logic: the default workload per GPU count (config 2 on one GPU, the sharded config 5 on 2+), the
+    executed-arithmetic figures come from the committed opcode census, and the ncu capture whose DRAM traffic the line
+    quotes is stamped with the hash of the device sources it was taken from."""
+    import argparse
+    import json
+    import bench
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    a = argparse.Namespace(workload="auto", filters=None, timesteps=None)
+    assert bench.resolve_workload(a, 1) == ("c2", 1 << 20, 1000)
+    assert bench.resolve_workload(a, 2) == ("c5", 1 << 24, 2000) and bench.resolve_workload(a, 8)[0] == "c5"
+    a.workload, a.filters = "c2", 4096
+    assert bench.resolve_workload(a, 8) == ("c2", 4096, 1000)
+    assert "configs[4]" in bench.workload_text("c5", 8, 1 << 24, 2000) and "configs[1]" in bench.workload_text("c2", 1, 1 << 20, 1000)
+    flops, lane_ops, src = bench.executed_arithmetic("qr2")
+    census = json.load(open(os.path.join(root, "profiles", "r02_replay_packed_opcode_census.json")))
+    assert flops == census["flops_per_filter_step_executed"] and src.endswith("r02_replay_packed_opcode_census.json")
+    assert 200 < lane_ops < 260 and 300 < flops < 400
+    sha = bench.kernel_source_sha()
+    assert len(sha) == 16 and sha == bench.kernel_source_sha()
+    prof = json.load(open(os.path.join(root, "profiles", "r02_replay_packed_ncu_full.json")))
+    assert len(prof["kernel_source_sha"]) == 16 and prof["dram_traffic_over_algorithmic"] < 1.1
+    assert prof["kernel_source_sha"] == sha, "profiles/r02_replay_packed_ncu_full.json was captured from other device sources: re-profile"
+    ref = bench.find_reference()
+    assert ref is None or os.path.exists(os.path.join(ref, "ExtendedKalmanFilter.py"))
