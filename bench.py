@@ -566,6 +566,9 @@ def run_c2(ctx, args):
         return None
     packed = args.staging in ("auto", "tma_packed") and args.wahba == "qr2" and N % 4 == 0
     roofline = build_roofline(ctx, args, steps_per_s_kernel, avg_kernel_ms, fp32_peak, clocks, N * T, packed)
+    # every pass's own device time: a drift across the K passes is the power / thermal state of the box, not the kernel
+    roofline["kernel_ms_per_pass"] = [round(v, 3) for v in kernel_ms]
+    roofline["best_pass_steps_per_s"] = N * T / (min(kernel_ms) * 1e-3)
     return {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": ctx.world, "steps": K, "warmup": W,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

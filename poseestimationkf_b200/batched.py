@@ -13,6 +13,7 @@ per-filter `[N, k]` / `[N, 4, 4]` shapes.
 """
 from __future__ import annotations
 
+import weakref
 from dataclasses import dataclass
 
 import torch
@@ -176,20 +177,29 @@ def _scales_need_precise(q, r) -> bool:
         if not rf > 0.0 or not qf >= 0.0:
             raise ValueError("r must be > 0 and q >= 0 (the kernel carries the covariance in units of r)")
         return rf >= 100.0 * qf or qf >= 1.0e4 * rf
-    key = tuple((id(t), t._version, t.data_ptr()) if isinstance(t, torch.Tensor) else float(t) for t in (q, r))
+    # cache entry: weak references to the very tensor objects (an id alone can be recycled by a new tensor after the old
+    # one is freed) and their version counters (bumped by any in-place write, also through views)
+    key = tuple(id(t) if isinstance(t, torch.Tensor) else float(t) for t in (q, r))
     hit = _checked_scales.get(key)
-    if hit is None:
-        qt = q if isinstance(q, torch.Tensor) else torch.full((1,), float(q), dtype=torch.float32, device=r.device)
-        rt = r if isinstance(r, torch.Tensor) else torch.full((1,), float(r), dtype=torch.float32, device=q.device)
-        bad = ~(rt > 0) | ~(qt >= 0)
-        need = (rt >= 100.0 * qt) | (qt >= 1.0e4 * rt)
-        flags = torch.stack((bad.any(), need.any())).tolist()
-        if flags[0]:
-            raise ValueError("every r must be > 0 and every q >= 0 (the kernel carries the covariance in units of r)")
-        if len(_checked_scales) > 64:
-            _checked_scales.clear()
-        hit = _checked_scales[key] = bool(flags[1])
-    return hit
+    if hit is not None:
+        refs, versions, flag = hit
+        same = all((ref is None and not isinstance(t, torch.Tensor)) or (ref is not None and ref() is t and t._version == ver)
+                   for t, ref, ver in zip((q, r), refs, versions))
+        if same:
+            return flag
+    qt = q if isinstance(q, torch.Tensor) else torch.full((1,), float(q), dtype=torch.float32, device=r.device)
+    rt = r if isinstance(r, torch.Tensor) else torch.full((1,), float(r), dtype=torch.float32, device=q.device)
+    bad = ~(rt > 0) | ~(qt >= 0)
+    need = (rt >= 100.0 * qt) | (qt >= 1.0e4 * rt)
+    flags = torch.stack((bad.any(), need.any())).tolist()
+    if flags[0]:
+        raise ValueError("every r must be > 0 and every q >= 0 (the kernel carries the covariance in units of r)")
+    if len(_checked_scales) > 64:
+        _checked_scales.clear()
+    refs = tuple(weakref.ref(t) if isinstance(t, torch.Tensor) else None for t in (q, r))
+    versions = tuple(t._version if isinstance(t, torch.Tensor) else 0 for t in (q, r))
+    _checked_scales[key] = (refs, versions, bool(flags[1]))
+    return bool(flags[1])
 
 
 def _per_filter(v, n, device):

@@ -238,3 +238,29 @@ def test_bench_workload_selection_and_evidence_stamps():
     assert prof["kernel_source_sha"] == sha, "profiles/r02_replay_packed_ncu_full.json was captured from other device sources: re-profile"
     ref = bench.find_reference()
     assert ref is None or os.path.exists(os.path.join(ref, "ExtendedKalmanFilter.py"))
+
+
+def test_scale_validation_and_precision_rule_cache():
+    """batched._scales_need_precise: validates r > 0, q >= 0 and answers whether any filter needs the precise variant
+    (r/q >= 100 or q/r >= 1e4) with one reduction per (q, r) tensor pair; the cached answer must follow in-place writes
+    (version counter) and must not survive the tensors themselves (ids are recycled)."""
+    q, r = torch.ones(8), torch.full((8,), 0.1)
+    assert B._scales_need_precise(q, r) is False and B._scales_need_precise(q, r) is False
+    r[3] = 500.0                                    # in-place write: the cached answer is stale
+    assert B._scales_need_precise(q, r) is True
+    q[5] = 1e5
+    r[3] = 0.1
+    assert B._scales_need_precise(q, r) is True     # q/r = 1e6 on filter 5
+    for _ in range(4):                              # fresh tensors that may reuse the ids / storage of freed ones
+        q2, r2 = torch.ones(8), torch.full((8,), 0.1)
+        assert B._scales_need_precise(q2, r2) is False
+        q3, r3 = torch.ones(8), torch.full((8,), 1000.0)
+        assert B._scales_need_precise(q3, r3) is True
+        del q2, r2, q3, r3
+    for bad_q, bad_r in ((torch.ones(4), torch.zeros(4)), (-torch.ones(4), torch.ones(4)), (torch.ones(4), torch.tensor([1.0, float("nan"), 1.0, 1.0]))):
+        with pytest.raises(ValueError):
+            B._scales_need_precise(bad_q, bad_r)
+    assert B._scales_need_precise(1.0, 0.1) is False and B._scales_need_precise(1e-3, 1e3) is True and B._scales_need_precise(1e3, 1e-3) is True
+    with pytest.raises(ValueError):
+        B._scales_need_precise(1.0, 0.0)
+    assert B._scales_need_precise(2.0, torch.full((4,), 0.5)) is False      # mixed scalar / tensor
