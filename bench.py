@@ -287,13 +287,24 @@ class ClockSampler:
 
 
 def host_memory_available() -> int:
+    """Bytes this process may still take: MemAvailable, capped by the container's cgroup limit minus its usage."""
+    avail = 0
     try:
         for line in open("/proc/meminfo"):
             if line.startswith("MemAvailable:"):
-                return int(line.split()[1]) * 1024
+                avail = int(line.split()[1]) * 1024
     except Exception:
         pass
-    return 0
+    for lim_f, use_f in (("/sys/fs/cgroup/memory.max", "/sys/fs/cgroup/memory.current"),
+                         ("/sys/fs/cgroup/memory/memory.limit_in_bytes", "/sys/fs/cgroup/memory/memory.usage_in_bytes")):
+        try:
+            lim = open(lim_f).read().strip()
+            if lim != "max" and int(lim) < (1 << 60):
+                left = int(lim) - int(open(use_f).read().strip())
+                avail = min(avail, left) if avail else left
+        except Exception:
+            pass
+    return max(avail, 0)
 
 
 # ------------------------------------------------------------------------------------------------
