@@ -173,7 +173,7 @@ class ShardedLongReplay:
     a sharded replay can be compared with a single-GPU one.  `chunk_bytes` bounds the device buffer of one window."""
 
     def __init__(self, device, rank: int = 0, world: int = 1, n_filters: int = C5_FILTERS, n_steps: int = C5_STEPS,
-                 base_n: int = 1 << 14, seed: int = 8, chunk_bytes: int = 16 << 30, sigma: float = 0.01):
+                 base_n: int = 1 << 14, seed: int = 8, chunk_bytes: int = 32 << 30, sigma: float = 0.01):
         self.device, self.rank, self.world = device, rank, world
         self.N, self.T = n_filters, n_steps
         self.begin, self.end = SH.shard_bounds(n_filters, rank, world)
