@@ -31,11 +31,11 @@ constexpr int kChannels = 9;
 #ifndef PKF_TMA2_STAGES
 #define PKF_TMA2_STAGES 2
 #endif
-#ifndef PKF_MIN_CTAS2
-#define PKF_MIN_CTAS2 6
-#endif
 #ifndef PKF_THREADS2
-#define PKF_THREADS2 64
+#define PKF_THREADS2 128          // 4 warps own a 256-filter tile (64 threads / 128 filters measured 1 % slower, burst and sustained)
+#endif
+#ifndef PKF_MIN_CTAS2
+#define PKF_MIN_CTAS2 (384 / PKF_THREADS2)     // 12 warps per SM: <= 168 registers per thread, 3 x 73.7 KB of tiles
 #endif
 constexpr int kThreads2 = PKF_THREADS2;        // threads per CTA of the packed kernel
 constexpr int kTile2 = 2 * kThreads2;          // filters per CTA (two per thread); TMA box width, <= 256

@@ -271,7 +271,8 @@ struct FilterRegs2 {
 };
 
 template <int ALGO, bool LPF, bool AUX, bool COMP>
-__global__ void __launch_bounds__(kThreads2, (AUX && COMP) ? (PKF_MIN_CTAS2 > 4 ? 4 : PKF_MIN_CTAS2) : ((LPF && COMP) ? (PKF_MIN_CTAS2 > 6 ? 6 : PKF_MIN_CTAS2) : PKF_MIN_CTAS2))
+// (the precise variant with per-step outputs needs ~184 registers: 8 warps per SM instead of 12)
+__global__ void __launch_bounds__(kThreads2, (AUX && COMP) ? ((256 / kThreads2) < PKF_MIN_CTAS2 ? (256 / kThreads2) : PKF_MIN_CTAS2) : PKF_MIN_CTAS2)
     replay_tma2_kernel(const ReplayParams p, const __grid_constant__ CUtensorMap tmap) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   Tma2Smem& sm = *reinterpret_cast<Tma2Smem*>(smem_raw);

@@ -19,6 +19,9 @@ ap.add_argument("--traj", type=int, default=0)
 ap.add_argument("--ns", type=int, default=0, help="distinct trajectories (sweep layout); 0 = one per filter")
 ap.add_argument("--tag", default="")
 ap.add_argument("--base", type=int, default=4096, help="filters in the synthetic batch that is tiled up to --n")
+ap.add_argument("--sustain", type=int, default=0,
+                help="launch this many passes back to back (no idle gaps) and also report the mean of the last half: the rate "
+                     "under the power cap, as the contract bench sees it")
 args = ap.parse_args()
 
 dev = torch.device("cuda:0")
@@ -50,6 +53,19 @@ for var in args.variants.split(","):
             times.append(e0.elapsed_time(e1))
     ms = min(times)
     steps = N * args.t
+    sustained = None
+    if args.sustain:
+        sts = [B.ReplayState.initial(N, dev, r=0.1) for _ in range(args.sustain)]
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.sustain)]
+        torch.cuda.synchronize()
+        for st_, (a, b) in zip(sts, evs):
+            a.record()
+            B.replay(streams, acc_ref, mag_ref, dt=0.01, q=1.0, r=0.1, state=st_, out_traj=traj, wahba=algo, staging=staging, n_filters=N)
+            b.record()
+        torch.cuda.synchronize()
+        per = [a.elapsed_time(b) for a, b in evs]
+        sustained = sum(per[len(per) // 2:]) / (len(per) - len(per) // 2)
     print(json.dumps({"tag": args.tag, "ns": args.ns, "variant": var, "N": N, "T": args.t, "traj": bool(args.traj), "ms": round(ms, 3),
-                      "gsteps_per_s": round(steps / ms / 1e6, 2), "hbm_gbs": round(steps * (36 + 16 * bool(args.traj)) / ms / 1e6, 1),
+                      "gsteps_per_s": round(steps / ms / 1e6, 2),
+                      "sustained_gsteps_per_s": None if sustained is None else round(steps / sustained / 1e6, 2), "hbm_gbs": round(steps * (36 + 16 * bool(args.traj)) / ms / 1e6, 1),
                       "x0": st.x[:, 0].tolist()}))

@@ -8,5 +8,5 @@ mkdir -p gpurun_out
 for so in tools/variants/$GLOB; do
   [ -e "$so" ] || continue
   tag=$(basename $so .so)
-  POSEKF_LIB=$so timeout 300 python tools/devbench.py --t 500 --reps 5 --variants tma_packed:qr2 --tag $tag 2>&1 | grep variant
+  POSEKF_LIB=$so timeout 300 python tools/devbench.py --t 500 --reps 5 --sustain ${SUSTAIN:-0} --variants tma_packed:qr2 --tag $tag 2>&1 | grep variant
 done | tee gpurun_out/${TAG}_variants.jsonl
