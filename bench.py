@@ -71,10 +71,15 @@ def parse():
 
 
 def kernel_source_sha() -> str:
-    """Hash of the device sources: profiles are stamped with it, and a profile taken from other sources is not quoted."""
+    """Hash of the device sources (comments and white space stripped): profiles are stamped with it, and a profile taken
+    from other sources is not quoted."""
+    import re
     h = hashlib.sha256()
     for f in ("ekf_math.cuh", "device_util.cuh", "replay_kernels.cuh"):
-        h.update(open(os.path.join(ROOT, "poseestimationkf_b200", "csrc", f), "rb").read())
+        src = open(os.path.join(ROOT, "poseestimationkf_b200", "csrc", f), encoding="utf-8").read()
+        src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+        src = re.sub(r"//[^\n]*", "", src)
+        h.update(re.sub(r"\s+", "", src).encode())
     return h.hexdigest()[:16]
 
 

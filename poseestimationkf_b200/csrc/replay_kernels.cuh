@@ -253,8 +253,10 @@ __global__ void __launch_bounds__(kThreads, ALGO == WAHBA_JACOBI ? 4 : ((COMP &&
 // ---------------------------------------------------------------------------------------------
 // Replay, TMA staging, PACKED: each thread advances TWO filters in the lanes of f32x2 values, so
 // every FP32 operation of the step is one FFMA2 / FMUL2 / FADD2.  Same tiles, same barriers and
-// the same arithmetic per filter as replay_tma_kernel (results are bit-identical); half the
-// threads.  ALGO is WAHBA_QR2 or WAHBA_PRECOMPUTED (the Jacobi variant uses the scalar kernel).
+// the same arithmetic per filter as replay_tma_kernel (results are bit-identical); kThreads2 = 128 threads own a
+// tile of 256 filters, 3 CTAs (12 warps) per SM.  A complete tile whose samples all have |a_z| <= 1 (and a constant
+// dt) runs as ONE basic block of kTma2Steps steps.  ALGO is WAHBA_QR2 or WAHBA_PRECOMPUTED (the Jacobi variant uses
+// the scalar kernel).
 // ---------------------------------------------------------------------------------------------
 struct __align__(128) Tma2Smem {
   float tile[kTma2Stages][kTma2Steps][kChannels][kTile2];
@@ -270,8 +272,8 @@ struct FilterRegs2 {
   Vec3<f32x2> la, lm;
 };
 
+// (the precise variant with per-step outputs needs ~190 registers: 8 warps per SM instead of 12)
 template <int ALGO, bool LPF, bool AUX, bool COMP>
-// (the precise variant with per-step outputs needs ~184 registers: 8 warps per SM instead of 12)
 __global__ void __launch_bounds__(kThreads2, (AUX && COMP) ? ((256 / kThreads2) < PKF_MIN_CTAS2 ? (256 / kThreads2) : PKF_MIN_CTAS2) : PKF_MIN_CTAS2)
     replay_tma2_kernel(const ReplayParams p, const __grid_constant__ CUtensorMap tmap) {
   extern __shared__ __align__(128) unsigned char smem_raw[];

@@ -4,11 +4,11 @@ committed under profiles/ (the .ncu-rep itself stays in gpurun_out/, which is sc
 """
 import argparse
 import csv
-import hashlib
 import io
 import json
 import os
 import subprocess
+import sys
 
 ap = argparse.ArgumentParser()
 ap.add_argument("rep")
@@ -54,14 +54,13 @@ inst = get("smsp__inst_executed.sum")
 stalls = {h.replace("smsp__average_warps_issue_stalled_", "").replace("_per_issue_active.ratio", ""): float(vals[i])
           for i, h in enumerate(hdr) if "issue_stalled" in h and h.endswith("per_issue_active.ratio")}
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-_h = hashlib.sha256()
-for _f in ("ekf_math.cuh", "device_util.cuh", "replay_kernels.cuh"):      # same recipe as bench.py kernel_source_sha()
-    _h.update(open(os.path.join(ROOT, "poseestimationkf_b200", "csrc", _f), "rb").read())
+sys.path.insert(0, ROOT)
+import bench      # noqa: E402  (one recipe for the source stamp: bench.kernel_source_sha)
 summary = {
     "report": a.rep,
     # stamp: bench.py quotes this capture's DRAM traffic only while the device sources still hash to this value
     # (run this script before touching the sources the capture was taken from)
-    "kernel_source_sha": _h.hexdigest()[:16],
+    "kernel_source_sha": bench.kernel_source_sha(),
     "kernel": vals[col["Kernel Name"]] if "Kernel Name" in col else None,
     "workload": {"filters": a.filters, "timesteps": a.timesteps, "filter_steps": steps},
     "duration_ms_under_ncu": dur_ms,
